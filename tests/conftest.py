@@ -1,0 +1,59 @@
+"""Shared test plumbing.
+
+`-m "not gpu"` : oracle vs golden vectors, host logic, C-ABI symbol checks (no GPU needed).
+`-m gpu`       : parity tests proper -- CUDA path (through the C ABI) vs the oracle.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG_DIR = os.path.join(ROOT, "monte-carlo-portfolio_b200")
+for p in (ROOT, PKG_DIR):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "needs_reference: needs /root/reference (dev container only)")
+
+
+def pytest_collection_modifyitems(config, items):
+    have_ref = os.path.isfile("/root/reference/app.py")
+    skip_ref = pytest.mark.skip(reason="/root/reference not present on this box")
+    for item in items:
+        if "needs_reference" in item.keywords and not have_ref:
+            item.add_marker(skip_ref)
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def c1():
+    return load_golden("c1_btc_eth.npz")
+
+
+@pytest.fixture(scope="session")
+def c2():
+    return load_golden("c2_14assets.npz")
+
+
+@pytest.fixture(scope="session")
+def synth16():
+    """C3's synthetic 16-asset mu / Sigma."""
+    return synthetic_inputs(16)
+
+
+def synthetic_inputs(n, seed=0):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((n, n))
+    sigma = A @ A.T / n * 0.2 + 1e-6 * np.eye(n)
+    mu = rng.uniform(0.05, 0.60, n)
+    return mu, sigma
