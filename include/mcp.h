@@ -1,0 +1,224 @@
+/*
+ * mcp.h -- C ABI of libmcp.so: the B200 (sm_100a) Monte Carlo portfolio hot path.
+ *
+ * The reference (mohammadmarghzari/monte-carlo-portfolio, app.py) has no FFI or plugin
+ * boundary: the path is inline script code plus one function-shaped twin.  Each entry
+ * point below names the reference lines it replaces; the Python host
+ * (monte-carlo-portfolio_b200/mcportfolio) binds exactly these symbols with ctypes and
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: opaque handle, POD structs, pointers + sizes; no C++ / torch types.
+ *   - every call returns MCP_OK (0) or a negative error class and never throws or exits;
+ *     mcp_last_error(handle) returns the message of the last failure on that handle.
+ *   - ownership: the caller allocates and frees every input / output buffer; the library
+ *     owns only handle-internal scratch.  `space` says whether array arguments are host
+ *     pointers (the library stages them through pinned buffers and copies inside the
+ *     call) or device pointers on the handle's device (no copies).
+ *   - threading: one handle per device; a handle is not re-entrant.  Work is ordered on
+ *     the handle's stream (mcp_set_stream) and every call returns after its results are
+ *     complete (synchronous from the caller's view).
+ *   - mu / Sigma / bounds / selection records always cross the boundary as host FP64,
+ *     exactly the values the reference holds in `mean_returns` / `cov_matrix`
+ *     (app.py:679-680); `dtype` selects the arithmetic and array element type on device.
+ */
+#ifndef MCP_H
+#define MCP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCP_ABI_VERSION 1
+
+#define MCP_OK               0
+#define MCP_ERR_INVALID     (-1)  /* bad argument / unsupported shape          */
+#define MCP_ERR_CUDA        (-2)  /* CUDA runtime failure (message has detail) */
+#define MCP_ERR_NUMERIC     (-3)  /* Sigma not positive definite (Cholesky)    */
+#define MCP_ERR_NOMEM       (-4)
+
+#define MCP_F32 0
+#define MCP_F64 1
+
+#define MCP_HOST   0
+#define MCP_DEVICE 1
+
+#define MCP_NO_INDEX UINT64_MAX
+#define MCP_MAX_ALPHAS 8
+
+typedef struct mcp_context* mcp_handle;
+
+/* ---- lifecycle ------------------------------------------------------------------- */
+int         mcp_abi_version(void);
+int         mcp_create(int device, mcp_handle* out);
+int         mcp_destroy(mcp_handle h);
+const char* mcp_last_error(mcp_handle h);            /* h == NULL: last mcp_create failure */
+int         mcp_set_stream(mcp_handle h, void* cuda_stream);   /* NULL: handle-owned stream */
+int         mcp_synchronize(mcp_handle h);
+/* pinned host memory for the HOST-space fast path (plain malloc'ed buffers also work) */
+int         mcp_host_alloc(size_t bytes, void** out);
+int         mcp_host_free(void* p);
+
+typedef struct {
+    int32_t sm_count;
+    int32_t cc_major, cc_minor;
+    int32_t max_smem_per_block;
+    uint64_t total_mem;
+    char    name[64];
+} mcp_device_info_t;
+int mcp_device_info(mcp_handle h, mcp_device_info_t* out);
+
+/* kernels launched by this handle since creation, and device time (CUDA events on the
+ * handle's stream) of the dominant kernel(s) of the most recent call                    */
+uint64_t mcp_launch_count(mcp_handle h);
+double   mcp_last_kernel_ms(mcp_handle h);
+
+/* ---- portfolio sweep ---------------------------------------------------------------
+ * Replaces the sampling + evaluation loop app.py:699-717, the array materialisation
+ * 719-722 and the selection 672/738/747 (twin: efficient_frontier, app.py:265-284).     */
+typedef struct {
+    int32_t  n_assets;          /* N >= 1                                                  */
+    int32_t  dtype;             /* MCP_F32 | MCP_F64                                       */
+    uint64_t n_portfolios;      /* P: units evaluated by this call (this rank's shard)     */
+    uint64_t first_index;       /* global index of unit 0 (Philox counter, reported idx)   */
+    uint64_t seed;              /* Philox key                                              */
+    double   risk_free;         /* subtracted raw, app.py:711 (the app passes 3.0)         */
+    double   risk_target;       /* nearest-risk pick target (README.md:4: 0.30)            */
+    const double* min_weights;  /* host, N values, or NULL = no lower bounds (app.py:703)  */
+    const double* max_weights;  /* host, N values, or NULL                                 */
+    int32_t  max_tries;         /* rejection tries per portfolio (app.py:701: 100)         */
+    int32_t  keep_last;         /* 1: keep the last draw on exhaustion (app.py:277)        */
+    int32_t  space;             /* MCP_HOST | MCP_DEVICE for weights_in and output arrays  */
+    int32_t  reserved;
+    const void*   weights_in;      /* supplied-weights mode: [P, N] dtype; NULL = Philox   */
+    const double* weights_recheck; /* optional FP64 copy of weights_in (same space) used to
+                                      re-rank FP32 near-ties in FP64; NULL = off           */
+    /* frontier envelope (replaces the scatter app.py:726-736 at scale); 0 bins = off      */
+    int32_t  n_bins;
+    int32_t  reserved2;
+    double   risk_lo, risk_hi;
+} mcp_portfolio_params;
+
+typedef struct {
+    uint64_t index;             /* global index, MCP_NO_INDEX if nothing was accepted      */
+    double   key;               /* Sharpe (max-Sharpe pick) or |risk - target| (risk pick) */
+    double   ret, risk, sharpe;
+    double*  weights;           /* host, N doubles, caller-allocated; may be NULL          */
+} mcp_selection;
+
+typedef struct {
+    /* optional arrays in params.space, element type params.dtype; NULL = no write-back.
+     * Rows of skipped portfolios (app.py:706-707) hold NaN metrics and accepted = 0.      */
+    void*    weights;           /* [P, N]  all_weights  (app.py:721)                       */
+    void*    returns;           /* [P]     all_returns  (app.py:720)                       */
+    void*    risks;             /* [P]     all_risks    (app.py:719)                       */
+    void*    sharpes;           /* [P]     all_metrics  (app.py:722, metric = sharpe)      */
+    uint8_t* accepted;          /* [P]                                                      */
+    /* envelope outputs (host), n_bins entries each, when params.n_bins > 0                */
+    double*   bin_best_return;
+    uint64_t* bin_best_index;
+    /* results */
+    uint64_t n_accepted;
+    double   risk_min, risk_max;   /* over accepted portfolios                              */
+    mcp_selection max_sharpe;      /* np.argmax(sharpe), first occurrence (app.py:672)      */
+    mcp_selection target_risk;     /* argmin |risk - target|, first occurrence              */
+    double   kernel_ms;            /* device time of the sweep kernel(s)                    */
+} mcp_portfolio_out;
+
+int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* params,
+                   const double* mu_host, const double* sigma_host,
+                   mcp_portfolio_out* out);
+
+/* ---- correlated-path simulator -------------------------------------------------------
+ * Not in the reference.  Spec: L = chol(Sigma); per step
+ * r = mu dt + sqrt(dt) L z; V *= (1 + r) per asset (app.py:253 compounding);
+ * terminal[m] = w . V_T - 1.                                                            */
+typedef struct {
+    int32_t  n_assets;
+    int32_t  dtype;
+    uint64_t n_paths;
+    uint64_t first_index;
+    uint64_t seed;
+    int32_t  n_steps;
+    int32_t  space;             /* of normals_in and terminal_out                          */
+    double   dt;
+    const void* normals_in;     /* supplied-normals mode: [M, S, N] dtype; NULL = Philox   */
+} mcp_path_params;
+
+int mcp_paths(mcp_handle h, const mcp_path_params* params,
+              const double* mu_host, const double* sigma_host, const double* weights_host,
+              void* terminal_out, double* kernel_ms);
+
+/* ---- VaR / CVaR ------------------------------------------------------------------------
+ * app.py:258-263 conventions: VaR = np.percentile(x, (1-alpha)*100) (linear), CVaR =
+ * mean(x[x <= VaR]) (VaR if empty), on exact order statistics (radix select).
+ * `allreduce` (may be NULL) is called between radix passes with a DEVICE buffer of
+ * `count` uint64 (kind 0) or double (kind 1) values that must be summed in place across
+ * ranks; `n_total` is the global element count (= n when allreduce is NULL).             */
+typedef int (*mcp_allreduce_fn)(void* device_buffer, size_t count, int kind, void* user);
+
+int mcp_quantiles(mcp_handle h, const void* values, int space, int dtype, uint64_t n,
+                  uint64_t n_total, const double* alphas, int n_alphas,
+                  double* var_out, double* cvar_out,
+                  mcp_allreduce_fn allreduce, void* user);
+
+/* Host-side state machine of the distributed exact radix select that mcp_quantiles runs
+ * internally (no CUDA calls; usable for CPU tests of the multi-rank merge).  Per pass: every
+ * rank histograms the next `mcp_select_pass_bits` key bits of its local values for each slot
+ * prefix, the histograms are summed across ranks, and mcp_select_advance consumes the sum.  */
+#define MCP_MAX_TARGETS 16
+typedef struct {
+    int32_t  key_bits;                       /* 32 (float) | 64 (double)                     */
+    int32_t  bits_done;
+    int32_t  n_targets;
+    int32_t  n_slots;                        /* distinct prefixes in the coming pass         */
+    uint64_t rank[MCP_MAX_TARGETS];          /* remaining 0-based rank inside the prefix     */
+    uint64_t prefix[MCP_MAX_TARGETS];        /* decided high key bits, right-aligned         */
+    int32_t  slot_of[MCP_MAX_TARGETS];
+    uint64_t slot_prefix[MCP_MAX_TARGETS];
+} mcp_select_state;
+
+int mcp_select_init(mcp_select_state* s, int key_bits, const uint64_t* ranks, int n_targets);
+int mcp_select_pass_bits(const mcp_select_state* s);          /* 0 when finished            */
+int mcp_select_advance(mcp_select_state* s, const uint64_t* hist /* [n_slots][1 << bits] */);
+/* one local radix pass on the device: hist_dev[n_slots << bits] (uint64) is overwritten     */
+int mcp_select_hist(mcp_handle h, const void* values_dev, int dtype, uint64_t n,
+                    const mcp_select_state* s, uint64_t* hist_dev);
+/* order-preserving key <-> value (bit patterns), so callers can turn final prefixes into values */
+double mcp_key_to_value(uint64_t key, int dtype);
+
+/* ---- per-portfolio historical VaR / CVaR (app.py:710-713) and the 'VaR' / 'CVaR' method
+ * selections (app.py:673-674, 717, 747)                                                  */
+typedef struct {
+    int32_t  n_assets;
+    int32_t  n_periods;         /* T rows of the returns matrix                            */
+    int32_t  dtype;
+    int32_t  space;
+    uint64_t n_portfolios;
+    uint64_t first_index;
+    double   alpha;             /* 0.95 (app.py:684)                                       */
+    const void* weights_in;     /* [P, N] dtype                                            */
+} mcp_hist_params;
+
+typedef struct {
+    void*    var;               /* [P] dtype, optional                                     */
+    void*    cvar;              /* [P] dtype, optional                                     */
+    uint64_t best_var_index;    /* argmin(-var)  = first index of the largest VaR          */
+    uint64_t best_cvar_index;   /* argmin(-cvar)                                           */
+    double   best_var, best_cvar;
+    double   kernel_ms;
+} mcp_hist_out;
+
+int mcp_historical_var(mcp_handle h, const mcp_hist_params* params,
+                       const double* returns_matrix_host /* [T, N] */, mcp_hist_out* out);
+
+/* ---- microbenchmarks used as roofline denominators (bench.py) ------------------------- */
+int mcp_measure_fma_peak(mcp_handle h, int dtype, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCP_H */

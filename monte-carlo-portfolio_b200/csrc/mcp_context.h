@@ -1,0 +1,66 @@
+// Host-side context shared by the C-ABI entry points (not part of the public ABI).
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "../../include/mcp.h"
+
+struct mcp_scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct mcp_context {
+    int device = 0;
+    cudaDeviceProp prop{};
+    cudaStream_t own_stream = nullptr;   // created by mcp_create
+    cudaStream_t stream = nullptr;       // current stream (own_stream or the caller's)
+    cudaStream_t side_stream[2] = {nullptr, nullptr};   // HOST-space chunk pipeline
+    cudaEvent_t ev[8] = {};
+    std::string err;
+    uint64_t launches = 0;
+    double last_ms = 0.0;
+    // device scratch (grow-only): [0] candidates/records, [1..2] pipeline slot inputs,
+    // [3..4] pipeline slot outputs, [5] quantile histograms, [6] misc
+    mcp_scratch dev[8];
+    mcp_scratch pinned[4];
+};
+
+int mcp_fail(mcp_context* h, int code, const char* fmt, ...);
+int mcp_dev_reserve(mcp_context* h, int slot, size_t bytes, void** out);
+int mcp_pinned_reserve(mcp_context* h, int slot, size_t bytes, void** out);
+
+#define MCP_CUDA(h, call)                                                                  \
+    do {                                                                                   \
+        cudaError_t _e = (call);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return mcp_fail((h), MCP_ERR_CUDA, "%s failed: %s (%s:%d)", #call,             \
+                            cudaGetErrorString(_e), __FILE__, __LINE__);                   \
+    } while (0)
+
+#define MCP_CHECK(expr)                                                                    \
+    do {                                                                                   \
+        int _rc = (expr);                                                                  \
+        if (_rc != MCP_OK) return _rc;                                                     \
+    } while (0)
+
+#define MCP_REQUIRE(h, cond, ...)                                                          \
+    do {                                                                                   \
+        if (!(cond)) return mcp_fail((h), MCP_ERR_INVALID, __VA_ARGS__);                   \
+    } while (0)
+
+struct mcp_device_guard {
+    int prev = -1;
+    explicit mcp_device_guard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~mcp_device_guard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};

@@ -1,0 +1,123 @@
+// Device-side building blocks shared by the sm_100a kernels: Philox4x32-10, the uniform ->
+// exponential / normal transforms, MUFU-level math wrappers and (key, index) reductions.
+// The generator spec (counter layout, bit -> float construction) is restated for the tests in
+// oracle/philox_np.py; keep the two in sync.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mcp {
+
+constexpr uint32_t PHILOX_M0 = 0xD2511F53u;
+constexpr uint32_t PHILOX_M1 = 0xCD9E8D57u;
+constexpr uint32_t PHILOX_W0 = 0x9E3779B9u;
+constexpr uint32_t PHILOX_W1 = 0xBB67AE85u;
+constexpr uint32_t STREAM_WEIGHTS = 1u << 24;
+constexpr uint32_t STREAM_NORMALS = 2u << 24;
+
+// Philox4x32-10 (Salmon et al., SC'11).  The key schedule k + r*W is uniform across the
+// grid (seed is a kernel parameter), so it lives in uniform registers; each round costs two
+// IMAD.WIDE.U32 and two LOP3 per thread.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
+        const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += PHILOX_W0;
+        k1 += PHILOX_W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// ---- math wrappers ---------------------------------------------------------------------
+// FP32 uses the MUFU approximations directly (lg2 / rcp / rsqrt / sin / cos: <= 2 ulp-class
+// error, far inside the 1e-4 parity tolerance); FP64 uses the IEEE library routines.
+template <typename T> struct Math;
+
+template <> struct Math<float> {
+    static __device__ __forceinline__ float lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+    static __device__ __forceinline__ float rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+    static __device__ __forceinline__ float rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+    static __device__ __forceinline__ float sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+    static __device__ __forceinline__ float sinf_(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+    static __device__ __forceinline__ float cosf_(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+    static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
+    static __device__ __forceinline__ float nan() { return __int_as_float(0x7fc00000); }
+    static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+    // U in (0, 1] with 23 random bits: float in [1, 2) built with one LOP3, then 2 - f.
+    static __device__ __forceinline__ float unit_open0(uint32_t x) { return 2.0f - __uint_as_float((x & 0x007fffffu) | 0x3f800000u); }
+    // fraction in [0, 1) with 23 random bits
+    static __device__ __forceinline__ float unit_frac(uint32_t x) { return __uint_as_float((x & 0x007fffffu) | 0x3f800000u) - 1.0f; }
+};
+
+template <> struct Math<double> {
+    static __device__ __forceinline__ double lg2(double x) { return ::log2(x); }
+    static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+    static __device__ __forceinline__ double rsqrt(double x) { return 1.0 / ::sqrt(x); }
+    static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+    static __device__ __forceinline__ double sinf_(double x) { return ::sin(x); }
+    static __device__ __forceinline__ double cosf_(double x) { return ::cos(x); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
+    static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
+    static __device__ __forceinline__ double nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+    static __device__ __forceinline__ double unit_open0(uint32_t x) { return 1.0 - (double)x * 0x1p-32; }
+    static __device__ __forceinline__ double unit_frac(uint32_t x) { return (double)x * 0x1p-32; }
+};
+
+// ---- (key, index) argmax with first-occurrence tie-break ---------------------------------
+// `better(a, ia, b, ib)`: does candidate a beat b?  Larger key wins; equal keys -> lower index.
+template <typename T>
+struct Cand {
+    T key;
+    uint64_t idx;
+};
+
+template <typename T>
+__device__ __forceinline__ bool cand_better(T ka, uint64_t ia, T kb, uint64_t ib) {
+    return (ka > kb) || (ka == kb && ia < ib);
+}
+
+template <typename T> __device__ __forceinline__ T shfl_xor(T v, int m);
+template <> __device__ __forceinline__ float shfl_xor<float>(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <> __device__ __forceinline__ double shfl_xor<double>(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <> __device__ __forceinline__ uint64_t shfl_xor<uint64_t>(uint64_t v, int m) { return __shfl_xor_sync(0xffffffffu, (unsigned long long)v, m); }
+
+template <typename T>
+__device__ __forceinline__ void warp_argmax(T& key, uint64_t& idx) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        const T ok = shfl_xor<T>(key, m);
+        const uint64_t oi = shfl_xor<uint64_t>(idx, m);
+        if (cand_better<T>(ok, oi, key, idx)) { key = ok; idx = oi; }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_min(T v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) { const T o = shfl_xor<T>(v, m); v = o < v ? o : v; }
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) { const T o = shfl_xor<T>(v, m); v = o > v ? o : v; }
+    return v;
+}
+
+// order-preserving float -> unsigned key (ascending), and back
+__device__ __host__ __forceinline__ uint32_t f32_to_key(uint32_t b) { return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u); }
+__device__ __host__ __forceinline__ uint32_t key_to_f32(uint32_t k) { return k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu); }
+__device__ __host__ __forceinline__ uint64_t f64_to_key(uint64_t b) { return b ^ ((b >> 63) ? 0xffffffffffffffffull : 0x8000000000000000ull); }
+__device__ __host__ __forceinline__ uint64_t key_to_f64(uint64_t k) { return k ^ ((k >> 63) ? 0x8000000000000000ull : 0xffffffffffffffffull); }
+
+}  // namespace mcp

@@ -1,0 +1,301 @@
+// mcp_portfolios: host orchestration of the fused portfolio sweep (C ABI entry point).
+//
+// DEVICE space: one persistent launch over the whole index range on the handle's stream.
+// HOST space:   the range is cut into chunks that flow through two slots (stream + device
+//               buffers each): H2D of chunk c+1 overlaps the sweep of chunk c and the D2H of
+//               chunk c-1, so the end-to-end rate is set by the slower of PCIe and the kernel.
+// Selection: per-CTA candidates -> pf_reduce_cands (one CTA) -> replay kernel that re-evaluates
+// the winners with the sweep's own arithmetic -> one small D2H of the two records.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "mcp_device.cuh"
+#include "mcp_portfolio.h"
+
+namespace mcp {
+
+__device__ __forceinline__ void cand_merge(PfCand& b, const PfCand& o) {
+    if (cand_better<double>(o.key_s, o.idx_s, b.key_s, b.idx_s)) { b.key_s = o.key_s; b.idx_s = o.idx_s; }
+    if (cand_better<double>(o.key_d, o.idx_d, b.key_d, b.idx_d)) { b.key_d = o.key_d; b.idx_d = o.idx_d; }
+    b.rmin = o.rmin < b.rmin ? o.rmin : b.rmin;
+    b.rmax = o.rmax > b.rmax ? o.rmax : b.rmax;
+}
+
+// Merges n per-CTA candidates (and, if accumulate, the running record) into *acc.
+__global__ void __launch_bounds__(256) pf_reduce_cands(const PfCand* __restrict__ cands, int n, PfCand* acc, int accumulate) {
+    __shared__ PfCand sm[256];
+    const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
+    PfCand b{ninf, MCP_NO_INDEX, ninf, MCP_NO_INDEX, -ninf, ninf};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) cand_merge(b, cands[i]);
+    sm[threadIdx.x] = b;
+    __syncthreads();
+    for (int s = 128; s >= 1; s >>= 1) {
+        if ((int)threadIdx.x < s) cand_merge(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        PfCand r = sm[0];
+        if (accumulate) cand_merge(r, *acc);
+        *acc = r;
+    }
+}
+
+static const int kSmallNP[] = {4, 8, 16, 24, 32};
+
+template <typename T>
+static int small_dispatch(mcp_context* h, PfJob& job, const PfReplay* rp) {
+    int np = 0;
+    for (int c : kSmallNP) if (job.n <= c) { np = c; break; }
+    switch (np) {
+#define MCP_CASE(NP) case NP: return rp ? pf_small_replay_t<T, NP>(h, job, *rp) : pf_small_launch_t<T, NP>(h, job);
+        MCP_CASE(4) MCP_CASE(8) MCP_CASE(16) MCP_CASE(24) MCP_CASE(32)
+#undef MCP_CASE
+    }
+    return mcp_fail(h, MCP_ERR_INVALID, "no register kernel for n_assets=%d", job.n);
+}
+
+int pf_small_launch(mcp_context* h, PfJob& job) {
+    return job.dtype == MCP_F64 ? small_dispatch<double>(h, job, nullptr) : small_dispatch<float>(h, job, nullptr);
+}
+int pf_small_replay(mcp_context* h, const PfJob& job, const PfReplay& rp) {
+    PfJob j = job;
+    return job.dtype == MCP_F64 ? small_dispatch<double>(h, j, &rp) : small_dispatch<float>(h, j, &rp);
+}
+
+static int pf_launch(mcp_context* h, PfJob& job) {
+    return job.n <= PF_SMALL_MAX_N ? pf_small_launch(h, job) : pf_large_launch(h, job);
+}
+static int pf_replay(mcp_context* h, const PfJob& job, const PfReplay& rp) {
+    return job.n <= PF_SMALL_MAX_N ? pf_small_replay(h, job, rp) : pf_large_replay(h, job, rp);
+}
+
+}  // namespace mcp
+
+using namespace mcp;
+
+static void fill_selection(mcp_selection& sel, const double* rec, int n) {
+    uint64_t idx;
+    memcpy(&idx, &rec[0], 8);
+    sel.index = idx;
+    sel.key = rec[1];
+    sel.ret = rec[2];
+    sel.risk = rec[3];
+    sel.sharpe = rec[4];
+    if (sel.weights) memcpy(sel.weights, rec + PF_REC_HEADER, sizeof(double) * n);
+}
+
+extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const double* mu, const double* sigma,
+                              mcp_portfolio_out* out) {
+    if (!h) return MCP_ERR_INVALID;
+    MCP_REQUIRE(h, p && mu && sigma && out, "mcp_portfolios: NULL argument");
+    MCP_REQUIRE(h, p->n_assets >= 1 && p->n_assets <= 4096, "mcp_portfolios: n_assets=%d out of range [1, 4096]", p->n_assets);
+    MCP_REQUIRE(h, p->dtype == MCP_F32 || p->dtype == MCP_F64, "mcp_portfolios: bad dtype %d", p->dtype);
+    MCP_REQUIRE(h, p->space == MCP_HOST || p->space == MCP_DEVICE, "mcp_portfolios: bad space %d", p->space);
+    MCP_REQUIRE(h, p->n_portfolios <= (1ull << 40), "mcp_portfolios: n_portfolios=%llu exceeds 2^40 per call; shard the range",
+                (unsigned long long)p->n_portfolios);
+    MCP_REQUIRE(h, p->max_tries >= 1, "mcp_portfolios: max_tries must be >= 1");
+    const int N = p->n_assets;
+    for (int i = 0; i < N; ++i) {
+        MCP_REQUIRE(h, std::isfinite(mu[i]), "mcp_portfolios: mean_returns[%d] is not finite", i);
+        for (int j = 0; j < N; ++j) MCP_REQUIRE(h, std::isfinite(sigma[(size_t)i * N + j]), "mcp_portfolios: cov_matrix[%d,%d] is not finite", i, j);
+    }
+    mcp_device_guard guard(h->device);
+    const size_t es = p->dtype == MCP_F64 ? 8 : 4;
+    const uint64_t P = p->n_portfolios;
+    const bool supplied = p->weights_in != nullptr;
+
+    out->n_accepted = 0;
+    out->kernel_ms = 0;
+    out->risk_min = out->risk_max = NAN;
+    for (mcp_selection* s : {&out->max_sharpe, &out->target_risk}) {
+        s->index = MCP_NO_INDEX;
+        s->key = s->ret = s->risk = s->sharpe = NAN;
+    }
+    if (P == 0) return MCP_OK;          // empty arrays, no selection (app.py:719-722 on empty lists)
+
+    // ---- scratch layout (device slot 0) ----
+    const int max_blocks = h->prop.multiProcessorCount * 16;
+    const size_t rec_doubles = (size_t)2 * (PF_REC_HEADER + N);
+    size_t off_cands = 0;
+    size_t off_run = off_cands + sizeof(PfCand) * (size_t)max_blocks * 2;      // two slots of CTA candidates
+    size_t off_acc = off_run + sizeof(PfCand) * 4;                              // running[0..1], final
+    size_t off_rec = off_acc + 64;
+    size_t off_rows = off_rec + rec_doubles * sizeof(double);
+    size_t total = off_rows + (size_t)2 * N * 8 + 64;
+    unsigned char* base = nullptr;
+    MCP_CHECK(mcp_dev_reserve(h, 0, total, (void**)&base));
+    PfCand* cands = (PfCand*)(base + off_cands);
+    PfCand* running = (PfCand*)(base + off_run);
+    unsigned long long* d_acc = (unsigned long long*)(base + off_acc);
+    double* d_rec = (double*)(base + off_rec);
+    void* d_rows = base + off_rows;
+
+    PfJob job;
+    job.n = N;
+    job.dtype = p->dtype;
+    job.max_tries = p->max_tries;
+    job.keep_last = p->keep_last;
+    job.bounds = p->min_weights != nullptr || p->max_weights != nullptr;
+    job.seed = p->seed;
+    job.rf = p->risk_free;
+    job.target = p->risk_target;
+    job.sigma = sigma;
+    job.mu = mu;
+    job.lo = p->min_weights;
+    job.hi = p->max_weights;
+    job.max_blocks = max_blocks;
+    job.n_accepted = d_acc;
+
+    cudaStream_t st = h->stream;
+    MCP_CUDA(h, cudaMemsetAsync(d_acc, 0, 8, st));
+    PfCand* final_cand = running + 2;
+    double kernel_ms = 0;
+
+    if (p->space == MCP_DEVICE) {
+        job.first = p->first_index;
+        job.P = P;
+        job.w_in = p->weights_in;
+        job.w_out = out->weights;
+        job.ret_out = out->returns;
+        job.risk_out = out->risks;
+        job.sharpe_out = out->sharpes;
+        job.acc_out = out->accepted;
+        job.cands = cands;
+        job.stream = st;
+        MCP_CUDA(h, cudaEventRecord(h->ev[0], st));
+        MCP_CHECK(pf_launch(h, job));
+        MCP_CUDA(h, cudaEventRecord(h->ev[1], st));
+        pf_reduce_cands<<<1, 256, 0, st>>>(cands, job.blocks_used, final_cand, 0);
+        MCP_CUDA(h, cudaGetLastError());
+        h->launches++;
+    } else {
+        // ---- HOST space: two-slot chunk pipeline ----
+        MCP_CUDA(h, cudaStreamSynchronize(st));           // the memset above must precede the side streams
+        const bool want_w = out->weights != nullptr;
+        const size_t in_row = supplied ? (size_t)N * es : 0;
+        const size_t out_row = (want_w ? (size_t)N * es : 0) + (out->returns ? es : 0) + (out->risks ? es : 0) +
+                               (out->sharpes ? es : 0) + (out->accepted ? 1 : 0);
+        uint64_t chunk = P;
+        const size_t budget = (size_t)96 << 20;            // bytes per slot and direction
+        if (in_row) chunk = std::min<uint64_t>(chunk, std::max<size_t>(budget / in_row, 1024));
+        if (out_row) chunk = std::min<uint64_t>(chunk, std::max<size_t>(budget / out_row, 1024));
+        chunk = (chunk + PF_BLOCK - 1) / PF_BLOCK * PF_BLOCK;
+        if (!in_row && !out_row) chunk = P;
+        const uint64_t n_chunks = (P + chunk - 1) / chunk;
+        bool used[2] = {false, false};
+        bool timed[2] = {false, false};
+        for (uint64_t c = 0; c < n_chunks; ++c) {
+            const int s = (int)(c & 1);
+            cudaStream_t ss = n_chunks == 1 ? st : h->side_stream[s];
+            const uint64_t r0 = c * chunk, rows = std::min<uint64_t>(chunk, P - r0);
+            if (used[s]) {
+                MCP_CUDA(h, cudaStreamSynchronize(ss));
+                if (timed[s]) {
+                    float ms = 0;
+                    MCP_CUDA(h, cudaEventElapsedTime(&ms, h->ev[2 * s], h->ev[2 * s + 1]));
+                    kernel_ms += ms;
+                }
+            }
+            unsigned char* d_in = nullptr;
+            unsigned char* d_out = nullptr;
+            if (in_row) MCP_CHECK(mcp_dev_reserve(h, 1 + s, (size_t)chunk * in_row, (void**)&d_in));
+            if (out_row) MCP_CHECK(mcp_dev_reserve(h, 3 + s, (size_t)chunk * (out_row + 16), (void**)&d_out));
+            if (in_row)
+                MCP_CUDA(h, cudaMemcpyAsync(d_in, (const unsigned char*)p->weights_in + r0 * in_row, rows * in_row,
+                                            cudaMemcpyHostToDevice, ss));
+            // carve the output slot
+            size_t o = 0;
+            auto carve = [&](bool want, size_t bytes_per_row) -> unsigned char* {
+                if (!want) return nullptr;
+                unsigned char* q = d_out + o;
+                o += (chunk * bytes_per_row + 255) / 256 * 256;
+                return q;
+            };
+            unsigned char* dw = carve(want_w, (size_t)N * es);
+            unsigned char* dr = carve(out->returns != nullptr, es);
+            unsigned char* dk = carve(out->risks != nullptr, es);
+            unsigned char* ds = carve(out->sharpes != nullptr, es);
+            unsigned char* da = carve(out->accepted != nullptr, 1);
+            job.first = p->first_index + r0;
+            job.P = rows;
+            job.w_in = d_in;
+            job.w_out = dw;
+            job.ret_out = dr;
+            job.risk_out = dk;
+            job.sharpe_out = ds;
+            job.acc_out = da;
+            job.cands = cands + (size_t)s * max_blocks;
+            job.stream = ss;
+            MCP_CUDA(h, cudaEventRecord(h->ev[2 * s], ss));
+            MCP_CHECK(pf_launch(h, job));
+            MCP_CUDA(h, cudaEventRecord(h->ev[2 * s + 1], ss));
+            timed[s] = true;
+            pf_reduce_cands<<<1, 256, 0, ss>>>(job.cands, job.blocks_used, running + s, used[s] ? 1 : 0);
+            MCP_CUDA(h, cudaGetLastError());
+            h->launches++;
+            if (dw) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->weights + r0 * N * es, dw, rows * N * es, cudaMemcpyDeviceToHost, ss));
+            if (dr) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->returns + r0 * es, dr, rows * es, cudaMemcpyDeviceToHost, ss));
+            if (dk) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->risks + r0 * es, dk, rows * es, cudaMemcpyDeviceToHost, ss));
+            if (ds) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->sharpes + r0 * es, ds, rows * es, cudaMemcpyDeviceToHost, ss));
+            if (da) MCP_CUDA(h, cudaMemcpyAsync(out->accepted + r0, da, rows, cudaMemcpyDeviceToHost, ss));
+            used[s] = true;
+        }
+        for (int s = 0; s < 2; ++s) {
+            if (!used[s]) continue;
+            cudaStream_t ss = n_chunks == 1 ? st : h->side_stream[s];
+            MCP_CUDA(h, cudaStreamSynchronize(ss));
+            if (timed[s]) {
+                float ms = 0;
+                MCP_CUDA(h, cudaEventElapsedTime(&ms, h->ev[2 * s], h->ev[2 * s + 1]));
+                kernel_ms += ms;
+            }
+        }
+        const int n_run = used[1] ? 2 : 1;
+        pf_reduce_cands<<<1, 256, 0, st>>>(running, n_run, final_cand, 0);
+        MCP_CUDA(h, cudaGetLastError());
+        h->launches++;
+    }
+
+    // ---- winners: indices to the host, rows (supplied mode) to scratch, replay, records back ----
+    PfCand fin;
+    unsigned long long n_acc = 0;
+    MCP_CUDA(h, cudaMemcpyAsync(&fin, final_cand, sizeof fin, cudaMemcpyDeviceToHost, st));
+    MCP_CUDA(h, cudaMemcpyAsync(&n_acc, d_acc, 8, cudaMemcpyDeviceToHost, st));
+    MCP_CUDA(h, cudaStreamSynchronize(st));
+    if (p->space == MCP_DEVICE) {
+        float ms = 0;
+        MCP_CUDA(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+        kernel_ms = ms;
+    }
+    out->n_accepted = n_acc;
+    out->kernel_ms = kernel_ms;
+    h->last_ms = kernel_ms;
+    if (n_acc == 0 || fin.idx_s == MCP_NO_INDEX) return MCP_OK;
+    out->risk_min = fin.rmin;
+    out->risk_max = fin.rmax;
+
+    PfReplay rp;
+    rp.n_sel = 2;
+    rp.idx[0] = fin.idx_s;
+    rp.idx[1] = fin.idx_d;
+    rp.rec = d_rec;
+    if (supplied) {
+        for (int k = 0; k < 2; ++k) {
+            const size_t row = (size_t)(rp.idx[k] - p->first_index) * N * es;
+            MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)d_rows + (size_t)k * N * es, (const unsigned char*)p->weights_in + row,
+                                        (size_t)N * es, p->space == MCP_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        }
+        rp.rows = d_rows;
+    }
+    job.first = p->first_index;
+    job.P = P;
+    job.stream = st;
+    MCP_CHECK(pf_replay(h, job, rp));
+    std::vector<double> rec(rec_doubles);
+    MCP_CUDA(h, cudaMemcpyAsync(rec.data(), d_rec, rec_doubles * sizeof(double), cudaMemcpyDeviceToHost, st));
+    MCP_CUDA(h, cudaStreamSynchronize(st));
+    fill_selection(out->max_sharpe, rec.data(), N);
+    fill_selection(out->target_risk, rec.data() + PF_REC_HEADER + N, N);
+    return MCP_OK;
+}

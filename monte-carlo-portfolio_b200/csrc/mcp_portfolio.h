@@ -1,0 +1,72 @@
+// Internal (non-ABI) declarations shared by the portfolio-sweep translation units.
+#pragma once
+#include "mcp_context.h"
+
+namespace mcp {
+
+constexpr int PF_BLOCK = 256;          // threads per CTA of the sweep kernels
+constexpr int PF_SMALL_MAX_N = 32;     // thread-per-portfolio register kernels up to this N
+
+// Per-CTA (and final) selection candidates.  Keys are widened to double so that one
+// reduction kernel serves both arithmetic types (float -> double is exact).
+struct PfCand {
+    double key_s;      // Sharpe
+    uint64_t idx_s;    // global index, MCP_NO_INDEX if none
+    double key_d;      // -|risk - target|
+    uint64_t idx_d;
+    double rmin, rmax; // risk range over accepted portfolios
+};
+
+// Selected-portfolio record written by the replay kernels: rec[0] = index bits,
+// rec[1..4] = key, ret, risk, sharpe, rec[5 .. 5+N) = weights.
+constexpr int PF_REC_HEADER = 5;
+
+// One sweep launch over a contiguous global index range.  All pointers are device pointers.
+struct PfJob {
+    int n = 0;
+    int dtype = MCP_F32;
+    int max_tries = 100;
+    int keep_last = 0;
+    bool bounds = false;
+    uint64_t seed = 0, first = 0, P = 0;
+    double rf = 0, target = 0.30;
+    const double* sigma = nullptr;     // host N x N
+    const double* mu = nullptr;        // host N
+    const double* lo = nullptr;        // host N or null
+    const double* hi = nullptr;
+    const void* w_in = nullptr;
+    void* w_out = nullptr;
+    void* ret_out = nullptr;
+    void* risk_out = nullptr;
+    void* sharpe_out = nullptr;
+    uint8_t* acc_out = nullptr;
+    PfCand* cands = nullptr;           // [max_blocks] per-CTA candidates
+    int max_blocks = 0;
+    unsigned long long* n_accepted = nullptr;
+    // envelope (packed (return key << 32 | ~local index) per bin, FP32) -- see mcp_envelope
+    int n_bins = 0;
+    double env_lo = 0, env_hi = 0;
+    unsigned long long* env_bins = nullptr;
+    cudaStream_t stream = nullptr;
+    int blocks_used = 0;               // out: grid size of the launch
+};
+
+// Replay of selected portfolios: regenerates (RNG mode) or re-reads (supplied mode, `rows`
+// = device pointer to n_sel rows of N values) and evaluates them with the sweep's arithmetic.
+struct PfReplay {
+    int n_sel = 0;
+    uint64_t idx[2] = {0, 0};
+    const void* rows = nullptr;
+    double* rec = nullptr;             // device, n_sel * (PF_REC_HEADER + N) doubles
+};
+
+int pf_small_launch(mcp_context* h, PfJob& job);
+int pf_small_replay(mcp_context* h, const PfJob& job, const PfReplay& rp);
+int pf_large_launch(mcp_context* h, PfJob& job);
+int pf_large_replay(mcp_context* h, const PfJob& job, const PfReplay& rp);
+
+// implemented per (type, padded N) in mcp_portfolio_small_inst.cu
+template <typename T, int NP> int pf_small_launch_t(mcp_context* h, PfJob& job);
+template <typename T, int NP> int pf_small_replay_t(mcp_context* h, const PfJob& job, const PfReplay& rp);
+
+}  // namespace mcp

@@ -1,0 +1,346 @@
+// Fused portfolio sweep for N <= 32 assets: one thread per portfolio, everything in registers.
+//
+// Replaces app.py:699-717 (sampling, bounds rejection, return / risk / Sharpe), 719-722
+// (optional write-back) and the argmax at 672/747 plus the nearest-risk pick, in ONE kernel:
+//   * weights are generated in-register from Philox4x32-10 (counter = global portfolio index,
+//     attempt, 4-asset block) as normalised base-2 exponentials (flat Dirichlet, app.py:702);
+//   * Sigma (packed lower triangle, off-diagonals pre-doubled) and mu are kernel parameters,
+//     i.e. they sit in the constant bank and feed the FFMAs as immediate-like operands -- no
+//     shared-memory or global loads in the inner loop, zero HBM traffic without write-back;
+//   * the quadratic form runs on the un-normalised exponentials (q_e = e' S e, r_e = e.mu) and
+//     is scaled once: ret = r_e / s, risk = sqrt(q_e) / s, sharpe = (r_e - rf s) rsqrt(q_e);
+//   * per-thread running (max Sharpe, min |risk - target|) -> warp shuffles -> one candidate
+//     per CTA; a second tiny kernel merges the CTA candidates (first-occurrence tie-break).
+// Supplied-weights mode stages each warp's 32 rows through padded shared memory so global
+// loads / stores are fully coalesced while each thread still owns one row.
+#pragma once
+#include "mcp_device.cuh"
+#include "mcp_portfolio.h"
+
+namespace mcp {
+
+template <typename T, int NP>
+struct SmallArgs {
+    T sig[NP * (NP + 1) / 2];   // row i holds j = 0..i; off-diagonals doubled
+    T mu[NP];
+    T mask[NP];                 // 1 for real assets, 0 for padded ones
+    T lo[NP], hi[NP];
+    T rf, target;
+    int n;                      // real asset count (<= NP); padded assets carry weight 0
+    int max_tries, keep_last;
+    uint32_t k0, k1;            // Philox key = seed
+    uint64_t first, P;
+    const T* w_in;
+    T* w_out;
+    T* ret_out;
+    T* risk_out;
+    T* sharpe_out;
+    uint8_t* acc_out;
+    PfCand* cands;
+    unsigned long long* n_accepted;
+};
+
+// One flat-Dirichlet draw: e[i] = -lg2(U_i), s = sum over the real assets (padded assets keep a
+// draw but are masked out of s, and their Sigma / mu entries are 0, so they never contribute).
+template <typename T, int NP>
+__device__ __forceinline__ void draw_exponentials(const SmallArgs<T, NP>& a, uint32_t c0, uint32_t c1,
+                                                  uint32_t attempt, T (&e)[NP], T& s) {
+    s = (T)0;
+#pragma unroll
+    for (int b = 0; b < NP / 4; ++b) {
+        uint32_t x[4];
+        philox4x32_10(c0, c1, attempt, STREAM_WEIGHTS | (uint32_t)b, a.k0, a.k1, x);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = 4 * b + k;
+            e[i] = -Math<T>::lg2(Math<T>::unit_open0(x[k]));
+            s = Math<T>::fma(e[i], a.mask[i], s);
+        }
+    }
+}
+
+// q = e' Sigma e over the packed, pre-doubled lower triangle; r = e . mu
+template <typename T, int NP>
+__device__ __forceinline__ void quad_and_dot(const SmallArgs<T, NP>& a, const T (&e)[NP], T& q, T& r) {
+    q = (T)0;
+    r = (T)0;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        T t = (T)0;
+#pragma unroll
+        for (int j = 0; j <= i; ++j) t = Math<T>::fma(a.sig[i * (i + 1) / 2 + j], e[j], t);
+        q = Math<T>::fma(e[i], t, q);
+        r = Math<T>::fma(a.mu[i], e[i], r);
+    }
+}
+
+template <typename T, int NP>
+__device__ __forceinline__ bool in_bounds(const SmallArgs<T, NP>& a, const T (&e)[NP], T inv) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const T w = e[i] * inv;
+        ok = ok && ((i >= a.n) || (w >= a.lo[i] && w <= a.hi[i]));
+    }
+    return ok;
+}
+
+// Draw with bounds rejection (app.py:700-707): returns accepted?; e / s hold the last draw.
+template <typename T, int NP, bool BOUNDS>
+__device__ __forceinline__ bool draw_accepted(const SmallArgs<T, NP>& a, uint64_t gidx, T (&e)[NP], T& s) {
+    const uint32_t c0 = (uint32_t)gidx, c1 = (uint32_t)(gidx >> 32);
+    if (!BOUNDS) {
+        draw_exponentials<T, NP>(a, c0, c1, 0u, e, s);
+        return true;
+    }
+    bool ok = false;
+    for (int t = 0; t < a.max_tries && !ok; ++t) {
+        draw_exponentials<T, NP>(a, c0, c1, (uint32_t)t, e, s);
+        ok = in_bounds<T, NP>(a, e, Math<T>::rcp(s));
+    }
+    return ok || (a.keep_last != 0);
+}
+
+// metrics from un-normalised weights (s = their sum; s = 1 for supplied weights)
+template <typename T>
+__device__ __forceinline__ void metrics_from(T q, T r, T s, T rf, bool normalised, T& ret, T& risk, T& sharpe) {
+    if (normalised) {
+        ret = r;
+        risk = Math<T>::sqrt(q);
+        sharpe = risk > (T)0 ? (r - rf) * Math<T>::rcp(risk) : (T)0;
+    } else {
+        const T inv = Math<T>::rcp(s);
+        const T rs = Math<T>::rsqrt(q);
+        ret = r * inv;
+        risk = q * rs * inv;                       // sqrt(q) / s
+        sharpe = q > (T)0 ? (r - rf * s) * rs : (T)0;   // (ret - rf) / risk
+        if (!(q > (T)0)) risk = (T)0;
+    }
+}
+
+template <typename T, int NP, int SRC /*0 Philox, 1 supplied*/, bool BOUNDS>
+__global__ void __launch_bounds__(PF_BLOCK) small_sweep(const __grid_constant__ SmallArgs<T, NP> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int stride = a.n | 1;                                  // odd row stride: conflict-free
+    T* stage = reinterpret_cast<T*>(smem_raw) + (size_t)warp * 32 * stride;
+    const int q32 = 32 / a.n, m32 = 32 % a.n;
+
+    const uint64_t n_tiles = (a.P + PF_BLOCK - 1) / PF_BLOCK;
+    constexpr uint32_t NONE = 0xffffffffu;
+    T best_s = -Math<T>::inf(), best_d = -Math<T>::inf();
+    uint32_t tile_s = NONE, tile_d = NONE;
+    T rmin = Math<T>::inf(), rmax = -Math<T>::inf();
+    uint32_t n_acc = 0;
+
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t warp_row0 = tile * PF_BLOCK + (uint64_t)warp * 32;
+        const uint64_t local = warp_row0 + lane;
+        const bool active = local < a.P;
+        const int rows = warp_row0 >= a.P ? 0 : (int)((a.P - warp_row0) < 32 ? (a.P - warp_row0) : 32);
+
+        T e[NP];
+        T s = (T)1;
+        bool accepted = active;
+        if (SRC == 1) {
+            // coalesced warp load of rows*n contiguous values into padded smem, then row -> registers
+            const T* src = a.w_in + warp_row0 * (uint64_t)a.n;
+            const int total = rows * a.n;
+            int r = lane / a.n, c = lane % a.n;
+            for (int f = lane; f < total; f += 32) {
+                stage[r * stride + c] = src[f];
+                r += q32; c += m32;
+                if (c >= a.n) { c -= a.n; ++r; }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < NP; ++i) e[i] = (active && i < a.n) ? stage[lane * stride + i] : (T)0;
+            __syncwarp();
+            if (BOUNDS) accepted = active && (in_bounds<T, NP>(a, e, (T)1) || a.keep_last != 0);
+        } else {
+            if (active) accepted = draw_accepted<T, NP, BOUNDS>(a, a.first + local, e, s);
+            else {
+#pragma unroll
+                for (int i = 0; i < NP; ++i) e[i] = (T)0;
+            }
+        }
+
+        T q, r, ret, risk, sharpe;
+        quad_and_dot<T, NP>(a, e, q, r);
+        metrics_from<T>(q, r, s, a.rf, SRC == 1, ret, risk, sharpe);
+
+        if (accepted) {
+            ++n_acc;
+            if (sharpe > best_s) { best_s = sharpe; tile_s = (uint32_t)tile; }
+            const T d = -Math<T>::abs(risk - a.target);
+            if (d > best_d) { best_d = d; tile_d = (uint32_t)tile; }
+            rmin = risk < rmin ? risk : rmin;
+            rmax = risk > rmax ? risk : rmax;
+        }
+
+        // ---- optional write-back (app.py:719-722) ----
+        if (active) {
+            const T nanv = Math<T>::nan();
+            if (a.ret_out != nullptr) a.ret_out[local] = accepted ? ret : nanv;
+            if (a.risk_out != nullptr) a.risk_out[local] = accepted ? risk : nanv;
+            if (a.sharpe_out != nullptr) a.sharpe_out[local] = accepted ? sharpe : nanv;
+        }
+        if (a.acc_out != nullptr && active) a.acc_out[local] = accepted ? 1 : 0;
+        if (a.w_out != nullptr) {
+            const T inv = SRC == 1 ? (T)1 : Math<T>::rcp(s);
+#pragma unroll
+            for (int i = 0; i < NP; ++i)
+                if (i < a.n) stage[lane * stride + i] = e[i] * inv;
+            __syncwarp();
+            T* dst = a.w_out + warp_row0 * (uint64_t)a.n;
+            const int total = rows * a.n;
+            int rr = lane / a.n, cc = lane % a.n;
+            for (int f = lane; f < total; f += 32) {
+                dst[f] = stage[rr * stride + cc];
+                rr += q32; cc += m32;
+                if (cc >= a.n) { cc -= a.n; ++rr; }
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- CTA reduction: (key, global index) argmax with first-occurrence tie-break ----
+    uint64_t idx_s = tile_s == NONE ? MCP_NO_INDEX : a.first + (uint64_t)tile_s * PF_BLOCK + threadIdx.x;
+    uint64_t idx_d = tile_d == NONE ? MCP_NO_INDEX : a.first + (uint64_t)tile_d * PF_BLOCK + threadIdx.x;
+    warp_argmax<T>(best_s, idx_s);
+    warp_argmax<T>(best_d, idx_d);
+    rmin = warp_min<T>(rmin);
+    rmax = warp_max<T>(rmax);
+    n_acc = __reduce_add_sync(0xffffffffu, n_acc);
+
+    __shared__ PfCand wc[PF_BLOCK / 32];
+    __shared__ unsigned int wacc[PF_BLOCK / 32];
+    if (lane == 0) {
+        wc[warp] = PfCand{(double)best_s, idx_s, (double)best_d, idx_d, (double)rmin, (double)rmax};
+        wacc[warp] = n_acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        PfCand b = wc[0];
+        unsigned long long acc = wacc[0];
+        for (int w = 1; w < PF_BLOCK / 32; ++w) {
+            const PfCand o = wc[w];
+            if (cand_better<double>(o.key_s, o.idx_s, b.key_s, b.idx_s)) { b.key_s = o.key_s; b.idx_s = o.idx_s; }
+            if (cand_better<double>(o.key_d, o.idx_d, b.key_d, b.idx_d)) { b.key_d = o.key_d; b.idx_d = o.idx_d; }
+            b.rmin = o.rmin < b.rmin ? o.rmin : b.rmin;
+            b.rmax = o.rmax > b.rmax ? o.rmax : b.rmax;
+            acc += wacc[w];
+        }
+        a.cands[blockIdx.x] = b;
+        if (acc) atomicAdd(a.n_accepted, acc);
+    }
+}
+
+// Re-evaluates the selected portfolios with exactly the sweep's arithmetic and emits
+// (index, key, ret, risk, sharpe, weights[N]) records in FP64.
+template <typename T, int NP>
+__global__ void small_replay(const __grid_constant__ SmallArgs<T, NP> a, int n_sel, uint64_t idx0, uint64_t idx1,
+                             const T* rows, int bounds, double* rec) {
+    const int k = threadIdx.x;
+    if (k >= n_sel) return;
+    const uint64_t gidx = k == 0 ? idx0 : idx1;
+    double* out = rec + (size_t)k * (PF_REC_HEADER + a.n);
+    out[0] = __longlong_as_double((long long)gidx);
+    if (gidx == MCP_NO_INDEX) {
+        for (int i = 1; i < PF_REC_HEADER + a.n; ++i) out[i] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
+    T e[NP];
+    T s = (T)1;
+    const bool supplied = rows != nullptr;
+    if (supplied) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) e[i] = i < a.n ? rows[(size_t)k * a.n + i] : (T)0;
+    } else if (bounds) {
+        draw_accepted<T, NP, true>(a, gidx, e, s);
+    } else {
+        draw_accepted<T, NP, false>(a, gidx, e, s);
+    }
+    T q, r, ret, risk, sharpe;
+    quad_and_dot<T, NP>(a, e, q, r);
+    metrics_from<T>(q, r, s, a.rf, supplied, ret, risk, sharpe);
+    out[1] = k == 0 ? (double)sharpe : (double)Math<T>::abs(risk - a.target);
+    out[2] = (double)ret;
+    out[3] = (double)risk;
+    out[4] = (double)sharpe;
+    const T inv = supplied ? (T)1 : Math<T>::rcp(s);
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+        if (i < a.n) out[PF_REC_HEADER + i] = (double)(e[i] * inv);
+}
+
+template <typename T, int NP>
+static void fill_small_args(const PfJob& job, SmallArgs<T, NP>& a) {
+    const int n = job.n;
+    for (int i = 0; i < NP; ++i) {
+        for (int j = 0; j <= i; ++j) {
+            double v = 0.0;
+            if (i < n && j < n) v = (i == j) ? job.sigma[(size_t)i * n + i] : job.sigma[(size_t)i * n + j] + job.sigma[(size_t)j * n + i];
+            a.sig[i * (i + 1) / 2 + j] = (T)v;
+        }
+        a.mu[i] = i < n ? (T)job.mu[i] : (T)0;
+        a.mask[i] = i < n ? (T)1 : (T)0;
+        a.lo[i] = (i < n && job.lo) ? (T)job.lo[i] : (T)-1e30;
+        a.hi[i] = (i < n && job.hi) ? (T)job.hi[i] : (T)1e30;
+    }
+    a.rf = (T)job.rf;
+    a.target = (T)job.target;
+    a.n = n;
+    a.max_tries = job.max_tries;
+    a.keep_last = job.keep_last;
+    a.k0 = (uint32_t)job.seed;
+    a.k1 = (uint32_t)(job.seed >> 32);
+    a.first = job.first;
+    a.P = job.P;
+    a.w_in = (const T*)job.w_in;
+    a.w_out = (T*)job.w_out;
+    a.ret_out = (T*)job.ret_out;
+    a.risk_out = (T*)job.risk_out;
+    a.sharpe_out = (T*)job.sharpe_out;
+    a.acc_out = job.acc_out;
+    a.cands = job.cands;
+    a.n_accepted = job.n_accepted;
+}
+
+template <typename T, int NP>
+int pf_small_launch_t(mcp_context* h, PfJob& job) {
+    SmallArgs<T, NP> a;
+    fill_small_args<T, NP>(job, a);
+    void (*kern)(SmallArgs<T, NP>) = nullptr;
+    if (job.w_in) kern = job.bounds ? small_sweep<T, NP, 1, true> : small_sweep<T, NP, 1, false>;
+    else kern = job.bounds ? small_sweep<T, NP, 0, true> : small_sweep<T, NP, 0, false>;
+    const bool staging = job.w_in != nullptr || job.w_out != nullptr;
+    const size_t smem = staging ? (size_t)(PF_BLOCK / 32) * 32 * (job.n | 1) * sizeof(T) : 0;
+    if (smem > 48 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    MCP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PF_BLOCK, smem));
+    if (per_sm < 1) return mcp_fail(h, MCP_ERR_CUDA, "small_sweep<N=%d>: zero occupancy (smem %zu B)", NP, smem);
+    const uint64_t n_tiles = (job.P + PF_BLOCK - 1) / PF_BLOCK;
+    uint64_t grid = (uint64_t)h->prop.multiProcessorCount * per_sm;
+    if (grid > n_tiles) grid = n_tiles;
+    if (grid > (uint64_t)job.max_blocks) grid = job.max_blocks;
+    if (grid < 1) grid = 1;
+    job.blocks_used = (int)grid;
+    kern<<<(unsigned)grid, PF_BLOCK, smem, job.stream>>>(a);
+    MCP_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return MCP_OK;
+}
+
+template <typename T, int NP>
+int pf_small_replay_t(mcp_context* h, const PfJob& job, const PfReplay& rp) {
+    SmallArgs<T, NP> a;
+    fill_small_args<T, NP>(job, a);
+    small_replay<T, NP><<<1, 32, 0, job.stream>>>(a, rp.n_sel, rp.idx[0], rp.idx[1], (const T*)rp.rows,
+                                                 job.bounds ? 1 : 0, rp.rec);
+    MCP_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return MCP_OK;
+}
+
+}  // namespace mcp

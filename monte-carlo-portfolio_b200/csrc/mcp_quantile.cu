@@ -1,0 +1,331 @@
+// mcp_quantiles: exact VaR / CVaR over a (possibly sharded) vector of simulated returns.
+//
+// Conventions of the reference's var / cvar (app.py:258-263): VaR = np.percentile(x, (1-a)*100)
+// with numpy's default 'linear' method -- h = (n-1) q, lerp between the floor(h)-th and next
+// order statistics -- and CVaR = mean(x[x <= VaR]) (VaR if empty).  The order statistics are
+// found exactly by an MSB-first radix select on order-preserving integer keys: each pass
+// histograms 11 key bits of the values whose higher bits match the target's prefix
+// (warp-aggregated shared-memory atomics via __match_any_sync), the per-rank histograms are
+// summed (NCCL all-reduce supplied by the host as a callback when the vector is sharded), and a
+// host-side scan picks the digit.  3 passes for FP32, 6 for FP64; the vector (40 MB at C4) is
+// L2-resident after the first pass.  A last pass accumulates the tail sums in FP64.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "mcp_context.h"
+#include "mcp_device.cuh"
+
+namespace mcp {
+
+constexpr int SEL_BITS = 11;
+constexpr int SEL_BLOCK = 256;
+
+struct SelSlots {
+    uint64_t prefix[MCP_MAX_TARGETS];
+};
+
+template <typename T> struct KeyOf;
+template <> struct KeyOf<float> {
+    using K = uint32_t;
+    static constexpr int BITS = 32;
+    static __device__ __forceinline__ K key(float v) { return f32_to_key(__float_as_uint(v)); }
+};
+template <> struct KeyOf<double> {
+    using K = uint64_t;
+    static constexpr int BITS = 64;
+    static __device__ __forceinline__ K key(double v) { return f64_to_key((uint64_t)__double_as_longlong(v)); }
+};
+
+// hist[slot][digit] += #{ i : key_i >> (shift + bits) == prefix[slot], digit(key_i) = digit }
+template <typename T>
+__global__ void __launch_bounds__(SEL_BLOCK) select_hist_kernel(const T* __restrict__ v, uint64_t n, int n_slots,
+                                                                const __grid_constant__ SelSlots slots, int shift, int bits,
+                                                                unsigned long long* __restrict__ hist) {
+    using K = typename KeyOf<T>::K;
+    extern __shared__ unsigned int sh[];
+    const int nb = 1 << bits;
+    for (int i = threadIdx.x; i < n_slots * nb; i += SEL_BLOCK) sh[i] = 0;
+    __syncthreads();
+    const int hi_shift = shift + bits;
+    const bool all_match = hi_shift >= KeyOf<T>::BITS;
+    const K mask = (K)(nb - 1);
+    const int lane = threadIdx.x & 31;
+    for (uint64_t i = (uint64_t)blockIdx.x * SEL_BLOCK + threadIdx.x; i < n; i += (uint64_t)gridDim.x * SEL_BLOCK) {
+        const K k = KeyOf<T>::key(v[i]);
+        const unsigned digit = (unsigned)((k >> shift) & mask);
+        const K hi = all_match ? (K)0 : (K)(k >> (all_match ? 0 : hi_shift));
+        for (int s = 0; s < n_slots; ++s) {
+            if (all_match || hi == (K)slots.prefix[s]) {
+                const unsigned act = __activemask();
+                const unsigned peers = __match_any_sync(act, digit);
+                if (lane == __ffs(peers) - 1) atomicAdd(&sh[s * nb + digit], (unsigned)__popc(peers));
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_slots * nb; i += SEL_BLOCK) {
+        const unsigned c = sh[i];
+        if (c) atomicAdd(&hist[i], (unsigned long long)c);
+    }
+}
+
+struct TailArgs {
+    double thr[MCP_MAX_ALPHAS];
+};
+
+// sums[t] += sum of v_i <= thr[t] (FP64), counts[t] += their number
+template <typename T>
+__global__ void __launch_bounds__(SEL_BLOCK) tail_sum_kernel(const T* __restrict__ v, uint64_t n, int nt,
+                                                             const __grid_constant__ TailArgs a, double* __restrict__ sums,
+                                                             double* __restrict__ counts) {
+    double s[MCP_MAX_ALPHAS], c[MCP_MAX_ALPHAS];
+#pragma unroll
+    for (int t = 0; t < MCP_MAX_ALPHAS; ++t) s[t] = c[t] = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * SEL_BLOCK + threadIdx.x; i < n; i += (uint64_t)gridDim.x * SEL_BLOCK) {
+        const double x = (double)v[i];
+#pragma unroll
+        for (int t = 0; t < MCP_MAX_ALPHAS; ++t)
+            if (t < nt && x <= a.thr[t]) { s[t] += x; c[t] += 1.0; }
+    }
+    __shared__ double ws[SEL_BLOCK / 32][2 * MCP_MAX_ALPHAS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int t = 0; t < MCP_MAX_ALPHAS; ++t) {
+        double a0 = s[t], a1 = c[t];
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, m);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, m);
+        }
+        if (lane == 0) { ws[warp][2 * t] = a0; ws[warp][2 * t + 1] = a1; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * nt) {
+        double acc = 0;
+        for (int w = 0; w < SEL_BLOCK / 32; ++w) acc += ws[w][threadIdx.x];
+        if (acc != 0.0) atomicAdd((threadIdx.x & 1) ? &counts[threadIdx.x >> 1] : &sums[threadIdx.x >> 1], acc);
+    }
+}
+
+static void assign_slots(mcp_select_state* s) {
+    s->n_slots = 0;
+    for (int t = 0; t < s->n_targets; ++t) {
+        int found = -1;
+        for (int k = 0; k < s->n_slots; ++k)
+            if (s->slot_prefix[k] == s->prefix[t]) { found = k; break; }
+        if (found < 0) {
+            found = s->n_slots++;
+            s->slot_prefix[found] = s->prefix[t];
+        }
+        s->slot_of[t] = found;
+    }
+}
+
+static int grid_for(mcp_context* h, uint64_t n, int per_sm) {
+    uint64_t g = (n + SEL_BLOCK - 1) / SEL_BLOCK;
+    const uint64_t cap = (uint64_t)h->prop.multiProcessorCount * per_sm;
+    return (int)std::max<uint64_t>(1, std::min(g, cap));
+}
+
+}  // namespace mcp
+
+using namespace mcp;
+
+extern "C" {
+
+int mcp_select_init(mcp_select_state* s, int key_bits, const uint64_t* ranks, int n_targets) {
+    if (!s || !ranks || (key_bits != 32 && key_bits != 64) || n_targets < 1 || n_targets > MCP_MAX_TARGETS) return MCP_ERR_INVALID;
+    memset(s, 0, sizeof *s);
+    s->key_bits = key_bits;
+    s->n_targets = n_targets;
+    for (int t = 0; t < n_targets; ++t) s->rank[t] = ranks[t];
+    assign_slots(s);
+    return MCP_OK;
+}
+
+int mcp_select_pass_bits(const mcp_select_state* s) {
+    if (!s) return 0;
+    const int left = s->key_bits - s->bits_done;
+    return left < SEL_BITS ? left : SEL_BITS;
+}
+
+int mcp_select_advance(mcp_select_state* s, const uint64_t* hist) {
+    if (!s || !hist) return MCP_ERR_INVALID;
+    const int bits = mcp_select_pass_bits(s);
+    if (bits <= 0) return MCP_ERR_INVALID;
+    const int nb = 1 << bits;
+    for (int t = 0; t < s->n_targets; ++t) {
+        const uint64_t* hrow = hist + (size_t)s->slot_of[t] * nb;
+        uint64_t cum = 0;
+        int d = 0;
+        for (; d < nb; ++d) {
+            if (cum + hrow[d] > s->rank[t]) break;
+            cum += hrow[d];
+        }
+        if (d == nb) return MCP_ERR_INVALID;      // rank beyond the population of this prefix
+        s->rank[t] -= cum;
+        s->prefix[t] = (s->prefix[t] << bits) | (uint64_t)d;
+    }
+    s->bits_done += bits;
+    assign_slots(s);
+    return MCP_OK;
+}
+
+double mcp_key_to_value(uint64_t key, int dtype) {
+    if (dtype == MCP_F64) {
+        const uint64_t b = key_to_f64(key);
+        double d;
+        memcpy(&d, &b, 8);
+        return d;
+    }
+    const uint32_t b = key_to_f32((uint32_t)key);
+    float f;
+    memcpy(&f, &b, 4);
+    return (double)f;
+}
+
+int mcp_select_hist(mcp_handle h, const void* values_dev, int dtype, uint64_t n, const mcp_select_state* s,
+                    uint64_t* hist_dev) {
+    if (!h) return MCP_ERR_INVALID;
+    MCP_REQUIRE(h, s && hist_dev && (values_dev || n == 0), "mcp_select_hist: NULL argument");
+    MCP_REQUIRE(h, (dtype == MCP_F32 && s->key_bits == 32) || (dtype == MCP_F64 && s->key_bits == 64),
+                "mcp_select_hist: dtype %d does not match key_bits %d", dtype, s->key_bits);
+    mcp_device_guard guard(h->device);
+    const int bits = mcp_select_pass_bits(s);
+    MCP_REQUIRE(h, bits > 0, "mcp_select_hist: selection already finished");
+    const int nb = 1 << bits;
+    const int shift = s->key_bits - s->bits_done - bits;
+    cudaStream_t st = h->stream;
+    MCP_CUDA(h, cudaMemsetAsync(hist_dev, 0, sizeof(uint64_t) * s->n_slots * nb, st));
+    if (n == 0) return MCP_OK;
+    SelSlots slots;
+    memset(&slots, 0, sizeof slots);
+    for (int k = 0; k < s->n_slots; ++k) slots.prefix[k] = s->slot_prefix[k];
+    const size_t smem = sizeof(unsigned int) * s->n_slots * nb;
+    if (dtype == MCP_F64) {
+        if (smem > 48 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(select_hist_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        select_hist_kernel<double><<<grid_for(h, n, 4), SEL_BLOCK, smem, st>>>((const double*)values_dev, n, s->n_slots, slots, shift, bits,
+                                                                                (unsigned long long*)hist_dev);
+    } else {
+        if (smem > 48 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(select_hist_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        select_hist_kernel<float><<<grid_for(h, n, 4), SEL_BLOCK, smem, st>>>((const float*)values_dev, n, s->n_slots, slots, shift, bits,
+                                                                               (unsigned long long*)hist_dev);
+    }
+    MCP_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return MCP_OK;
+}
+
+int mcp_quantiles(mcp_handle h, const void* values, int space, int dtype, uint64_t n, uint64_t n_total,
+                  const double* alphas, int n_alphas, double* var_out, double* cvar_out,
+                  mcp_allreduce_fn allreduce, void* user) {
+    if (!h) return MCP_ERR_INVALID;
+    MCP_REQUIRE(h, alphas && var_out && cvar_out, "mcp_quantiles: NULL argument");
+    MCP_REQUIRE(h, values || n == 0, "mcp_quantiles: values is NULL");
+    MCP_REQUIRE(h, n_alphas >= 1 && n_alphas <= MCP_MAX_ALPHAS, "mcp_quantiles: n_alphas=%d out of range [1, %d]", n_alphas, MCP_MAX_ALPHAS);
+    MCP_REQUIRE(h, dtype == MCP_F32 || dtype == MCP_F64, "mcp_quantiles: bad dtype %d", dtype);
+    MCP_REQUIRE(h, space == MCP_HOST || space == MCP_DEVICE, "mcp_quantiles: bad space %d", space);
+    if (!allreduce) n_total = n;
+    MCP_REQUIRE(h, n_total >= 1 && n_total >= n, "mcp_quantiles: empty input (np.percentile of an empty array is an error)");
+    mcp_device_guard guard(h->device);
+    cudaStream_t st = h->stream;
+    const size_t es = dtype == MCP_F64 ? 8 : 4;
+    const void* v = values;
+    if (space == MCP_HOST && n) {
+        void* d = nullptr;
+        MCP_CHECK(mcp_dev_reserve(h, 3, n * es, &d));
+        MCP_CUDA(h, cudaMemcpyAsync(d, values, n * es, cudaMemcpyHostToDevice, st));
+        v = d;
+    }
+    // ---- order-statistic ranks: numpy 'linear' (virtual index (n-1) q, q = percent / 100) ----
+    uint64_t ranks[MCP_MAX_TARGETS];
+    double gamma[MCP_MAX_ALPHAS];
+    int lo_t[MCP_MAX_ALPHAS], hi_t[MCP_MAX_ALPHAS];
+    int nt = 0;
+    auto add_rank = [&](uint64_t r) {
+        for (int k = 0; k < nt; ++k) if (ranks[k] == r) return k;
+        ranks[nt] = r;
+        return nt++;
+    };
+    for (int a = 0; a < n_alphas; ++a) {
+        MCP_REQUIRE(h, alphas[a] >= 0.0 && alphas[a] <= 1.0, "mcp_quantiles: alpha[%d]=%g outside [0, 1]", a, alphas[a]);
+        const double percent = (1 - alphas[a]) * 100;          // app.py:259, same FP64 expression
+        const double q = percent / 100.0;
+        const double hidx = (double)(n_total - 1) * q;
+        uint64_t lo, hi;
+        if (hidx >= (double)(n_total - 1)) lo = hi = n_total - 1;
+        else if (hidx < 0) lo = hi = 0;
+        else { lo = (uint64_t)std::floor(hidx); hi = lo + 1; }
+        gamma[a] = hidx - std::floor(hidx);
+        lo_t[a] = add_rank(lo);
+        hi_t[a] = add_rank(hi);
+    }
+    mcp_select_state sel;
+    MCP_CHECK(mcp_select_init(&sel, dtype == MCP_F64 ? 64 : 32, ranks, nt) == MCP_OK ? MCP_OK
+              : mcp_fail(h, MCP_ERR_INVALID, "mcp_quantiles: select init failed"));
+    const size_t hist_elems = (size_t)MCP_MAX_TARGETS << SEL_BITS;
+    unsigned long long* d_hist = nullptr;
+    MCP_CHECK(mcp_dev_reserve(h, 5, hist_elems * 8 + 64 * 8, (void**)&d_hist));
+    std::vector<uint64_t> h_hist(hist_elems);
+    double ms_total = 0;
+    MCP_CUDA(h, cudaEventRecord(h->ev[0], st));
+    while (mcp_select_pass_bits(&sel) > 0) {
+        const int bits = mcp_select_pass_bits(&sel);
+        const size_t cnt = (size_t)sel.n_slots << bits;
+        MCP_CHECK(mcp_select_hist(h, v, dtype, n, &sel, (uint64_t*)d_hist));
+        if (allreduce) {
+            MCP_CUDA(h, cudaStreamSynchronize(st));
+            if (allreduce(d_hist, cnt, 0, user) != 0) return mcp_fail(h, MCP_ERR_INVALID, "mcp_quantiles: allreduce callback failed");
+        }
+        MCP_CUDA(h, cudaMemcpyAsync(h_hist.data(), d_hist, cnt * 8, cudaMemcpyDeviceToHost, st));
+        MCP_CUDA(h, cudaStreamSynchronize(st));
+        if (mcp_select_advance(&sel, h_hist.data()) != MCP_OK)
+            return mcp_fail(h, MCP_ERR_INVALID, "mcp_quantiles: rank outside the population (n_total=%llu inconsistent with the data?)",
+                            (unsigned long long)n_total);
+    }
+    // ---- VaR: numpy's _lerp on the two exact order statistics ----
+    TailArgs ta;
+    memset(&ta, 0, sizeof ta);
+    for (int a = 0; a < n_alphas; ++a) {
+        const double lo = mcp_key_to_value(sel.prefix[lo_t[a]], dtype);
+        const double hi = mcp_key_to_value(sel.prefix[hi_t[a]], dtype);
+        const double t = gamma[a], diff = hi - lo;
+        double r = lo + diff * t;
+        if (t >= 0.5) r = hi - diff * (1 - t);
+        var_out[a] = r;
+        ta.thr[a] = r;
+    }
+    // ---- CVaR: FP64 tail sums ----
+    double* d_sums = (double*)(d_hist + hist_elems);
+    double* d_counts = d_sums + MCP_MAX_ALPHAS;
+    MCP_CUDA(h, cudaMemsetAsync(d_sums, 0, sizeof(double) * 2 * MCP_MAX_ALPHAS, st));
+    if (n) {
+        if (dtype == MCP_F64) tail_sum_kernel<double><<<grid_for(h, n, 8), SEL_BLOCK, 0, st>>>((const double*)v, n, n_alphas, ta, d_sums, d_counts);
+        else tail_sum_kernel<float><<<grid_for(h, n, 8), SEL_BLOCK, 0, st>>>((const float*)v, n, n_alphas, ta, d_sums, d_counts);
+        MCP_CUDA(h, cudaGetLastError());
+        h->launches++;
+    }
+    MCP_CUDA(h, cudaEventRecord(h->ev[1], st));
+    if (allreduce) {
+        MCP_CUDA(h, cudaStreamSynchronize(st));
+        if (allreduce(d_sums, 2 * MCP_MAX_ALPHAS, 1, user) != 0) return mcp_fail(h, MCP_ERR_INVALID, "mcp_quantiles: allreduce callback failed");
+    }
+    double sums[2 * MCP_MAX_ALPHAS];
+    MCP_CUDA(h, cudaMemcpyAsync(sums, d_sums, sizeof sums, cudaMemcpyDeviceToHost, st));
+    MCP_CUDA(h, cudaStreamSynchronize(st));
+    for (int a = 0; a < n_alphas; ++a) {
+        const double cnt = sums[MCP_MAX_ALPHAS + a];
+        cvar_out[a] = cnt > 0 ? sums[a] / cnt : var_out[a];
+    }
+    float ms = 0;
+    if (!allreduce) {
+        MCP_CUDA(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+        ms_total = ms;
+    }
+    h->last_ms = ms_total;
+    return MCP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,409 @@
+"""Python host side of the B200 Monte Carlo portfolio path.
+
+Mirrors the reference's function-shaped interface for the path
+(``/root/reference/app.py``): ``efficient_frontier`` keeps the exact signature and
+return layout of app.py:265-284; ``simulate_portfolios`` is the inline loop
+app.py:682-722 collapsed into one call (same array names / order: risks, returns,
+weights, metrics) plus the two picks; ``simulate_paths`` and ``frontier_envelope``
+are the north-star additions.  All arithmetic runs in libmcp.so (hand-written
+sm_100a CUDA) through the C ABI of include/mcp.h -- this module only validates
+arguments, owns buffers and shapes results.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import weakref
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import (MCP_DEVICE, MCP_F32, MCP_F64, MCP_HOST, MCP_NO_INDEX, McpError, PathParams,
+                   PortfolioOut, PortfolioParams, check, lib)
+
+_DTYPES = {"float32": (MCP_F32, np.float32), "float64": (MCP_F64, np.float64),
+           np.float32: (MCP_F32, np.float32), np.float64: (MCP_F64, np.float64)}
+
+
+def _dtype(dtype):
+    try:
+        key = dtype if isinstance(dtype, str) else np.dtype(dtype).type
+        return _DTYPES[key]
+    except (KeyError, TypeError):
+        raise ValueError(f"dtype must be 'float32' or 'float64', got {dtype!r}") from None
+
+
+class Engine:
+    """One libmcp handle = one device.  Not re-entrant (one call at a time per engine)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        rc = lib().mcp_create(int(device), C.byref(self._h))
+        if rc != 0:
+            msg = lib().mcp_last_error(None)
+            raise McpError(rc, msg.decode() if msg else "mcp_create failed")
+        self.device = int(device)
+        self._finalizer = weakref.finalize(self, lib().mcp_destroy, self._h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        self._finalizer()
+
+    def info(self):
+        d = _lib.DeviceInfo()
+        check(self._h, lib().mcp_device_info(self._h, C.byref(d)))
+        return {"name": d.name.decode(), "sm_count": d.sm_count, "cc": (d.cc_major, d.cc_minor),
+                "max_smem_per_block": d.max_smem_per_block, "total_mem": d.total_mem}
+
+    def launch_count(self) -> int:
+        return int(lib().mcp_launch_count(self._h))
+
+    def last_kernel_ms(self) -> float:
+        return float(lib().mcp_last_kernel_ms(self._h))
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        """Order this engine's work on a caller stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        check(self._h, lib().mcp_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def synchronize(self):
+        check(self._h, lib().mcp_synchronize(self._h))
+
+    def measure_fma_peak(self, dtype="float32") -> float:
+        code, _ = _dtype(dtype)
+        out = C.c_double()
+        check(self._h, lib().mcp_measure_fma_peak(self._h, code, C.byref(out)))
+        return out.value
+
+
+_engines: dict[int, Engine] = {}
+
+
+def get_engine(device: int | None = None) -> Engine:
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    eng = _engines.get(device)
+    if eng is None:
+        eng = _engines[device] = Engine(device)
+    return eng
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """numpy array on page-locked host memory (fast path for HOST-space buffers)."""
+    dt = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dt.itemsize
+    p = C.c_void_p()
+    rc = lib().mcp_host_alloc(max(nbytes, 1), C.byref(p))
+    if rc != 0:
+        raise McpError(rc, "mcp_host_alloc failed")
+    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, lib().mcp_host_free, p)
+    return arr
+
+
+# ------------------------------------------------------------------------------------------
+# argument handling shared by the entry points
+# ------------------------------------------------------------------------------------------
+
+def _mu_sigma(mean_returns, cov_matrix):
+    """Accepts pd.Series / pd.DataFrame or ndarrays, like the app does (app.py:679-680)."""
+    mu = np.ascontiguousarray(np.asarray(mean_returns, dtype=np.float64))
+    sigma = np.ascontiguousarray(np.asarray(cov_matrix, dtype=np.float64))
+    if mu.ndim != 1 or mu.size < 1:
+        raise ValueError(f"mean_returns must be a non-empty vector, got shape {mu.shape}")
+    n = mu.size
+    if sigma.shape != (n, n):
+        raise ValueError(f"cov_matrix must have shape ({n}, {n}), got {sigma.shape}")
+    if not (np.all(np.isfinite(mu)) and np.all(np.isfinite(sigma))):
+        raise ValueError("mean_returns / cov_matrix contain non-finite values")
+    return mu, sigma, n
+
+
+def _bounds(v, n, name):
+    if v is None:
+        return None
+    a = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), (n,)))
+    if a.shape != (n,):
+        raise ValueError(f"{name} must have {n} entries")
+    return a
+
+
+def _is_device_tensor(x) -> bool:
+    return hasattr(x, "data_ptr") and getattr(x, "is_cuda", False)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_device_tensor(a):
+        return a.data_ptr()
+    return a.ctypes.data
+
+
+@dataclass
+class PortfolioResult:
+    """What one method's pass of app.py:682-722 leaves behind, plus the two picks."""
+    risks: np.ndarray | None          # all_risks   (app.py:719)
+    returns: np.ndarray | None        # all_returns (app.py:720)
+    weights: np.ndarray | None        # all_weights (app.py:721)
+    sharpes: np.ndarray | None        # all_metrics (app.py:722, metric = sharpe)
+    max_sharpe: dict | None           # np.argmax(sharpe) pick (app.py:672, 747)
+    target_risk: dict | None          # argmin |risk - target| pick (README.md:4)
+    n_requested: int = 0
+    n_accepted: int = 0
+    risk_range: tuple = (float("nan"), float("nan"))
+    kernel_ms: float = 0.0
+    accepted: np.ndarray | None = None
+    extra: dict = field(default_factory=dict)
+
+    def __iter__(self):               # risks, returns, weights, metrics = simulate_portfolios(...)
+        return iter((self.risks, self.returns, self.weights, self.sharpes))
+
+
+def _selection_dict(sel, wbuf, first_index, positions):
+    if sel.index == MCP_NO_INDEX:
+        return None
+    g = int(sel.index)
+    d = {"index": g, "global_index": g, "weights": wbuf.copy(), "ret": sel.ret, "risk": sel.risk,
+         "sharpe": sel.sharpe, "key": sel.key}
+    if positions is not None:         # index into the returned (accepted-only) arrays, as app.py:747
+        d["index"] = int(positions[g - first_index])
+    return d
+
+
+def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, risk_free=0.0, risk_target=0.30,
+                        min_weights=None, max_weights=None, weights=None, seed=0, dtype="float32",
+                        return_arrays=True, first_index=0, keep_last=False, max_tries=100,
+                        device=None, out=None) -> PortfolioResult:
+    """Random-weight portfolio sweep: the loop of app.py:699-722 in one call.
+
+    weights=None      flat-Dirichlet weights generated in-kernel (Philox4x32-10, counter =
+                      first_index + i), at most `max_tries` draws per portfolio against
+                      [min_weights, max_weights] (app.py:700-707; skipped on exhaustion
+                      unless keep_last, which is efficient_frontier's behaviour, app.py:277).
+    weights=(P, N)    supplied-weights (parity) mode: evaluated as given, no RNG.  numpy
+                      array (HOST space, copies inside the call) or CUDA torch tensor
+                      (DEVICE space, no copies; arrays come back as torch tensors).
+    risk_free         subtracted raw, as app.py:711 (pass 3.0 for the app's default widget value).
+    return_arrays     False: selections only, zero HBM write-back (C3 sizes).
+    out               optional dict of preallocated arrays ('weights', 'returns', 'risks',
+                      'sharpes', 'accepted') to reuse pinned buffers across calls.
+    Returns a PortfolioResult; arrays hold accepted portfolios only (P' <= P rows).
+    """
+    mu, sigma, n = _mu_sigma(mean_returns, cov_matrix)
+    code, npdt = _dtype(dtype)
+    lo = _bounds(min_weights, n, "min_weights")
+    hi = _bounds(max_weights, n, "max_weights")
+    P = int(n_portfolios)
+    if P < 0:
+        raise ValueError("n_portfolios must be >= 0")
+
+    device_mode = _is_device_tensor(weights)
+    w_in = None
+    recheck = None
+    if weights is not None:
+        if device_mode:
+            import torch
+            want = torch.float32 if code == MCP_F32 else torch.float64
+            w_in = weights.to(want).contiguous()
+            shape = tuple(w_in.shape)
+        else:
+            src = np.asarray(weights)
+            w_in = np.ascontiguousarray(src, dtype=npdt)
+            if code == MCP_F32 and src.dtype == np.float64:
+                recheck = np.ascontiguousarray(src)
+            shape = w_in.shape
+        if len(shape) != 2 or shape[1] != n:
+            raise ValueError(f"weights must have shape (P, {n}), got {shape}")
+        if shape[0] != P:
+            raise ValueError(f"weights has {shape[0]} rows but n_portfolios={P}")
+    eng = get_engine(device)
+
+    params = PortfolioParams()
+    params.n_assets, params.dtype = n, code
+    params.n_portfolios, params.first_index, params.seed = P, int(first_index), int(seed) & MCP_NO_INDEX
+    params.risk_free, params.risk_target = float(risk_free), float(risk_target)
+    params.min_weights, params.max_weights = _ptr(lo), _ptr(hi)
+    params.max_tries, params.keep_last = int(max_tries), int(bool(keep_last))
+    params.space = MCP_DEVICE if device_mode or return_arrays == "device" else MCP_HOST
+    params.weights_in = _ptr(w_in)
+    params.weights_recheck = _ptr(recheck)
+
+    res = PortfolioOut()
+    arrays = {}
+    if return_arrays:
+        names = (("weights", (P, n), npdt), ("returns", (P,), npdt), ("risks", (P,), npdt),
+                 ("sharpes", (P,), npdt), ("accepted", (P,), np.uint8))
+        if params.space == MCP_DEVICE:
+            import torch
+            tdt = torch.float32 if code == MCP_F32 else torch.float64
+            dev = torch.device("cuda", eng.device)
+            for name, shape, dt in names:
+                arrays[name] = torch.empty(shape, dtype=torch.uint8 if dt is np.uint8 else tdt, device=dev)
+        else:
+            for name, shape, dt in names:
+                a = None if out is None else out.get(name)
+                if a is not None and (a.shape != shape or a.dtype != dt or not a.flags.c_contiguous):
+                    raise ValueError(f"out[{name!r}] must be C-contiguous {shape} {np.dtype(dt)}")
+                arrays[name] = a if a is not None else np.empty(shape, dtype=dt)
+        for name in ("weights", "returns", "risks", "sharpes", "accepted"):
+            setattr(res, name, _ptr(arrays[name]))
+    ws = np.empty(n)
+    wt = np.empty(n)
+    res.max_sharpe.weights = ws.ctypes.data
+    res.target_risk.weights = wt.ctypes.data
+
+    if params.space == MCP_DEVICE:
+        import torch
+        eng.set_stream(torch.cuda.current_stream(eng.device).cuda_stream)
+    check(eng.handle, lib().mcp_portfolios(eng.handle, C.byref(params), mu.ctypes.data, sigma.ctypes.data, C.byref(res)))
+
+    n_acc = int(res.n_accepted)
+    positions = None
+    if return_arrays and n_acc < P:
+        # skipped portfolios (app.py:706-707): the reference's arrays simply do not contain them
+        acc = arrays["accepted"]
+        if params.space == MCP_DEVICE:
+            mask = acc.bool()
+            positions = (mask.cumsum(0) - 1).cpu().numpy()
+        else:
+            mask = acc.astype(bool)
+            positions = np.cumsum(mask) - 1
+        for name in ("weights", "returns", "risks", "sharpes"):
+            arrays[name] = arrays[name][mask]
+    elif return_arrays:
+        positions = _Identity()
+    return PortfolioResult(
+        risks=arrays.get("risks"), returns=arrays.get("returns"), weights=arrays.get("weights"),
+        sharpes=arrays.get("sharpes"),
+        max_sharpe=_selection_dict(res.max_sharpe, ws, int(first_index), positions),
+        target_risk=_selection_dict(res.target_risk, wt, int(first_index), positions),
+        n_requested=P, n_accepted=n_acc, risk_range=(res.risk_min, res.risk_max),
+        kernel_ms=res.kernel_ms, accepted=arrays.get("accepted"))
+
+
+class _Identity:
+    def __getitem__(self, i):
+        return i
+
+
+def efficient_frontier(mean_returns, cov_matrix, points=200, min_weights=None, max_weights=None, *,
+                       seed=0, dtype="float64", device=None):
+    """Drop-in for the reference's ``efficient_frontier`` (app.py:265-284).
+
+    Same signature, same return layout: ``results`` (3, points) = [std; return; return/std]
+    (Sharpe WITHOUT risk-free, app.py:282) and ``weights`` (points, N), both FP64 ndarrays.
+    Keeps the last draw when 100 tries are exhausted (app.py:277).  The reference draws
+    from the global legacy MT19937 state; here the stream is Philox keyed by ``seed``.
+    """
+    r = simulate_portfolios(mean_returns, cov_matrix, points, risk_free=0.0, min_weights=min_weights,
+                            max_weights=max_weights, seed=seed, dtype=dtype, keep_last=True,
+                            return_arrays=True, device=device)
+    results = np.zeros((3, int(points)))
+    results[0] = r.risks
+    results[1] = r.returns
+    results[2] = r.sharpes
+    return results, np.asarray(r.weights, dtype=np.float64)
+
+
+# ------------------------------------------------------------------------------------------
+# correlated paths + VaR / CVaR
+# ------------------------------------------------------------------------------------------
+
+def simulate_paths(mean_returns, cov_matrix, weights, n_paths, n_steps=252, *, dt=1.0 / 252,
+                   alphas=(0.95, 0.99), normals=None, seed=0, dtype="float32", first_index=0,
+                   return_terminal=None, device=None, allreduce=None, n_total=None):
+    """Correlated-return paths (Cholesky of Sigma, per-asset cumulative product) -> VaR / CVaR.
+
+    Not in the reference: r = mu dt + sqrt(dt) L z, V *= 1 + r (the
+    compounding of app.py:253), terminal = w . V_T - 1; VaR / CVaR follow app.py:258-263.
+    normals=(M, S, N) switches to supplied-normals (parity) mode.
+    Returns {'stats': {alpha: (var, cvar)}, 'terminal': ndarray | None, 'kernel_ms': float}.
+    """
+    mu, sigma, n = _mu_sigma(mean_returns, cov_matrix)
+    code, npdt = _dtype(dtype)
+    w = np.ascontiguousarray(np.asarray(weights, dtype=np.float64))
+    if w.shape != (n,):
+        raise ValueError(f"weights must have shape ({n},), got {w.shape}")
+    M, S = int(n_paths), int(n_steps)
+    if M < 1 or S < 1:
+        raise ValueError("n_paths and n_steps must be >= 1")
+    alphas = tuple(float(a) for a in alphas)
+    eng = get_engine(device)
+    import torch   # device memory for the terminal values (plumbing only)
+    dev = torch.device("cuda", eng.device)
+    eng.set_stream(torch.cuda.current_stream(eng.device).cuda_stream)
+    tdt = torch.float32 if code == MCP_F32 else torch.float64
+
+    z_dev = None
+    if normals is not None:
+        if _is_device_tensor(normals):
+            z_dev = normals.to(tdt).contiguous()
+        else:
+            z = np.ascontiguousarray(np.asarray(normals), dtype=npdt)
+            if z.shape != (M, S, n):
+                raise ValueError(f"normals must have shape ({M}, {S}, {n}), got {z.shape}")
+            z_dev = torch.from_numpy(z).to(dev)
+        if tuple(z_dev.shape) != (M, S, n):
+            raise ValueError(f"normals must have shape ({M}, {S}, {n}), got {tuple(z_dev.shape)}")
+
+    terminal = torch.empty(M, dtype=tdt, device=dev)
+    p = PathParams()
+    p.n_assets, p.dtype, p.n_paths, p.first_index = n, code, M, int(first_index)
+    p.seed, p.n_steps, p.space, p.dt = int(seed) & MCP_NO_INDEX, S, MCP_DEVICE, float(dt)
+    p.normals_in = _ptr(z_dev)
+    ms = C.c_double()
+    check(eng.handle, lib().mcp_paths(eng.handle, C.byref(p), mu.ctypes.data, sigma.ctypes.data, w.ctypes.data,
+                                      terminal.data_ptr(), C.byref(ms)))
+    stats = quantile_stats(terminal, alphas, device=eng.device, allreduce=allreduce, n_total=n_total)
+    if return_terminal is None:
+        return_terminal = M <= (1 << 22)
+    return {"stats": stats, "terminal": terminal.cpu().numpy() if return_terminal else None,
+            "terminal_device": terminal, "kernel_ms": ms.value,
+            "quantile_ms": eng.last_kernel_ms()}
+
+
+def quantile_stats(values, alphas=(0.95, 0.99), *, device=None, allreduce=None, n_total=None):
+    """{alpha: (VaR, CVaR)} with app.py:258-263 conventions via the exact radix select.
+
+    `values`: numpy array (HOST space) or CUDA torch tensor (DEVICE space), float32/float64.
+    `allreduce(ptr, count, kind)`: in-place sum across ranks of a device buffer (see
+    mcportfolio.dist.make_allreduce); `n_total` = global element count.
+    """
+    eng = get_engine(device)
+    alphas = np.ascontiguousarray(np.asarray(alphas, dtype=np.float64))
+    if alphas.ndim != 1 or not (1 <= alphas.size <= _lib.MCP_MAX_ALPHAS):
+        raise ValueError(f"between 1 and {_lib.MCP_MAX_ALPHAS} alphas are supported")
+    if _is_device_tensor(values):
+        import torch
+        v = values.contiguous()
+        code = {torch.float32: MCP_F32, torch.float64: MCP_F64}[v.dtype]
+        space, n = MCP_DEVICE, v.numel()
+        eng.set_stream(torch.cuda.current_stream(eng.device).cuda_stream)
+    else:
+        v = np.ascontiguousarray(values)
+        if v.dtype not in (np.float32, np.float64):
+            v = v.astype(np.float64)
+        code = MCP_F32 if v.dtype == np.float32 else MCP_F64
+        space, n = MCP_HOST, v.size
+    var_out = np.empty(alphas.size)
+    cvar_out = np.empty(alphas.size)
+    cb = _lib.ALLREDUCE_FN(0)
+    if allreduce is not None:
+        def _cb(ptr, count, kind, _user):
+            try:
+                allreduce(ptr, count, kind)
+                return 0
+            except Exception:      # never let an exception cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return 1
+        cb = _lib.ALLREDUCE_FN(_cb)
+    total = int(n_total) if n_total is not None else n
+    check(eng.handle, lib().mcp_quantiles(eng.handle, _ptr(v), space, code, n, total, alphas.ctypes.data,
+                                          alphas.size, var_out.ctypes.data, cvar_out.ctypes.data, cb, None))
+    return {float(a): (float(var_out[i]), float(cvar_out[i])) for i, a in enumerate(alphas)}

@@ -1,0 +1,210 @@
+"""Multi-GPU sharding of the path: one process per GPU, ``torch.distributed`` for the plumbing.
+
+Portfolios and paths are independent units: rank r owns the contiguous global index block
+``shard_range(total, r, world)`` and, because the Philox counter is the GLOBAL index, the
+union over ranks is the same set of portfolios / paths for any world size.  No data-path
+collective exists; only results cross NVLink (NCCL), all latency-bound:
+
+* selection:  all_gather of one fixed-size record per rank and criterion, then the same
+  deterministic merge on every rank (best key, lowest global index on ties = numpy's
+  first-occurrence rule, app.py:672);
+* VaR / CVaR: per radix pass an all-reduce(sum) of the <= 16 x 2048 histogram counts, then an
+  all-reduce of the FP64 tail sums (``make_allreduce`` is the callback libmcp calls).
+
+Per-portfolio arrays are never moved between GPUs.
+"""
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+
+from . import api
+
+
+def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous block of rank `rank`: (first_index, count); blocks differ by at most 1."""
+    total, rank, world = int(total), int(rank), int(world)
+    if world < 1 or not (0 <= rank < world) or total < 0:
+        raise ValueError(f"bad shard request total={total} rank={rank} world={world}")
+    base, rem = divmod(total, world)
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+# ---- selection merge -----------------------------------------------------------------------
+
+_REC_HEAD = 6     # valid, key, ret, risk, sharpe, (index travels separately as int64)
+
+
+def pack_record(rec: dict | None, n_assets: int):
+    """(int64 index, float64[_REC_HEAD - 1 + N]) -- fixed size so all_gather needs no negotiation."""
+    body = np.full(_REC_HEAD - 1 + n_assets, np.nan)
+    if rec is None:
+        body[0] = 0.0
+        return -1, body
+    body[0] = 1.0
+    body[1:5] = rec["key"], rec["ret"], rec["risk"], rec["sharpe"]
+    body[5:] = rec["weights"]
+    return int(rec["global_index"]), body
+
+
+def unpack_record(index: int, body: np.ndarray) -> dict | None:
+    if body[0] != 1.0:
+        return None
+    return {"index": int(index), "global_index": int(index), "key": float(body[1]), "ret": float(body[2]),
+            "risk": float(body[3]), "sharpe": float(body[4]), "weights": np.array(body[5:], dtype=np.float64)}
+
+
+def merge_records(records, larger_is_better: bool) -> dict | None:
+    """Best key wins; ties go to the lowest global index (first occurrence, app.py:672)."""
+    best = None
+    for r in records:
+        if r is None or np.isnan(r["key"]):
+            continue
+        if best is None:
+            best = r
+            continue
+        better = r["key"] > best["key"] if larger_is_better else r["key"] < best["key"]
+        if better or (r["key"] == best["key"] and r["global_index"] < best["global_index"]):
+            best = r
+    return best
+
+
+def all_gather_records(rec: dict | None, n_assets: int, device=None, group=None):
+    """Every rank's record, on every rank (one all_gather of (6 + N) doubles per criterion)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    idx, body = pack_record(rec, n_assets)
+    dev = torch.device("cpu") if device is None else device
+    t_idx = torch.tensor([idx], dtype=torch.int64, device=dev)
+    t_body = torch.from_numpy(body).to(dev)
+    g_idx = [torch.empty_like(t_idx) for _ in range(world)]
+    g_body = [torch.empty_like(t_body) for _ in range(world)]
+    dist.all_gather(g_idx, t_idx, group=group)
+    dist.all_gather(g_body, t_body, group=group)
+    return [unpack_record(int(i.item()), b.cpu().numpy()) for i, b in zip(g_idx, g_body)]
+
+
+def simulate_portfolios_sharded(mean_returns, cov_matrix, n_portfolios, *, group=None, **kw):
+    """`simulate_portfolios` over the whole job: this rank evaluates its block, selections are
+    merged across ranks.  Arrays (if requested) stay local to the rank that produced them."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    first, count = shard_range(n_portfolios, rank, world)
+    n = len(np.asarray(mean_returns))
+    r = api.simulate_portfolios(mean_returns, cov_matrix, count, first_index=first, **kw)
+    dev = torch.device("cuda", api.get_engine(kw.get("device")).device) if dist.get_backend(group) == "nccl" else None
+    for name, larger in (("max_sharpe", True), ("target_risk", False)):
+        rec = getattr(r, name)
+        if rec is not None:
+            rec = dict(rec, index=rec["global_index"])
+        setattr(r, name, merge_records(all_gather_records(rec, n, dev, group), larger))
+    acc = torch.tensor([r.n_accepted], dtype=torch.int64, device=dev or "cpu")
+    dist.all_reduce(acc, group=group)
+    r.extra["n_accepted_global"] = int(acc.item())
+    r.extra["shard"] = (first, count)
+    return r
+
+
+# ---- VaR / CVaR merge ------------------------------------------------------------------------
+
+class _DeviceBuffer:
+    """Zero-copy view of a raw device pointer for torch (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, count: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False),
+                                         "version": 2, "strides": None}
+
+
+def wrap_device_buffer(ptr: int, count: int, kind: int, device_index: int):
+    import torch
+    return torch.as_tensor(_DeviceBuffer(ptr, count, "<i8" if kind == 0 else "<f8"),
+                           device=torch.device("cuda", device_index))
+
+
+def make_allreduce(device_index: int, group=None):
+    """The callback libmcp's mcp_quantiles calls between radix passes: NCCL sum, in place."""
+    import torch
+    import torch.distributed as dist
+
+    def allreduce(ptr, count, kind):
+        t = wrap_device_buffer(ptr, count, kind, device_index)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        torch.cuda.current_stream(device_index).synchronize()
+
+    return allreduce
+
+
+def simulate_paths_sharded(mean_returns, cov_matrix, weights, n_paths, n_steps=252, *, group=None, **kw):
+    """`simulate_paths` over the whole job: local paths, globally exact VaR / CVaR."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    first, count = shard_range(n_paths, rank, world)
+    eng = api.get_engine(kw.get("device"))
+    return api.simulate_paths(mean_returns, cov_matrix, weights, count, n_steps, first_index=first,
+                              allreduce=make_allreduce(eng.device, group) if world > 1 else None,
+                              n_total=n_paths, **kw)
+
+
+def emulate_sharded_quantiles(shards, alphas, device_index: int = 0):
+    """Multi-rank VaR / CVaR merge on ONE GPU, for tests: one host thread and one libmcp handle
+    per shard; the all-reduce is a thread barrier plus a device-side sum.  (No kernel ever
+    waits on another kernel: the waiting happens on the host between launches.)"""
+    import torch
+    world = len(shards)
+    barrier = threading.Barrier(world)
+    slots = [None] * world
+    results = [None] * world
+    errors = []
+
+    def worker(rank):
+        try:
+            eng = api.Engine(device_index)
+            stream = torch.cuda.Stream(device_index)
+
+            def allreduce(ptr, count, kind):
+                slots[rank] = wrap_device_buffer(ptr, count, kind, device_index)
+                torch.cuda.synchronize(device_index)
+                barrier.wait()
+                if rank == 0:
+                    total = torch.stack(slots).sum(0)
+                    for s in slots:
+                        s.copy_(total)
+                    torch.cuda.synchronize(device_index)
+                barrier.wait()
+
+            with torch.cuda.stream(stream):
+                eng.set_stream(stream.cuda_stream)
+                n_total = sum(int(s.numel()) for s in shards)
+                alph = np.ascontiguousarray(np.asarray(alphas, dtype=np.float64))
+                import ctypes as C
+                from . import _lib
+                v = shards[rank].contiguous()
+                code = _lib.MCP_F32 if v.dtype == torch.float32 else _lib.MCP_F64
+                var_out, cvar_out = np.empty(alph.size), np.empty(alph.size)
+
+                def _cb(ptr, count, kind, _u):
+                    allreduce(ptr, count, kind)
+                    return 0
+                cb = _lib.ALLREDUCE_FN(_cb)
+                _lib.check(eng.handle, _lib.lib().mcp_quantiles(
+                    eng.handle, v.data_ptr(), _lib.MCP_DEVICE, code, v.numel(), n_total, alph.ctypes.data,
+                    alph.size, var_out.ctypes.data, cvar_out.ctypes.data, cb, None))
+                results[rank] = {float(a): (float(var_out[i]), float(cvar_out[i])) for i, a in enumerate(alph)}
+            eng.close()
+        except Exception as e:      # surface worker failures in the caller
+            errors.append(e)
+            barrier.abort()
+
+    threads = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    assert all(r == results[0] for r in results), "ranks disagree on the merged quantiles"
+    return results[0]

@@ -125,8 +125,9 @@ def dirichlet_weights(first_index, n_portfolios, n_assets, seed, dtype="float32"
 def normals(first_index, n_paths, n_steps, n_assets, seed, dtype="float32"):
     """Standard normals Z[m, s, i] by Box-Muller on output pairs (2k, 2k+1).
 
-    U1 in (0,1] from output 2k, angle fraction from output 2k+1:
-    z[2k] = r cos(theta), z[2k+1] = r sin(theta), r = sqrt(-2 ln U1), theta = 2 pi f.
+    U1 in (0,1] from output 2k, angle fraction f in [0,1) from output 2k+1:
+    z[2k] = r cos(theta), z[2k+1] = r sin(theta), r = sqrt(-2 ln U1), theta = pi (2f - 1)
+    (the angle is centred on 0 so the MUFU sin/cos approximations stay in [-pi, pi)).
     float32 uses 23-bit fractions, float64 32-bit ones (same convention as `exponentials`).
     """
     idx = np.arange(first_index, first_index + n_paths, dtype=np.uint64)
@@ -139,7 +140,7 @@ def normals(first_index, n_paths, n_steps, n_assets, seed, dtype="float32"):
         else:
             f = x.astype(np.float64) * 2.0 ** -32
         u1 = 1.0 - f[:, 0::2]
-        th = 2.0 * np.pi * f[:, 1::2]
+        th = np.pi * (2.0 * f[:, 1::2] - 1.0)
         r = np.sqrt(-2.0 * np.log(u1))
         z = np.empty((n_paths, n_even))
         z[:, 0::2] = r * np.cos(th)

@@ -1,0 +1,105 @@
+"""CPU tier, world_size 2 over gloo: the host logic of the N>1 path -- index-range sharding,
+the selection-record merge (all_gather + deterministic pick) and the distributed radix select
+(histogram all-reduce between passes driving libmcp's host state machine)."""
+import ctypes as C
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from conftest import PKG_DIR, ROOT
+
+
+def test_shard_range_partitions_exactly():
+    from mcportfolio.dist import shard_range
+    for total in (0, 1, 7, 10**10, 10**10 + 3):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [shard_range(total, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and sum(c for _, c in blocks) == total
+            for (f0, c0), (f1, _) in zip(blocks[:-1], blocks[1:]):
+                assert f0 + c0 == f1
+            assert max(c for _, c in blocks) - min(c for _, c in blocks) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def test_merge_records_first_occurrence():
+    from mcportfolio.dist import merge_records, pack_record, unpack_record
+    mk = lambda k, i: {"key": k, "global_index": i, "index": i, "ret": 0.1, "risk": 0.2, "sharpe": k, "weights": np.array([0.5, 0.5])}
+    recs = [mk(1.0, 50), None, mk(2.0, 99), mk(2.0, 7), mk(float("nan"), 1)]
+    assert merge_records(recs, True)["global_index"] == 7
+    assert merge_records(recs, False)["global_index"] == 50
+    assert merge_records([None, None], True) is None
+    i, b = pack_record(recs[2], 2)
+    back = unpack_record(i, b)
+    assert back["global_index"] == 99 and back["key"] == 2.0 and np.array_equal(back["weights"], [0.5, 0.5])
+    assert unpack_record(*pack_record(None, 2)) is None
+    big = mk(1.0, 2**40 + 12345)                     # 64-bit indices survive the trip
+    assert unpack_record(*pack_record(big, 2))["global_index"] == 2**40 + 12345
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    import sys
+    for p in (ROOT, PKG_DIR, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    from mcportfolio import _lib
+    from mcportfolio.dist import all_gather_records, merge_records, shard_range
+    from test_abi_cpu import _hist_np, f32_keys
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        # ---- selection merge: each rank contributes its local best; ties -> lowest global index
+        local = {"key": 1.5, "global_index": 1000 - rank, "index": 0, "ret": 0.3, "risk": 0.2,
+                 "sharpe": 1.5, "weights": np.full(4, 0.25) * (rank + 1)}
+        merged = merge_records(all_gather_records(local, 4), True)
+        # ---- distributed exact select: this rank holds one shard of a common vector
+        x = np.random.default_rng(42).standard_normal(20_001).astype(np.float32)
+        first, count = shard_range(len(x), rank, world)
+        keys = f32_keys(x[first:first + count])
+        L = _lib.lib()
+        st = _lib.SelectState()
+        ranks = np.array([0, 1000, 1001, len(x) - 1], dtype=np.uint64)
+        assert L.mcp_select_init(C.byref(st), 32, ranks.ctypes.data, len(ranks)) == 0
+        while L.mcp_select_pass_bits(C.byref(st)):
+            bits = L.mcp_select_pass_bits(C.byref(st))
+            hist = np.stack([_hist_np(keys, st.slot_prefix[s], st.bits_done, bits, 32) for s in range(st.n_slots)])
+            t = torch.from_numpy(hist.astype(np.int64))
+            dist.all_reduce(t)                                     # what NCCL does on the GPU box
+            summed = np.ascontiguousarray(t.numpy().astype(np.uint64))
+            assert L.mcp_select_advance(C.byref(st), summed.ctypes.data) == 0
+        vals = [L.mcp_key_to_value(st.prefix[i], 0) for i in range(len(ranks))]
+        q.put((rank, merged["global_index"], merged["weights"].tolist(), vals))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_selection_and_select_merge():
+    import torch.multiprocessing as mp
+    import mcportfolio
+    mcportfolio.build()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x = np.random.default_rng(42).standard_normal(20_001).astype(np.float32)
+    xs = np.sort(x)
+    want = [float(xs[i]) for i in (0, 1000, 1001, len(x) - 1)]
+    for rank, gidx, w, vals in out:
+        assert gidx == 999                       # equal keys: lowest global index (rank 1's) wins
+        assert w == [0.5] * 4
+        assert vals == want

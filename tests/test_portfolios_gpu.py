@@ -1,0 +1,253 @@
+"""GPU tier: the CUDA portfolio sweep (through the C ABI) against the oracle.
+
+Tolerances (BASELINE.json north_star): supplied-weights mode within 1e-6 relative in FP64
+and 1e-4 in FP32, with the same selected index; in-kernel RNG is checked value-by-value
+against the numpy restatement of the generator and statistically against np.random.dirichlet.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden, synthetic_inputs
+from oracle import philox_np, reference_np as ref
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {"float64": 1e-6, "float32": 1e-4}
+
+
+@pytest.fixture(scope="module")
+def mcp():
+    import mcportfolio
+    mcportfolio.build()
+    return mcportfolio
+
+
+def check_against_oracle(r, W, mu, sigma, rf, target, dtype, same_index=True):
+    want = ref.evaluate(W, mu, sigma, rf, target)
+    tol = RTOL[dtype]
+    assert r.n_accepted == len(W)
+    assert np.allclose(r.returns, want["returns"], rtol=tol, atol=tol * 1e-3)
+    assert np.allclose(r.risks, want["risks"], rtol=tol)
+    assert np.allclose(r.sharpes, want["sharpes"], rtol=tol, atol=tol * np.abs(want["sharpes"]).max())
+    assert np.allclose(r.weights, W, rtol=tol, atol=1e-7)
+    for pick in ("max_sharpe", "target_risk"):
+        got, exp = getattr(r, pick), want[pick]
+        if same_index:
+            assert got["index"] == exp["index"], pick
+        assert np.isclose(got["ret"], exp["ret"], rtol=tol) and np.isclose(got["risk"], exp["risk"], rtol=tol)
+        assert np.allclose(got["weights"], exp["weights"], rtol=tol, atol=1e-7)
+    return want
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("rf,opt", [(3.0, 1451), (0.03, 4593)])
+def test_c1_supplied_weights_matches_reference_lines(mcp, c1, dtype, rf, opt):
+    """C1: the 10k legacy-seed-42 Dirichlet draws, evaluated by the reference's own lines."""
+    W = c1["weights"]
+    r = mcp.simulate_portfolios(c1["mu"], c1["sigma"], len(W), weights=W, risk_free=rf, dtype=dtype)
+    tol = RTOL[dtype]
+    tag = "rf3" if rf == 3.0 else "rf003"
+    assert np.allclose(r.risks, c1["risks"], rtol=tol)
+    assert np.allclose(r.returns, c1["returns"], rtol=tol)
+    assert np.allclose(r.sharpes, c1[f"sharpes_{tag}"], rtol=tol)
+    assert r.max_sharpe["index"] == opt == int(c1[f"opt_sharpe_{tag}"])
+    assert r.target_risk["index"] == int(c1["opt_target30"])
+    check_against_oracle(r, W, c1["mu"], c1["sigma"], rf, 0.30, dtype)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_c2_14_assets_supplied(mcp, c2, dtype):
+    W = c2["weights"]
+    r = mcp.simulate_portfolios(c2["mu"], c2["sigma"], len(W), weights=W, risk_free=0.03, dtype=dtype)
+    assert np.allclose(r.risks, c2["risks"], rtol=RTOL[dtype])
+    assert np.allclose(r.sharpes, c2["sharpes"], rtol=RTOL[dtype], atol=RTOL[dtype])
+    assert r.max_sharpe["index"] == int(c2["opt_sharpe"])
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 13, 16, 17, 24, 31, 32])
+def test_supplied_weights_all_small_n(mcp, n, dtype):
+    mu, sigma = synthetic_inputs(n, seed=n)
+    rng = np.random.RandomState(n)
+    P = 3001                                    # ragged: not a multiple of the CTA tile
+    W = rng.dirichlet(np.ones(n), size=P)
+    r = mcp.simulate_portfolios(mu, sigma, P, weights=W, risk_free=0.03, risk_target=0.25, dtype=dtype)
+    check_against_oracle(r, W, mu, sigma, 0.03, 0.25, dtype, same_index=(dtype == "float64"))
+
+
+def test_edge_sizes(mcp):
+    mu, sigma = synthetic_inputs(4)
+    r = mcp.simulate_portfolios(mu, sigma, 0)
+    assert r.n_accepted == 0 and r.max_sharpe is None and r.risks.shape == (0,)
+    W = np.array([[0.25, 0.25, 0.25, 0.25]])
+    r = mcp.simulate_portfolios(mu, sigma, 1, weights=W, dtype="float64")
+    assert r.max_sharpe["index"] == 0 and r.target_risk["index"] == 0
+    # zero-risk portfolio: sharpe = 0 (app.py:711 `if port_std > 0 else 0`)
+    r = mcp.simulate_portfolios(mu, np.zeros((4, 4)), 1, weights=W, dtype="float64")
+    assert r.risks[0] == 0.0 and r.sharpes[0] == 0.0
+
+
+def test_first_occurrence_tie_break(mcp):
+    """np.argmax / np.argmin return the first index among ties."""
+    mu, sigma = synthetic_inputs(4)
+    rng = np.random.RandomState(0)
+    base = rng.dirichlet(np.ones(4), size=50)
+    W = np.tile(base, (40, 1))                 # every row repeated 40 times -> exact ties
+    for dtype in ("float64", "float32"):
+        r = mcp.simulate_portfolios(mu, sigma, len(W), weights=W, dtype=dtype, risk_free=0.03)
+        assert r.max_sharpe["index"] < 50 and r.target_risk["index"] < 50
+        want = ref.evaluate(W, mu, sigma, 0.03, 0.30)
+        if dtype == "float64":
+            assert r.max_sharpe["index"] == want["max_sharpe"]["index"]
+            assert r.target_risk["index"] == want["target_risk"]["index"]
+
+
+@pytest.mark.parametrize("dtype,atol", [("float32", 2e-6), ("float64", 1e-12)])
+@pytest.mark.parametrize("n", [2, 5, 16, 20, 32])
+def test_rng_mode_matches_generator_restatement(mcp, n, dtype, atol):
+    """In-kernel Philox weights == oracle/philox_np.py on the same counters; metrics follow."""
+    mu, sigma = synthetic_inputs(n, seed=3)
+    P, first, seed = 5000, 123_456_789_012, 0xDEADBEEFCAFE
+    r = mcp.simulate_portfolios(mu, sigma, P, risk_free=0.03, seed=seed, first_index=first, dtype=dtype)
+    W, valid = philox_np.dirichlet_weights(first, P, n, seed, dtype)
+    assert valid.all() and r.n_accepted == P
+    assert np.allclose(r.weights, W, atol=atol)
+    want = ref.evaluate(W, mu, sigma, 0.03, 0.30)
+    tol = RTOL[dtype]
+    assert np.allclose(r.risks, want["risks"], rtol=tol) and np.allclose(r.returns, want["returns"], rtol=tol)
+    assert np.allclose(r.sharpes, want["sharpes"], rtol=tol, atol=tol)
+    # picks: the selected portfolio must be (within tolerance) the oracle's optimum
+    assert np.isclose(r.max_sharpe["sharpe"], want["max_sharpe"]["sharpe"], rtol=tol)
+    assert r.max_sharpe["global_index"] == first + r.max_sharpe["index"]
+    if dtype == "float64":
+        assert r.max_sharpe["index"] == want["max_sharpe"]["index"]
+        assert r.target_risk["index"] == want["target_risk"]["index"]
+    # the record is re-evaluated with the sweep's arithmetic: identical to the array entries
+    i = r.max_sharpe["index"]
+    assert r.max_sharpe["sharpe"] == float(r.sharpes[i]) and r.max_sharpe["risk"] == float(r.risks[i])
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_rng_bounds_rejection_and_skip(mcp, dtype):
+    """app.py:700-707: <= max_tries draws, skip on exhaustion -> arrays shorter than P."""
+    n = 4
+    mu, sigma = synthetic_inputs(n)
+    lo, hi = np.array([0.2, 0.0, 0.0, 0.0]), np.array([0.3, 1.0, 1.0, 0.5])
+    P, seed = 4000, 11
+    r = mcp.simulate_portfolios(mu, sigma, P, min_weights=lo, max_weights=hi, seed=seed, dtype=dtype,
+                                max_tries=4, risk_free=0.03)
+    W, valid = philox_np.dirichlet_weights(0, P, n, seed, dtype, lo, hi, max_tries=4)
+    assert 0 < valid.sum() < P
+    # acceptance can differ only where a weight sits on a bound within rounding
+    acc = r.accepted.astype(bool)
+    margin = np.minimum(np.abs(W - lo).min(1), np.abs(W - hi).min(1))
+    differ = acc != valid
+    assert differ.sum() <= 2 and np.all(margin[differ] < 1e-5)
+    both = acc & valid
+    assert np.allclose(r.weights[np.cumsum(acc)[both] - 1], W[both], atol=2e-6 if dtype == "float32" else 1e-12)
+    assert np.all(r.weights >= lo - 1e-6) and np.all(r.weights <= hi + 1e-6)
+    assert r.n_accepted == acc.sum() == len(r.risks)
+    # picks index the accepted-only arrays, like the reference's opt_idx (app.py:747)
+    assert r.max_sharpe["index"] == int(np.argmax(r.sharpes))
+    # keep_last (efficient_frontier semantics, app.py:277): nothing is skipped
+    r2 = mcp.simulate_portfolios(mu, sigma, P, min_weights=lo, max_weights=hi, seed=seed, dtype=dtype,
+                                 max_tries=4, keep_last=True)
+    assert r2.n_accepted == P and np.allclose(r2.weights, W, atol=2e-6)
+    # impossible bounds: everything skipped, empty arrays, no pick
+    r3 = mcp.simulate_portfolios(mu, sigma, 500, min_weights=np.full(n, 0.6), seed=1, dtype=dtype, max_tries=3)
+    assert r3.n_accepted == 0 and r3.max_sharpe is None and len(r3.risks) == 0
+
+
+def test_sharding_invariance(mcp, synth16):
+    """Counter = global index: any split of the range gives the same portfolios and picks."""
+    mu, sigma = synth16
+    P = 300_000
+    whole = mcp.simulate_portfolios(mu, sigma, P, risk_free=0.03, seed=5, return_arrays=False)
+    cuts = [0, 70_001, 150_000, 299_999, P]
+    parts = [mcp.simulate_portfolios(mu, sigma, b - a, risk_free=0.03, seed=5, first_index=a, return_arrays=False)
+             for a, b in zip(cuts[:-1], cuts[1:])]
+    best = max(parts, key=lambda r: (r.max_sharpe["key"], -r.max_sharpe["global_index"]))
+    assert best.max_sharpe["global_index"] == whole.max_sharpe["global_index"]
+    assert best.max_sharpe["sharpe"] == whole.max_sharpe["sharpe"]
+    near = min(parts, key=lambda r: (r.target_risk["key"], r.target_risk["global_index"]))
+    assert near.target_risk["global_index"] == whole.target_risk["global_index"]
+    assert np.array_equal(near.target_risk["weights"], whole.target_risk["weights"])
+    assert sum(p.n_accepted for p in parts) == whole.n_accepted == P
+    # and the no-write-back run agrees with the run that materialises the arrays
+    full = mcp.simulate_portfolios(mu, sigma, P, risk_free=0.03, seed=5)
+    assert full.max_sharpe["global_index"] == whole.max_sharpe["global_index"] == int(np.argmax(full.sharpes))
+    assert whole.target_risk["global_index"] == int(np.argmin(np.abs(full.risks - 0.30)))
+
+
+def test_rng_statistics_against_numpy_dirichlet(mcp, synth16):
+    """Flat Dirichlet: mean 1/N, var (N-1)/(N^2 (N+1)); (risk, return) envelope vs numpy's sampler."""
+    mu, sigma = synth16
+    N, P = 16, 2_000_000
+    r = mcp.simulate_portfolios(mu, sigma, P, risk_free=0.03, seed=99)
+    W = r.weights
+    assert np.allclose(W.sum(1), 1.0, atol=1e-5)
+    v = (N - 1) / (N * N * (N + 1))
+    assert np.allclose(W.mean(0), 1 / N, atol=5 * np.sqrt(v / P))
+    assert np.allclose(W.var(0), v, rtol=0.01)
+    c = np.cov(W[:200_000], rowvar=False)
+    off = c[~np.eye(N, dtype=bool)]
+    assert np.allclose(off, -1 / (N * N * (N + 1)), atol=2e-5)          # Dirichlet covariance
+    Wn = np.random.RandomState(1).dirichlet(np.ones(N), size=P)
+    _, risk_n, sharpe_n = ref.portfolio_metrics(Wn, mu, sigma, 0.03)
+    for q in (0.001, 0.01, 0.5, 0.99, 0.999):
+        assert np.isclose(np.quantile(r.risks, q), np.quantile(risk_n, q), rtol=5e-3)
+        assert np.isclose(np.quantile(r.sharpes, q), np.quantile(sharpe_n, q), rtol=1e-2, atol=1e-3)
+    # a single coordinate is Beta(1, N-1): KS distance against the exact CDF
+    x = np.sort(W[:500_000, 3].astype(np.float64))
+    cdf = 1 - (1 - x) ** (N - 1)
+    ks = np.abs(cdf - (np.arange(len(x)) + 0.5) / len(x)).max()
+    assert ks < 1.63 / np.sqrt(len(x)) * 1.5
+
+
+def test_efficient_frontier_drop_in(mcp, c1):
+    """Same signature and return layout as app.py:265-284."""
+    res, W = mcp.efficient_frontier(c1["mu"], c1["sigma"], points=200, seed=4)
+    assert res.shape == (3, 200) and W.shape == (200, 2) and res.dtype == np.float64
+    Wp, _ = philox_np.dirichlet_weights(0, 200, 2, 4, "float64")
+    assert np.allclose(W, Wp, atol=1e-12)
+    ret, risk, sh = ref.portfolio_metrics(W, c1["mu"], c1["sigma"], 0.0)
+    assert np.allclose(res[0], risk, rtol=1e-9) and np.allclose(res[1], ret, rtol=1e-9)
+    assert np.allclose(res[2], ret / risk, rtol=1e-9)                 # Sharpe without rf (app.py:282)
+    import pandas as pd                                               # the app passes pandas objects
+    res2, W2 = mcp.efficient_frontier(pd.Series(c1["mu"]), pd.DataFrame(c1["sigma"]), 200, seed=4)
+    assert np.array_equal(res2, res) and np.array_equal(W2, W)
+    # bounded: keeps the last draw on exhaustion, so all `points` rows come back
+    res3, W3 = mcp.efficient_frontier(c1["mu"], c1["sigma"], 64, np.array([0.49, 0.0]), np.array([0.5, 1.0]), seed=4)
+    assert W3.shape == (64, 2)
+    inside = (W3[:, 0] >= 0.49) & (W3[:, 0] <= 0.5)
+    assert 0 < inside.sum() < 64
+
+
+def test_device_space_torch_tensors(mcp, synth16):
+    import torch
+    mu, sigma = synth16
+    W = np.random.RandomState(2).dirichlet(np.ones(16), size=10_000)
+    Wt = torch.from_numpy(W).cuda()
+    r = mcp.simulate_portfolios(mu, sigma, len(W), weights=Wt, risk_free=0.03, dtype="float64")
+    assert r.risks.is_cuda
+    want = ref.evaluate(W, mu, sigma, 0.03, 0.30)
+    assert np.allclose(r.risks.cpu().numpy(), want["risks"], rtol=1e-9)
+    assert r.max_sharpe["index"] == want["max_sharpe"]["index"]
+    r2 = mcp.simulate_portfolios(mu, sigma, 50_000, seed=1, return_arrays="device")
+    assert r2.weights.is_cuda and r2.weights.shape == (50_000, 16)
+    assert torch.allclose(r2.weights.sum(1), torch.ones(50_000, device="cuda"), atol=1e-5)
+
+
+def test_host_pipeline_many_chunks(mcp):
+    """HOST space with more rows than one pipeline slot holds: chunks, both slots, ragged tail."""
+    n = 32
+    mu, sigma = synthetic_inputs(n, seed=1)
+    P = 2_000_003
+    W = np.random.RandomState(3).dirichlet(np.ones(n), size=P).astype(np.float32)
+    r = mcp.simulate_portfolios(mu, sigma, P, weights=W, risk_free=0.03, dtype="float32")
+    ret, risk, sharpe = ref.portfolio_metrics(W.astype(np.float64), mu, sigma, 0.03)
+    assert np.allclose(r.risks, risk, rtol=1e-4) and np.allclose(r.sharpes, sharpe, rtol=1e-4, atol=1e-4)
+    assert np.array_equal(r.weights, W)
+    assert np.isclose(r.max_sharpe["sharpe"], sharpe.max(), rtol=1e-5)
+    assert r.max_sharpe["index"] == int(np.argmax(r.sharpes))
+    assert r.target_risk["index"] == int(np.argmin(np.abs(r.risks - np.float32(0.30))))
