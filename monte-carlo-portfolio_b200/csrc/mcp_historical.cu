@@ -1,11 +1,276 @@
-// mcp_historical_var: per-portfolio historical VaR / CVaR (app.py:710-713) and the 'VaR' /
-// 'CVaR' method selections (app.py:673-674).  SURVEY.md 8(f) row f1 -- scheduled after the
-// core path; fails loudly until the kernel lands (no CPU fallback).
-#include "mcp_context.h"
+// mcp_historical_var: per-portfolio HISTORICAL VaR / CVaR and the 'VaR' / 'CVaR' selections.
+//
+// Reference: app.py:710 `port_series = returns_df @ ws`, 712-713 `var(port_series, .95)` /
+// `cvar(port_series, .95)` (definitions 258-263), 717 metric = -var / -cvar, 673-674 + 747
+// `np.argmin(metric)`  ==  first index of the LARGEST var (cvar).  This is where ~70 % of the
+// reference's loop time goes.
+//
+// One warp per portfolio.  The returns matrix R (T x N) sits in shared memory, transposed and
+// padded so that lanes reading consecutive periods hit consecutive banks; the portfolio's
+// weights are a shared-memory broadcast.  Each lane owns periods lane, lane+32, ... of the
+// series in registers.  The two order statistics np.percentile needs are found exactly by an
+// MSB-first bitwise radix select on order-preserving keys with warp vote/reduce primitives
+// (32 or 64 REDUX rounds), the tail mean by a warp reduction; the selections reuse the
+// (key, first index) argmax machinery of the sweep.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
 
-extern "C" int mcp_historical_var(mcp_handle h, const mcp_hist_params* params, const double* returns_matrix_host,
-                                  mcp_hist_out* out) {
+#include "mcp_device.cuh"
+#include "mcp_portfolio.h"
+
+namespace mcp {
+
+constexpr int HV_BLOCK = 256;
+constexpr int HV_WARPS = HV_BLOCK / 32;
+
+template <typename T> struct HKey;
+template <> struct HKey<float> {
+    using K = uint32_t;
+    static constexpr int BITS = 32;
+    static __device__ __forceinline__ K to_key(float v) { return f32_to_key(__float_as_uint(v)); }
+    static __device__ __forceinline__ float from_key(K k) { return __uint_as_float(key_to_f32(k)); }
+};
+template <> struct HKey<double> {
+    using K = uint64_t;
+    static constexpr int BITS = 64;
+    static __device__ __forceinline__ K to_key(double v) { return f64_to_key((uint64_t)__double_as_longlong(v)); }
+    static __device__ __forceinline__ double from_key(K k) { return __longlong_as_double((long long)key_to_f64(k)); }
+};
+
+template <typename T>
+struct HistArgs {
+    const T* w_in;          // [P, n]
+    const T* r_t;           // [n][t_pad] transposed returns (global; staged into smem)
+    T* var_out;
+    T* cvar_out;
+    PfCand* cands;
+    uint64_t first, P;
+    int n, T_, t_pad;
+    int k_lo, k_hi;         // 0-based order statistics
+    T gamma;                // interpolation weight
+};
+
+template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += shfl_xor<T>(v, m);
+    return v;
+}
+
+template <typename T, int VPL>
+__global__ void __launch_bounds__(HV_BLOCK) hist_var_kernel(const HistArgs<T> a) {
+    using K = typename HKey<T>::K;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* sR = reinterpret_cast<T*>(smem_raw);                 // [n][t_pad]
+    T* sW = sR + (size_t)a.n * a.t_pad;                     // [HV_WARPS][n]
+    for (int i = threadIdx.x; i < a.n * a.t_pad; i += HV_BLOCK) sR[i] = a.r_t[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T* myW = sW + warp * a.n;
+
+    T best_v = -Math<T>::inf(), best_c = -Math<T>::inf();
+    uint64_t idx_v = MCP_NO_INDEX, idx_c = MCP_NO_INDEX;
+    const uint64_t warps_total = (uint64_t)gridDim.x * HV_WARPS;
+    for (uint64_t p = (uint64_t)blockIdx.x * HV_WARPS + warp; p < a.P; p += warps_total) {
+        __syncwarp();
+        for (int i = lane; i < a.n; i += 32) myW[i] = a.w_in[p * a.n + i];
+        __syncwarp();
+        // ---- series[t] = sum_i R[t, i] w_i for this lane's periods ----
+        T x[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) x[v] = (T)0;
+        for (int i = 0; i < a.n; ++i) {
+            const T wi = myW[i];
+            const T* row = sR + (size_t)i * a.t_pad + lane;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) x[v] = Math<T>::fma(row[32 * v], wi, x[v]);   // padded columns are 0
+        }
+        K key[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const bool valid = lane + 32 * v < a.T_;
+            key[v] = valid ? HKey<T>::to_key(x[v]) : ~(K)0;      // padding sorts last
+        }
+        // ---- k_lo-th smallest key: MSB-first, count keys with the candidate prefix and bit 0 ----
+        K prefix = 0;
+        int rank = a.k_lo;
+#pragma unroll 1
+        for (int b = HKey<T>::BITS - 1; b >= 0; --b) {
+            const K himask = b == HKey<T>::BITS - 1 ? (K)0 : (K)(~(K)0 << (b + 1));
+            int c = 0;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) c += ((key[v] & himask) == prefix && !((key[v] >> b) & 1)) ? 1 : 0;
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (rank >= c) { rank -= c; prefix |= (K)1 << b; }
+        }
+        const T v_lo = HKey<T>::from_key(prefix);
+        // (k_lo+1)-th: v_lo again if it is repeated far enough, else the smallest value above it
+        int le = 0;
+        T above = Math<T>::inf();
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const bool valid = lane + 32 * v < a.T_;
+            le += (valid && key[v] <= prefix) ? 1 : 0;
+            if (valid && key[v] > prefix && x[v] < above) above = x[v];
+        }
+        le = __reduce_add_sync(0xffffffffu, le);
+        above = warp_min<T>(above);
+        const T v_hi = (a.k_hi == a.k_lo || le >= a.k_hi + 1) ? v_lo : above;
+        // numpy _lerp
+        const T diff = v_hi - v_lo;
+        T var = v_lo + diff * a.gamma;
+        if (a.gamma >= (T)0.5) var = v_hi - diff * ((T)1 - a.gamma);
+        // ---- CVaR = mean(x[x <= VaR]) (VaR if empty), app.py:261-263 ----
+        T s = (T)0;
+        int cnt = 0;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const bool in = (lane + 32 * v < a.T_) && x[v] <= var;
+            s += in ? x[v] : (T)0;
+            cnt += in ? 1 : 0;
+        }
+        s = warp_sum<T>(s);
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        const T cvar = cnt > 0 ? s / (T)cnt : var;
+        if (lane == 0) {
+            if (a.var_out) a.var_out[p] = var;
+            if (a.cvar_out) a.cvar_out[p] = cvar;
+        }
+        const uint64_t g = a.first + p;
+        if (var > best_v) { best_v = var; idx_v = g; }          // p ascends per warp: first occurrence kept
+        if (cvar > best_c) { best_c = cvar; idx_c = g; }
+    }
+    __shared__ PfCand wc[HV_WARPS];
+    if (lane == 0) wc[warp] = PfCand{(double)best_v, idx_v, (double)best_c, idx_c, 0.0, 0.0};
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        PfCand b = wc[0];
+        for (int w = 1; w < HV_WARPS; ++w) {
+            const PfCand o = wc[w];
+            if (cand_better<double>(o.key_s, o.idx_s, b.key_s, b.idx_s)) { b.key_s = o.key_s; b.idx_s = o.idx_s; }
+            if (cand_better<double>(o.key_d, o.idx_d, b.key_d, b.idx_d)) { b.key_d = o.key_d; b.idx_d = o.idx_d; }
+        }
+        a.cands[blockIdx.x] = b;
+    }
+}
+
+template <typename T, int VPL>
+static int hist_launch_t(mcp_context* h, const HistArgs<T>& a, size_t smem, int max_blocks, int* blocks, cudaStream_t st) {
+    auto kern = hist_var_kernel<T, VPL>;
+    if (smem > 48 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    MCP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HV_BLOCK, smem));
+    if (per_sm < 1) return mcp_fail(h, MCP_ERR_INVALID, "mcp_historical_var: returns matrix does not fit in shared memory (%zu B)", smem);
+    uint64_t grid = std::min<uint64_t>((uint64_t)h->prop.multiProcessorCount * per_sm, (a.P + HV_WARPS - 1) / HV_WARPS);
+    grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, max_blocks));
+    *blocks = (int)grid;
+    kern<<<(unsigned)grid, HV_BLOCK, smem, st>>>(a);
+    MCP_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return MCP_OK;
+}
+
+template <typename T>
+static int hist_dispatch(mcp_context* h, const HistArgs<T>& a, size_t smem, int max_blocks, int* blocks, cudaStream_t st) {
+    const int vpl = (a.T_ + 31) / 32;
+#define MCP_HV(V) if (vpl <= V) return hist_launch_t<T, V>(h, a, smem, max_blocks, blocks, st);
+    MCP_HV(1) MCP_HV(2) MCP_HV(4) MCP_HV(8) MCP_HV(12) MCP_HV(16) MCP_HV(24) MCP_HV(32) MCP_HV(64)
+#undef MCP_HV
+    return mcp_fail(h, MCP_ERR_INVALID, "mcp_historical_var: n_periods=%d exceeds the supported maximum of 2048", a.T_);
+}
+
+template <typename T>
+static int hist_run(mcp_context* h, const mcp_hist_params* p, const double* R, mcp_hist_out* out) {
+    const int n = p->n_assets, Tn = p->n_periods;
+    const uint64_t P = p->n_portfolios;
+    cudaStream_t st = h->stream;
+    const int vpl = (Tn + 31) / 32;
+    MCP_REQUIRE(h, vpl <= 64, "mcp_historical_var: n_periods=%d exceeds the supported maximum of 2048", Tn);
+    // padded lanes read columns up to 32 * VPL_template; pad to the dispatch bucket
+    int bucket = 64;
+    for (int v : {1, 2, 4, 8, 12, 16, 24, 32, 64}) if (vpl <= v) { bucket = v; break; }
+    const int tp = 32 * bucket;
+    std::vector<T> rt((size_t)n * tp, (T)0);
+    for (int t = 0; t < Tn; ++t)
+        for (int i = 0; i < n; ++i) rt[(size_t)i * tp + t] = (T)R[(size_t)t * n + i];
+    const size_t smem = ((size_t)n * tp + (size_t)HV_WARPS * n) * sizeof(T);
+    MCP_REQUIRE(h, smem <= h->prop.sharedMemPerBlockOptin, "mcp_historical_var: T=%d x N=%d needs %zu B of shared memory (max %zu)",
+                Tn, n, smem, (size_t)h->prop.sharedMemPerBlockOptin);
+
+    const int max_blocks = h->prop.multiProcessorCount * 16;
+    unsigned char* base = nullptr;
+    const size_t off_rt = sizeof(PfCand) * (size_t)(max_blocks + 1);
+    MCP_CHECK(mcp_dev_reserve(h, 0, off_rt + rt.size() * sizeof(T) + 256, (void**)&base));
+    PfCand* cands = (PfCand*)base;
+    PfCand* fin = cands + max_blocks;
+    T* d_rt = (T*)(base + (off_rt + 255) / 256 * 256);
+    MCP_CUDA(h, cudaMemcpyAsync(d_rt, rt.data(), rt.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+
+    const T* d_w = (const T*)p->weights_in;
+    T* d_var = (T*)out->var;
+    T* d_cvar = (T*)out->cvar;
+    if (p->space == MCP_HOST) {
+        void* q = nullptr;
+        MCP_CHECK(mcp_dev_reserve(h, 1, P * n * sizeof(T), &q));
+        MCP_CUDA(h, cudaMemcpyAsync(q, p->weights_in, P * n * sizeof(T), cudaMemcpyHostToDevice, st));
+        d_w = (const T*)q;
+        if (out->var || out->cvar) {
+            MCP_CHECK(mcp_dev_reserve(h, 3, 2 * P * sizeof(T), &q));
+            d_var = out->var ? (T*)q : nullptr;
+            d_cvar = out->cvar ? (T*)q + P : nullptr;
+        }
+    }
+    // order statistics of np.percentile(x, (1-alpha)*100), 'linear': h = (T-1) q  (app.py:259)
+    const double percent = (1 - p->alpha) * 100, q = percent / 100.0, hidx = (double)(Tn - 1) * q;
+    int k_lo, k_hi;
+    if (hidx >= (double)(Tn - 1)) k_lo = k_hi = Tn - 1;
+    else if (hidx < 0) k_lo = k_hi = 0;
+    else { k_lo = (int)std::floor(hidx); k_hi = k_lo + 1; }
+    HistArgs<T> a;
+    a.w_in = d_w; a.r_t = d_rt; a.var_out = d_var; a.cvar_out = d_cvar; a.cands = cands;
+    a.first = p->first_index; a.P = P; a.n = n; a.T_ = Tn; a.t_pad = tp;
+    a.k_lo = k_lo; a.k_hi = k_hi; a.gamma = (T)(hidx - std::floor(hidx));
+    int blocks = 0;
+    MCP_CUDA(h, cudaEventRecord(h->ev[0], st));
+    MCP_CHECK(hist_dispatch<T>(h, a, smem, max_blocks, &blocks, st));
+    MCP_CUDA(h, cudaEventRecord(h->ev[1], st));
+    MCP_CHECK(pf_reduce_launch(h, cands, blocks, fin, 0, st));
+    if (p->space == MCP_HOST) {
+        if (out->var) MCP_CUDA(h, cudaMemcpyAsync(out->var, d_var, P * sizeof(T), cudaMemcpyDeviceToHost, st));
+        if (out->cvar) MCP_CUDA(h, cudaMemcpyAsync(out->cvar, d_cvar, P * sizeof(T), cudaMemcpyDeviceToHost, st));
+    }
+    PfCand f;
+    MCP_CUDA(h, cudaMemcpyAsync(&f, fin, sizeof f, cudaMemcpyDeviceToHost, st));
+    MCP_CUDA(h, cudaStreamSynchronize(st));
+    float ms = 0;
+    MCP_CUDA(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    out->best_var_index = f.idx_s;
+    out->best_var = f.key_s;
+    out->best_cvar_index = f.idx_d;
+    out->best_cvar = f.key_d;
+    out->kernel_ms = ms;
+    h->last_ms = ms;
+    return MCP_OK;
+}
+
+}  // namespace mcp
+
+using namespace mcp;
+
+extern "C" int mcp_historical_var(mcp_handle h, const mcp_hist_params* p, const double* R, mcp_hist_out* out) {
     if (!h) return MCP_ERR_INVALID;
-    (void)params; (void)returns_matrix_host; (void)out;
-    return mcp_fail(h, MCP_ERR_INVALID, "mcp_historical_var: kernel not built yet");
+    MCP_REQUIRE(h, p && R && out, "mcp_historical_var: NULL argument");
+    MCP_REQUIRE(h, p->n_assets >= 1 && p->n_assets <= 4096, "mcp_historical_var: bad n_assets %d", p->n_assets);
+    MCP_REQUIRE(h, p->n_periods >= 1, "mcp_historical_var: n_periods must be >= 1 (np.percentile of an empty series is an error)");
+    MCP_REQUIRE(h, p->dtype == MCP_F32 || p->dtype == MCP_F64, "mcp_historical_var: bad dtype %d", p->dtype);
+    MCP_REQUIRE(h, p->space == MCP_HOST || p->space == MCP_DEVICE, "mcp_historical_var: bad space %d", p->space);
+    MCP_REQUIRE(h, p->alpha >= 0 && p->alpha <= 1, "mcp_historical_var: alpha=%g outside [0, 1]", p->alpha);
+    MCP_REQUIRE(h, p->weights_in || p->n_portfolios == 0, "mcp_historical_var: weights_in is NULL");
+    out->best_var_index = out->best_cvar_index = MCP_NO_INDEX;
+    out->best_var = out->best_cvar = NAN;
+    out->kernel_ms = 0;
+    if (p->n_portfolios == 0) return MCP_OK;
+    mcp_device_guard guard(h->device);
+    return p->dtype == MCP_F64 ? hist_run<double>(h, p, R, out) : hist_run<float>(h, p, R, out);
 }

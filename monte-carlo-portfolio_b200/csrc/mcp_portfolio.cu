@@ -41,6 +41,13 @@ __global__ void __launch_bounds__(256) pf_reduce_cands(const PfCand* __restrict_
     }
 }
 
+int pf_reduce_launch(mcp_context* h, const PfCand* cands, int n, PfCand* acc, int accumulate, cudaStream_t st) {
+    pf_reduce_cands<<<1, 256, 0, st>>>(cands, n, acc, accumulate);
+    MCP_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return MCP_OK;
+}
+
 static const int kSmallNP[] = {4, 8, 16, 24, 32};
 
 template <typename T>
@@ -166,9 +173,7 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
         MCP_CUDA(h, cudaEventRecord(h->ev[0], st));
         MCP_CHECK(pf_launch(h, job));
         MCP_CUDA(h, cudaEventRecord(h->ev[1], st));
-        pf_reduce_cands<<<1, 256, 0, st>>>(cands, job.blocks_used, final_cand, 0);
-        MCP_CUDA(h, cudaGetLastError());
-        h->launches++;
+        MCP_CHECK(pf_reduce_launch(h, cands, job.blocks_used, final_cand, 0, st));
     } else {
         // ---- HOST space: two-slot chunk pipeline ----
         MCP_CUDA(h, cudaStreamSynchronize(st));           // the memset above must precede the side streams
@@ -231,9 +236,7 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
             MCP_CHECK(pf_launch(h, job));
             MCP_CUDA(h, cudaEventRecord(h->ev[2 * s + 1], ss));
             timed[s] = true;
-            pf_reduce_cands<<<1, 256, 0, ss>>>(job.cands, job.blocks_used, running + s, used[s] ? 1 : 0);
-            MCP_CUDA(h, cudaGetLastError());
-            h->launches++;
+            MCP_CHECK(pf_reduce_launch(h, job.cands, job.blocks_used, running + s, used[s] ? 1 : 0, ss));
             if (dw) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->weights + r0 * N * es, dw, rows * N * es, cudaMemcpyDeviceToHost, ss));
             if (dr) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->returns + r0 * es, dr, rows * es, cudaMemcpyDeviceToHost, ss));
             if (dk) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->risks + r0 * es, dk, rows * es, cudaMemcpyDeviceToHost, ss));
@@ -252,9 +255,7 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
             }
         }
         const int n_run = used[1] ? 2 : 1;
-        pf_reduce_cands<<<1, 256, 0, st>>>(running, n_run, final_cand, 0);
-        MCP_CUDA(h, cudaGetLastError());
-        h->launches++;
+        MCP_CHECK(pf_reduce_launch(h, running, n_run, final_cand, 0, st));
     }
 
     // ---- winners: indices to the host, rows (supplied mode) to scratch, replay, records back ----

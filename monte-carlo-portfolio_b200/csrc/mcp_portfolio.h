@@ -60,6 +60,9 @@ struct PfReplay {
     double* rec = nullptr;             // device, n_sel * (PF_REC_HEADER + N) doubles
 };
 
+// merges n per-CTA candidates (and the running record when accumulate != 0) into *acc
+int pf_reduce_launch(mcp_context* h, const PfCand* cands, int n, PfCand* acc, int accumulate, cudaStream_t st);
+
 int pf_small_launch(mcp_context* h, PfJob& job);
 int pf_small_replay(mcp_context* h, const PfJob& job, const PfReplay& rp);
 int pf_large_launch(mcp_context* h, PfJob& job);

@@ -407,3 +407,98 @@ def quantile_stats(values, alphas=(0.95, 0.99), *, device=None, allreduce=None, 
     check(eng.handle, lib().mcp_quantiles(eng.handle, _ptr(v), space, code, n, total, alphas.ctypes.data,
                                           alphas.size, var_out.ctypes.data, cvar_out.ctypes.data, cb, None))
     return {float(a): (float(var_out[i]), float(cvar_out[i])) for i, a in enumerate(alphas)}
+
+
+# ------------------------------------------------------------------------------------------
+# per-portfolio historical VaR / CVaR and the five "methods" of the app
+# ------------------------------------------------------------------------------------------
+
+def historical_var_cvar(returns_matrix, weights, alpha=0.95, *, dtype="float32", first_index=0,
+                        return_arrays=True, device=None):
+    """VaR / CVaR of the historical series ``returns_matrix @ w`` for every portfolio.
+
+    app.py:710-713 (definitions 258-263).  `weights`: (P, N) numpy array or CUDA torch tensor.
+    Returns {'var': (P,), 'cvar': (P,), 'best_var': {...}, 'best_cvar': {...}, 'kernel_ms'}
+    where best_var / best_cvar are the picks of the 'VaR' / 'CVaR' methods:
+    ``np.argmin(-var)`` = first index of the largest VaR (app.py:673-674, 717, 747).
+    """
+    R = np.ascontiguousarray(np.asarray(returns_matrix, dtype=np.float64))
+    if R.ndim != 2 or R.shape[0] < 1:
+        raise ValueError(f"returns_matrix must be (T, N) with T >= 1, got {R.shape}")
+    T, n = R.shape
+    code, npdt = _dtype(dtype)
+    dev_mode = _is_device_tensor(weights)
+    if dev_mode:
+        import torch
+        w = weights.to(torch.float32 if code == MCP_F32 else torch.float64).contiguous()
+        shape = tuple(w.shape)
+    else:
+        w = np.ascontiguousarray(np.asarray(weights), dtype=npdt)
+        shape = w.shape
+    if len(shape) != 2 or shape[1] != n:
+        raise ValueError(f"weights must have shape (P, {n}), got {shape}")
+    P = shape[0]
+    eng = get_engine(device)
+    p = _lib.HistParams()
+    p.n_assets, p.n_periods, p.dtype = n, T, code
+    p.space = MCP_DEVICE if dev_mode else MCP_HOST
+    p.n_portfolios, p.first_index, p.alpha = P, int(first_index), float(alpha)
+    p.weights_in = _ptr(w)
+    out = _lib.HistOut()
+    var = cvar = None
+    if return_arrays:
+        if dev_mode:
+            import torch
+            var, cvar = torch.empty(P, dtype=w.dtype, device=w.device), torch.empty(P, dtype=w.dtype, device=w.device)
+            eng.set_stream(torch.cuda.current_stream(eng.device).cuda_stream)
+        else:
+            var, cvar = np.empty(P, dtype=npdt), np.empty(P, dtype=npdt)
+        out.var, out.cvar = _ptr(var), _ptr(cvar)
+    check(eng.handle, lib().mcp_historical_var(eng.handle, C.byref(p), R.ctypes.data, C.byref(out)))
+    pick = lambda i, v: None if i == MCP_NO_INDEX else {"index": int(i) - int(first_index), "global_index": int(i), "value": v}
+    return {"var": var, "cvar": cvar, "best_var": pick(out.best_var_index, out.best_var),
+            "best_cvar": pick(out.best_cvar_index, out.best_cvar), "kernel_ms": out.kernel_ms}
+
+
+METHODS = ("Monte Carlo", "VaR", "CVaR", "MPT", "Equal Weight")
+
+
+def simulate_method(returns_matrix, method="Monte Carlo", n_portfolios=2500, *, annual_factor=12,
+                    risk_free=3.0, min_weights=None, max_weights=None, alpha=0.95, seed=0,
+                    dtype="float32", device=None):
+    """One pass of the app's per-method loop (app.py:682-722) and its pick (672-676, 747).
+
+    Returns {'risks', 'returns', 'weights', 'metrics', 'opt_idx', 'opt_weights'} with the
+    reference's array semantics: 'metrics' holds sharpe ('Monte Carlo', 'MPT', 'Equal Weight'),
+    -var_95 ('VaR') or -cvar_95 ('CVaR') (app.py:717); opt_idx = argmax / argmin / 0.
+    mu / Sigma estimation (app.py:679-680) stays on the host: it runs once per call.
+    """
+    if method not in METHODS:
+        raise KeyError(method)
+    R = np.ascontiguousarray(np.asarray(returns_matrix, dtype=np.float64))
+    T, n = R.shape
+    mu = R.mean(axis=0) * annual_factor
+    sigma = np.atleast_2d(np.cov(R, rowvar=False, ddof=1)) * annual_factor
+    _, npdt = _dtype(dtype)
+    if method == "Equal Weight":
+        w = np.full((1, n), 1.0 / n)
+        r = simulate_portfolios(mu, sigma, 1, weights=w, risk_free=risk_free, min_weights=min_weights,
+                                max_weights=max_weights, dtype=dtype, device=device)
+        if r.n_accepted == 0:
+            raise IndexError("equal weights violate the bounds: the reference's arrays are empty (app.py:687, 747)")
+        return {"risks": r.risks, "returns": r.returns, "weights": r.weights, "metrics": r.sharpes,
+                "opt_idx": 0, "opt_weights": np.asarray(r.weights[0], dtype=np.float64)}
+    r = simulate_portfolios(mu, sigma, int(n_portfolios), risk_free=risk_free, min_weights=min_weights,
+                            max_weights=max_weights, seed=seed, dtype=dtype, device=device)
+    if r.n_accepted == 0:
+        raise ValueError("no portfolio satisfied the bounds (the reference raises at argmax of an empty array, app.py:747)")
+    if method in ("Monte Carlo", "MPT"):
+        metrics, opt = r.sharpes, r.max_sharpe["index"]
+    else:
+        hv = historical_var_cvar(R, r.weights, alpha, dtype=dtype, device=device)
+        if method == "VaR":
+            metrics, opt = -hv["var"], hv["best_var"]["index"]
+        else:
+            metrics, opt = -hv["cvar"], hv["best_cvar"]["index"]
+    return {"risks": r.risks, "returns": r.returns, "weights": r.weights, "metrics": metrics,
+            "opt_idx": int(opt), "opt_weights": np.asarray(r.weights[opt], dtype=np.float64)}

@@ -1,0 +1,90 @@
+"""GPU tier: per-portfolio historical VaR / CVaR (app.py:710-713) and the 'VaR' / 'CVaR' /
+'Equal Weight' method picks (app.py:673-676) against golden vectors from the reference's lines."""
+import numpy as np
+import pytest
+
+from conftest import synthetic_inputs
+from oracle import reference_np as ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mcp():
+    import mcportfolio
+    mcportfolio.build()
+    return mcportfolio
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-9), ("float32", 1e-4)])
+def test_c1_historical_var_cvar_golden(mcp, c1, dtype, tol):
+    """C1: T=365 weekly rows, the 10k reference draws; -var / -cvar arrays and both picks."""
+    out = mcp.historical_var_cvar(c1["returns_matrix"], c1["weights"], 0.95, dtype=dtype)
+    assert np.allclose(-out["var"], c1["neg_var95"], rtol=tol, atol=tol * 0.1)
+    assert np.allclose(-out["cvar"], c1["neg_cvar95"], rtol=tol, atol=tol * 0.1)
+    assert out["best_var"]["index"] == int(c1["opt_var"]) == 4593
+    assert out["best_cvar"]["index"] == int(c1["opt_cvar"]) == 4593
+    assert np.isclose(out["best_var"]["value"], -0.13301122778135846, rtol=tol)
+    assert np.isclose(out["best_cvar"]["value"], -0.1954488675070788, rtol=tol)
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-9), ("float32", 1e-4)])
+def test_c2_historical_golden(mcp, c2, dtype, tol):
+    out = mcp.historical_var_cvar(c2["returns_matrix"], c2["weights"], 0.95, dtype=dtype)
+    assert np.allclose(-out["var"], c2["neg_var95"], rtol=tol, atol=tol * 0.01)
+    assert np.allclose(-out["cvar"], c2["neg_cvar95"], rtol=tol, atol=tol * 0.01)
+    if dtype == "float64":
+        assert out["best_var"]["index"] == int(c2["opt_var"])
+        assert out["best_cvar"]["index"] == int(c2["opt_cvar"])
+
+
+@pytest.mark.parametrize("T", [1, 2, 20, 21, 33, 64, 100, 365, 1000, 2048])
+@pytest.mark.parametrize("alpha", [0.95, 0.99, 0.5])
+def test_historical_shapes_and_alphas(mcp, T, alpha):
+    n = 7
+    rng = np.random.default_rng(T)
+    R = rng.standard_normal((T, n)) * 0.04
+    R[::5] = np.round(R[::5], 2)                       # ties in the series
+    W = rng.dirichlet(np.ones(n), size=257)
+    out = mcp.historical_var_cvar(R, W, alpha, dtype="float64")
+    v, c = ref.historical_var_cvar(R, W, alpha)
+    assert np.allclose(out["var"], v, rtol=1e-10, atol=1e-15)
+    assert np.allclose(out["cvar"], c, rtol=1e-10, atol=1e-15)
+    assert out["best_var"]["index"] == ref.select_method(-v, "VaR")
+    assert out["best_cvar"]["index"] == ref.select_method(-c, "CVaR")
+
+
+def test_historical_device_tensor_and_errors(mcp):
+    import torch
+    rng = np.random.default_rng(0)
+    R = rng.standard_normal((120, 16)) * 0.03
+    W = rng.dirichlet(np.ones(16), size=5000)
+    out = mcp.historical_var_cvar(R, torch.from_numpy(W).cuda(), 0.95, dtype="float64")
+    v, c = ref.historical_var_cvar(R, W, 0.95)
+    assert np.allclose(out["var"].cpu().numpy(), v, rtol=1e-10) and np.allclose(out["cvar"].cpu().numpy(), c, rtol=1e-10)
+    with pytest.raises(ValueError):
+        mcp.historical_var_cvar(R, W[:, :3])
+    with pytest.raises(mcp.McpError, match="2048"):
+        mcp.historical_var_cvar(rng.standard_normal((3000, 2)), np.ones((4, 2)) / 2)
+
+
+def test_methods_like_the_app(mcp, c1):
+    """The five methods of app.py:671-677 on C1's weekly returns."""
+    R = c1["returns_matrix"]
+    for method in ("Monte Carlo", "MPT", "VaR", "CVaR"):
+        out = mcp.simulate_method(R, method, 2500, annual_factor=52, risk_free=3.0, seed=1, dtype="float64")
+        W = out["weights"]
+        assert W.shape == (2500, 2)
+        ret, risk, sharpe = ref.portfolio_metrics(W, c1["mu"], c1["sigma"], 3.0)
+        assert np.allclose(out["risks"], risk, rtol=1e-9)
+        if method in ("Monte Carlo", "MPT"):
+            want = sharpe
+        else:
+            v, c = ref.historical_var_cvar(R, W, 0.95)
+            want = -v if method == "VaR" else -c
+        assert np.allclose(out["metrics"], want, rtol=1e-9, atol=1e-14)
+        assert out["opt_idx"] == ref.select_method(want, method)
+    ew = mcp.simulate_method(R, "Equal Weight", annual_factor=52, risk_free=3.0, dtype="float64")
+    assert np.allclose([ew["risks"][0], ew["returns"][0], ew["metrics"][0]], c1["ew_rf3"], rtol=1e-9)
+    with pytest.raises(IndexError):
+        mcp.simulate_method(R, "Equal Weight", annual_factor=52, min_weights=np.array([0.6, 0.0]))
