@@ -118,7 +118,36 @@ __device__ __forceinline__ void metrics_from(T q, T r, T s, T rf, bool normalise
     }
 }
 
-template <typename T, int NP, int SRC /*0 Philox, 1 supplied*/, bool BOUNDS>
+// K portfolios per thread and iteration: every Sigma / mu operand fetched from the constant
+// bank (LDCU -> uniform register) feeds K FFMAs, the K Philox / lg2 chains are independent
+// (ILP), and the loop / index overhead is paid once per K portfolios.
+template <typename T, int NP> struct SweepK { static constexpr int value = (sizeof(T) == 4) ? (NP <= 16 ? 4 : 2) : (NP <= 16 ? 2 : 1); };
+
+template <typename T, int NP, int K>
+__device__ __forceinline__ void quad_and_dot_k(const SmallArgs<T, NP>& a, const T (&e)[K][NP], T (&q)[K], T (&r)[K]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) { q[k] = (T)0; r[k] = (T)0; }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        T t[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) t[k] = (T)0;
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            const T sij = a.sig[i * (i + 1) / 2 + j];
+#pragma unroll
+            for (int k = 0; k < K; ++k) t[k] = Math<T>::fma(sij, e[k][j], t[k]);
+        }
+        const T mui = a.mu[i];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            q[k] = Math<T>::fma(e[k][i], t[k], q[k]);
+            r[k] = Math<T>::fma(mui, e[k][i], r[k]);
+        }
+    }
+}
+
+template <typename T, int NP, int K, int SRC /*0 Philox, 1 supplied*/, bool BOUNDS>
 __global__ void __launch_bounds__(PF_BLOCK) small_sweep(const __grid_constant__ SmallArgs<T, NP> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -126,87 +155,105 @@ __global__ void __launch_bounds__(PF_BLOCK) small_sweep(const __grid_constant__ 
     T* stage = reinterpret_cast<T*>(smem_raw) + (size_t)warp * 32 * stride;
     const int q32 = 32 / a.n, m32 = 32 % a.n;
 
-    const uint64_t n_tiles = (a.P + PF_BLOCK - 1) / PF_BLOCK;
+    // a "sub-tile" is PF_BLOCK consecutive portfolios (one per thread); a tile is K sub-tiles
+    const uint64_t n_sub = (a.P + PF_BLOCK - 1) / PF_BLOCK;
+    const uint64_t n_tiles = (n_sub + K - 1) / K;
     constexpr uint32_t NONE = 0xffffffffu;
     T best_s = -Math<T>::inf(), best_d = -Math<T>::inf();
-    uint32_t tile_s = NONE, tile_d = NONE;
+    uint32_t sub_s = NONE, sub_d = NONE;
     T rmin = Math<T>::inf(), rmax = -Math<T>::inf();
     uint32_t n_acc = 0;
 
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t warp_row0 = tile * PF_BLOCK + (uint64_t)warp * 32;
-        const uint64_t local = warp_row0 + lane;
-        const bool active = local < a.P;
-        const int rows = warp_row0 >= a.P ? 0 : (int)((a.P - warp_row0) < 32 ? (a.P - warp_row0) : 32);
-
-        T e[NP];
-        T s = (T)1;
-        bool accepted = active;
-        if (SRC == 1) {
-            // coalesced warp load of rows*n contiguous values into padded smem, then row -> registers
-            const T* src = a.w_in + warp_row0 * (uint64_t)a.n;
-            const int total = rows * a.n;
-            int r = lane / a.n, c = lane % a.n;
-            for (int f = lane; f < total; f += 32) {
-                stage[r * stride + c] = src[f];
-                r += q32; c += m32;
-                if (c >= a.n) { c -= a.n; ++r; }
-            }
-            __syncwarp();
+        T e[K][NP];
+        T s[K];
+        bool accepted[K];
+        const uint64_t local0 = tile * (uint64_t)(K * PF_BLOCK) + threadIdx.x;      // sub-tile k: + k * PF_BLOCK
 #pragma unroll
-            for (int i = 0; i < NP; ++i) e[i] = (active && i < a.n) ? stage[lane * stride + i] : (T)0;
-            __syncwarp();
-            if (BOUNDS) accepted = active && (in_bounds<T, NP>(a, e, (T)1) || a.keep_last != 0);
-        } else {
-            if (active) accepted = draw_accepted<T, NP, BOUNDS>(a, a.first + local, e, s);
-            else {
+        for (int k = 0; k < K; ++k) {
+            const uint64_t local = local0 + (uint64_t)k * PF_BLOCK;
+            const bool active = local < a.P;
+            s[k] = (T)1;
+            accepted[k] = active;
+            if (SRC == 1) {
+                // coalesced warp load of rows*n contiguous values into padded smem, then row -> registers
+                const uint64_t warp_row0 = local - lane;
+                const int rows = warp_row0 >= a.P ? 0 : (int)((a.P - warp_row0) < 32 ? (a.P - warp_row0) : 32);
+                const T* src = a.w_in + warp_row0 * (uint64_t)a.n;
+                const int total = rows * a.n;
+                int rr = lane / a.n, cc = lane % a.n;
+                for (int f = lane; f < total; f += 32) {
+                    stage[rr * stride + cc] = src[f];
+                    rr += q32; cc += m32;
+                    if (cc >= a.n) { cc -= a.n; ++rr; }
+                }
+                __syncwarp();
 #pragma unroll
-                for (int i = 0; i < NP; ++i) e[i] = (T)0;
+                for (int i = 0; i < NP; ++i) e[k][i] = (active && i < a.n) ? stage[lane * stride + i] : (T)0;
+                __syncwarp();
+                if (BOUNDS) accepted[k] = active && (in_bounds<T, NP>(a, e[k], (T)1) || a.keep_last != 0);
+            } else if (BOUNDS) {
+                if (active) accepted[k] = draw_accepted<T, NP, true>(a, a.first + local, e[k], s[k]);
+                else {
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) e[k][i] = (T)0;
+                }
+            } else {
+                // no rejection loop: draw unconditionally (tail threads draw too, results unused)
+                draw_accepted<T, NP, false>(a, a.first + local, e[k], s[k]);
             }
         }
 
-        T q, r, ret, risk, sharpe;
-        quad_and_dot<T, NP>(a, e, q, r);
-        metrics_from<T>(q, r, s, a.rf, SRC == 1, ret, risk, sharpe);
+        T q[K], r[K];
+        quad_and_dot_k<T, NP, K>(a, e, q, r);
 
-        if (accepted) {
-            ++n_acc;
-            if (sharpe > best_s) { best_s = sharpe; tile_s = (uint32_t)tile; }
-            const T d = -Math<T>::abs(risk - a.target);
-            if (d > best_d) { best_d = d; tile_d = (uint32_t)tile; }
-            rmin = risk < rmin ? risk : rmin;
-            rmax = risk > rmax ? risk : rmax;
-        }
-
-        // ---- optional write-back (app.py:719-722) ----
-        if (active) {
-            const T nanv = Math<T>::nan();
-            if (a.ret_out != nullptr) a.ret_out[local] = accepted ? ret : nanv;
-            if (a.risk_out != nullptr) a.risk_out[local] = accepted ? risk : nanv;
-            if (a.sharpe_out != nullptr) a.sharpe_out[local] = accepted ? sharpe : nanv;
-        }
-        if (a.acc_out != nullptr && active) a.acc_out[local] = accepted ? 1 : 0;
-        if (a.w_out != nullptr) {
-            const T inv = SRC == 1 ? (T)1 : Math<T>::rcp(s);
 #pragma unroll
-            for (int i = 0; i < NP; ++i)
-                if (i < a.n) stage[lane * stride + i] = e[i] * inv;
-            __syncwarp();
-            T* dst = a.w_out + warp_row0 * (uint64_t)a.n;
-            const int total = rows * a.n;
-            int rr = lane / a.n, cc = lane % a.n;
-            for (int f = lane; f < total; f += 32) {
-                dst[f] = stage[rr * stride + cc];
-                rr += q32; cc += m32;
-                if (cc >= a.n) { cc -= a.n; ++rr; }
+        for (int k = 0; k < K; ++k) {
+            const uint64_t local = local0 + (uint64_t)k * PF_BLOCK;
+            const bool active = local < a.P;
+            T ret, risk, sharpe;
+            metrics_from<T>(q[k], r[k], s[k], a.rf, SRC == 1, ret, risk, sharpe);
+            if (accepted[k]) {
+                const uint32_t sub = (uint32_t)(tile * K + k);
+                ++n_acc;
+                if (sharpe > best_s) { best_s = sharpe; sub_s = sub; }
+                const T d = -Math<T>::abs(risk - a.target);
+                if (d > best_d) { best_d = d; sub_d = sub; }
+                rmin = risk < rmin ? risk : rmin;
+                rmax = risk > rmax ? risk : rmax;
             }
-            __syncwarp();
+            // ---- optional write-back (app.py:719-722) ----
+            if (active) {
+                const T nanv = Math<T>::nan();
+                if (a.ret_out != nullptr) a.ret_out[local] = accepted[k] ? ret : nanv;
+                if (a.risk_out != nullptr) a.risk_out[local] = accepted[k] ? risk : nanv;
+                if (a.sharpe_out != nullptr) a.sharpe_out[local] = accepted[k] ? sharpe : nanv;
+                if (a.acc_out != nullptr) a.acc_out[local] = accepted[k] ? 1 : 0;
+            }
+            if (a.w_out != nullptr) {
+                const T inv = SRC == 1 ? (T)1 : Math<T>::rcp(s[k]);
+#pragma unroll
+                for (int i = 0; i < NP; ++i)
+                    if (i < a.n) stage[lane * stride + i] = e[k][i] * inv;
+                __syncwarp();
+                const uint64_t warp_row0 = local - lane;
+                const int rows = warp_row0 >= a.P ? 0 : (int)((a.P - warp_row0) < 32 ? (a.P - warp_row0) : 32);
+                T* dst = a.w_out + warp_row0 * (uint64_t)a.n;
+                const int total = rows * a.n;
+                int rr = lane / a.n, cc = lane % a.n;
+                for (int f = lane; f < total; f += 32) {
+                    dst[f] = stage[rr * stride + cc];
+                    rr += q32; cc += m32;
+                    if (cc >= a.n) { cc -= a.n; ++rr; }
+                }
+                __syncwarp();
+            }
         }
     }
 
     // ---- CTA reduction: (key, global index) argmax with first-occurrence tie-break ----
-    uint64_t idx_s = tile_s == NONE ? MCP_NO_INDEX : a.first + (uint64_t)tile_s * PF_BLOCK + threadIdx.x;
-    uint64_t idx_d = tile_d == NONE ? MCP_NO_INDEX : a.first + (uint64_t)tile_d * PF_BLOCK + threadIdx.x;
+    uint64_t idx_s = sub_s == NONE ? MCP_NO_INDEX : a.first + (uint64_t)sub_s * PF_BLOCK + threadIdx.x;
+    uint64_t idx_d = sub_d == NONE ? MCP_NO_INDEX : a.first + (uint64_t)sub_d * PF_BLOCK + threadIdx.x;
     warp_argmax<T>(best_s, idx_s);
     warp_argmax<T>(best_d, idx_d);
     rmin = warp_min<T>(rmin);
@@ -307,20 +354,18 @@ static void fill_small_args(const PfJob& job, SmallArgs<T, NP>& a) {
     a.n_accepted = job.n_accepted;
 }
 
-template <typename T, int NP>
-int pf_small_launch_t(mcp_context* h, PfJob& job) {
-    SmallArgs<T, NP> a;
-    fill_small_args<T, NP>(job, a);
+template <typename T, int NP, int K>
+static int small_launch_k(mcp_context* h, PfJob& job, const SmallArgs<T, NP>& a) {
     void (*kern)(SmallArgs<T, NP>) = nullptr;
-    if (job.w_in) kern = job.bounds ? small_sweep<T, NP, 1, true> : small_sweep<T, NP, 1, false>;
-    else kern = job.bounds ? small_sweep<T, NP, 0, true> : small_sweep<T, NP, 0, false>;
+    if (job.w_in) kern = job.bounds ? small_sweep<T, NP, K, 1, true> : small_sweep<T, NP, K, 1, false>;
+    else kern = job.bounds ? small_sweep<T, NP, K, 0, true> : small_sweep<T, NP, K, 0, false>;
     const bool staging = job.w_in != nullptr || job.w_out != nullptr;
     const size_t smem = staging ? (size_t)(PF_BLOCK / 32) * 32 * (job.n | 1) * sizeof(T) : 0;
     if (smem > 48 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     MCP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PF_BLOCK, smem));
     if (per_sm < 1) return mcp_fail(h, MCP_ERR_CUDA, "small_sweep<N=%d>: zero occupancy (smem %zu B)", NP, smem);
-    const uint64_t n_tiles = (job.P + PF_BLOCK - 1) / PF_BLOCK;
+    const uint64_t n_tiles = ((job.P + PF_BLOCK - 1) / PF_BLOCK + K - 1) / K;
     uint64_t grid = (uint64_t)h->prop.multiProcessorCount * per_sm;
     if (grid > n_tiles) grid = n_tiles;
     if (grid > (uint64_t)job.max_blocks) grid = job.max_blocks;
@@ -330,6 +375,17 @@ int pf_small_launch_t(mcp_context* h, PfJob& job) {
     MCP_CUDA(h, cudaGetLastError());
     h->launches++;
     return MCP_OK;
+}
+
+template <typename T, int NP>
+int pf_small_launch_t(mcp_context* h, PfJob& job) {
+    SmallArgs<T, NP> a;
+    fill_small_args<T, NP>(job, a);
+    // K portfolios per thread only when nothing streams through HBM: with supplied weights or
+    // weight write-back the kernel is memory-side bound and the extra registers only cost occupancy
+    constexpr int K = SweepK<T, NP>::value;
+    if (K > 1 && job.w_in == nullptr && job.w_out == nullptr) return small_launch_k<T, NP, K>(h, job, a);
+    return small_launch_k<T, NP, 1>(h, job, a);
 }
 
 template <typename T, int NP>
