@@ -52,7 +52,7 @@ def _deps_digest():
                 with open(os.path.join(root, f), "rb") as fh:
                     h.update(f.encode())
                     h.update(fh.read())
-    h.update(" ".join(ARCH + CFLAGS).encode())
+    h.update(" ".join(a for a in ARCH + CFLAGS if a != INCLUDE).encode())     # path-independent: the tree moves
     return h.hexdigest()
 
 
@@ -72,8 +72,15 @@ def _compile(tu, verbose):
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    import fcntl
     os.makedirs(BUILD, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
+    with open(os.path.join(BUILD, ".lock"), "w") as lock:        # one builder at a time (torchrun ranks)
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        return _build_locked(force, verbose)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
     stamp = os.path.join(BUILD, "stamp")
     digest = _deps_digest()
     if not force and os.path.isfile(LIB) and os.path.isfile(stamp) and open(stamp).read() == digest:
