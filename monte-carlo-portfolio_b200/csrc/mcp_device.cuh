@@ -114,6 +114,23 @@ __device__ __forceinline__ T warp_max(T v) {
     return v;
 }
 
+// metrics from un-normalised weights (s = their sum; s = 1 for supplied weights)
+template <typename T>
+__device__ __forceinline__ void metrics_from(T q, T r, T s, T rf, bool normalised, T& ret, T& risk, T& sharpe) {
+    if (normalised) {
+        ret = r;
+        risk = Math<T>::sqrt(q);
+        sharpe = risk > (T)0 ? (r - rf) * Math<T>::rcp(risk) : (T)0;
+    } else {
+        const T inv = Math<T>::rcp(s);
+        const T rs = Math<T>::rsqrt(q);
+        ret = r * inv;
+        risk = q * rs * inv;                       // sqrt(q) / s
+        sharpe = q > (T)0 ? (r - rf * s) * rs : (T)0;   // (ret - rf) / risk
+        if (!(q > (T)0)) risk = (T)0;
+    }
+}
+
 // order-preserving float -> unsigned key (ascending), and back
 __device__ __host__ __forceinline__ uint32_t f32_to_key(uint32_t b) { return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u); }
 __device__ __host__ __forceinline__ uint32_t key_to_f32(uint32_t k) { return k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu); }

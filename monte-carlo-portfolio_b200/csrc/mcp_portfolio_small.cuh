@@ -101,23 +101,6 @@ __device__ __forceinline__ bool draw_accepted(const SmallArgs<T, NP>& a, uint64_
     return ok || (a.keep_last != 0);
 }
 
-// metrics from un-normalised weights (s = their sum; s = 1 for supplied weights)
-template <typename T>
-__device__ __forceinline__ void metrics_from(T q, T r, T s, T rf, bool normalised, T& ret, T& risk, T& sharpe) {
-    if (normalised) {
-        ret = r;
-        risk = Math<T>::sqrt(q);
-        sharpe = risk > (T)0 ? (r - rf) * Math<T>::rcp(risk) : (T)0;
-    } else {
-        const T inv = Math<T>::rcp(s);
-        const T rs = Math<T>::rsqrt(q);
-        ret = r * inv;
-        risk = q * rs * inv;                       // sqrt(q) / s
-        sharpe = q > (T)0 ? (r - rf * s) * rs : (T)0;   // (ret - rf) / risk
-        if (!(q > (T)0)) risk = (T)0;
-    }
-}
-
 // K portfolios per thread and iteration: every Sigma / mu operand fetched from the constant
 // bank (LDCU -> uniform register) feeds K FFMAs, the K Philox / lg2 chains are independent
 // (ILP), and the loop / index overhead is paid once per K portfolios.

@@ -258,3 +258,73 @@ def test_host_pipeline_many_chunks(mcp):
     assert np.isclose(r.max_sharpe["sharpe"], sharpe.max(), rtol=1e-5)
     assert r.max_sharpe["index"] == int(np.argmax(r.sharpes))
     assert r.target_risk["index"] == int(np.argmin(np.abs(r.risks - np.float32(0.30))))
+
+
+# ---- N > 32: tiled FP32 kernel (N <= 256) and the generic warp-per-portfolio kernel ----------
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("n", [33, 48, 64, 100, 200, 256, 300])
+def test_large_n_supplied_weights(mcp, n, dtype):
+    mu, sigma = synthetic_inputs(n, seed=n)
+    P = 1000 if n <= 256 else 300
+    W = np.random.RandomState(n).dirichlet(np.ones(n), size=P)
+    r = mcp.simulate_portfolios(mu, sigma, P, weights=W, risk_free=0.03, risk_target=0.03, dtype=dtype)
+    check_against_oracle(r, W, mu, sigma, 0.03, 0.03, dtype, same_index=(dtype == "float64"))
+
+
+@pytest.mark.parametrize("dtype,atol", [("float32", 1e-6), ("float64", 1e-12)])
+@pytest.mark.parametrize("n", [40, 256, 260])
+def test_large_n_rng_matches_generator_restatement(mcp, n, dtype, atol):
+    mu, sigma = synthetic_inputs(n, seed=1)
+    P, first, seed = 777, 9_876_543_210, 42
+    r = mcp.simulate_portfolios(mu, sigma, P, risk_free=0.03, seed=seed, first_index=first, dtype=dtype)
+    W, valid = philox_np.dirichlet_weights(first, P, n, seed, dtype)
+    assert r.n_accepted == P and np.allclose(r.weights, W, atol=atol)
+    tol = RTOL[dtype]
+    want = ref.evaluate(W, mu, sigma, 0.03, 0.30)
+    assert np.allclose(r.risks, want["risks"], rtol=tol) and np.allclose(r.sharpes, want["sharpes"], rtol=tol, atol=tol)
+    assert np.isclose(r.max_sharpe["sharpe"], want["max_sharpe"]["sharpe"], rtol=tol)
+    i = r.max_sharpe["index"]
+    assert r.max_sharpe["sharpe"] == float(r.sharpes[i]) and r.max_sharpe["risk"] == float(r.risks[i])
+    assert np.allclose(r.max_sharpe["weights"], r.weights[i], atol=0, rtol=0)
+    j = r.target_risk["index"]
+    assert j == int(np.argmin(np.abs(r.risks - r.risks.dtype.type(0.30))))
+    if dtype == "float64":
+        assert i == want["max_sharpe"]["index"] and j == want["target_risk"]["index"]
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_large_n_bounds_rejection(mcp, dtype):
+    n = 64
+    mu, sigma = synthetic_inputs(n)
+    hi = np.full(n, 0.07)                      # max weight 7 %: a flat-Dirichlet draw at N=64 often violates it
+    P, seed = 900, 3
+    r = mcp.simulate_portfolios(mu, sigma, P, max_weights=hi, seed=seed, dtype=dtype, max_tries=3, risk_free=0.03)
+    W, valid = philox_np.dirichlet_weights(0, P, n, seed, dtype, None, hi, max_tries=3)
+    assert 0 < valid.sum() < P
+    acc = r.accepted.astype(bool)
+    margin = np.abs(W - hi).min(1)
+    differ = acc != valid
+    assert differ.sum() <= 2 and np.all(margin[differ] < 1e-5)
+    both = acc & valid
+    assert np.allclose(r.weights[np.cumsum(acc)[both] - 1], W[both], atol=1e-6 if dtype == "float32" else 1e-12)
+    assert r.weights.max() <= 0.07 + 1e-6 and r.n_accepted == acc.sum()
+    want = ref.evaluate(np.asarray(r.weights, dtype=np.float64), mu, sigma, 0.03, 0.30)
+    assert np.allclose(r.sharpes, want["sharpes"], rtol=RTOL[dtype], atol=RTOL[dtype])
+    assert r.max_sharpe["index"] == int(np.argmax(r.sharpes))
+
+
+def test_large_n_sharding_invariance_and_tail_tiles(mcp):
+    n = 256
+    mu, sigma = synthetic_inputs(n)
+    P = 20_011                                  # not a multiple of the 64-portfolio tile
+    whole = mcp.simulate_portfolios(mu, sigma, P, risk_free=0.03, seed=8, return_arrays=False)
+    cuts = [0, 63, 64, 10_000, P]
+    parts = [mcp.simulate_portfolios(mu, sigma, b - a, risk_free=0.03, seed=8, first_index=a, return_arrays=False)
+             for a, b in zip(cuts[:-1], cuts[1:])]
+    best = max(parts, key=lambda r: (r.max_sharpe["key"], -r.max_sharpe["global_index"]))
+    assert best.max_sharpe["global_index"] == whole.max_sharpe["global_index"]
+    assert best.max_sharpe["sharpe"] == whole.max_sharpe["sharpe"]
+    near = min(parts, key=lambda r: (r.target_risk["key"], r.target_risk["global_index"]))
+    assert near.target_risk["global_index"] == whole.target_risk["global_index"]
+    assert sum(p.n_accepted for p in parts) == P
