@@ -34,6 +34,7 @@ def translation_units():
     tus = [("mcp_context", "mcp_context.cu", []),
            ("mcp_portfolio", "mcp_portfolio.cu", []),
            ("mcp_portfolio_large", "mcp_portfolio_large.cu", []),
+           ("mcp_envelope", "mcp_envelope.cu", []),
            ("mcp_paths", "mcp_paths.cu", []),
            ("mcp_quantile", "mcp_quantile.cu", []),
            ("mcp_historical", "mcp_historical.cu", [])]

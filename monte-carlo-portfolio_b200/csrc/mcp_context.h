@@ -25,8 +25,9 @@ struct mcp_context {
     uint64_t launches = 0;
     double last_ms = 0.0;
     // device scratch (grow-only): [0] candidates/records, [1..2] pipeline slot inputs,
-    // [3..4] pipeline slot outputs, [5] quantile histograms, [6] misc
-    mcp_scratch dev[8];
+    // [3..4] pipeline slot outputs, [5] quantile histograms, [6] kernel constants, [7] replay,
+    // [8] envelope bins, [9..10] envelope risk/return scratch per slot
+    mcp_scratch dev[12];
     mcp_scratch pinned[4];
 };
 

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "mcp_device.cuh"
 #include "mcp_portfolio.h"
@@ -119,6 +120,14 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
         s->index = MCP_NO_INDEX;
         s->key = s->ret = s->risk = s->sharpe = NAN;
     }
+    const int K = p->n_bins;
+    MCP_REQUIRE(h, K >= 0 && K <= ENV_MAX_BINS, "mcp_portfolios: n_bins=%d out of range [0, %d]", K, ENV_MAX_BINS);
+    if (K > 0) {
+        MCP_REQUIRE(h, out->bin_best_return && out->bin_best_index, "mcp_portfolios: envelope requested but bin outputs are NULL");
+        MCP_REQUIRE(h, std::isfinite(p->risk_lo) && std::isfinite(p->risk_hi) && p->risk_hi > p->risk_lo,
+                    "mcp_portfolios: envelope needs finite risk_lo < risk_hi");
+        for (int b = 0; b < K; ++b) { out->bin_best_return[b] = -INFINITY; out->bin_best_index[b] = MCP_NO_INDEX; }
+    }
     if (P == 0) return MCP_OK;          // empty arrays, no selection (app.py:719-722 on empty lists)
 
     // ---- scratch layout (device slot 0) ----
@@ -137,6 +146,19 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
     unsigned long long* d_acc = (unsigned long long*)(base + off_acc);
     double* d_rec = (double*)(base + off_rec);
     void* d_rows = base + off_rows;
+    // envelope bins: running (f*) and per-chunk (c*) sets for each pipeline slot
+    unsigned long long* env = nullptr;
+    if (K > 0) MCP_CHECK(mcp_dev_reserve(h, 8, sizeof(unsigned long long) * 8 * (size_t)K, (void**)&env));
+    auto fmax = [&](int s) { return env + (size_t)(0 + s) * K; };
+    auto fidx = [&](int s) { return env + (size_t)(2 + s) * K; };
+    auto cmax = [&](int s) { return env + (size_t)(4 + s) * K; };
+    auto cidx = [&](int s) { return env + (size_t)(6 + s) * K; };
+    // bins one finished chunk (its risks / returns are on the device) into slot s's running bins
+    auto envelope_chunk = [&](int s, const PfJob& j, cudaStream_t ss) -> int {
+        MCP_CHECK(env_reset(h, K, cmax(s), cidx(s), ss));
+        MCP_CHECK(env_chunk(h, p->dtype, j.risk_out, j.ret_out, j.P, j.first, p->risk_lo, p->risk_hi, K, cmax(s), cidx(s), ss));
+        return env_fold(h, K, cmax(s), cidx(s), fmax(s), fidx(s), ss);
+    };
 
     PfJob job;
     job.n = N;
@@ -156,30 +178,47 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
 
     cudaStream_t st = h->stream;
     MCP_CUDA(h, cudaMemsetAsync(d_acc, 0, 8, st));
+    if (K > 0) {
+        MCP_CHECK(env_reset(h, K, fmax(0), fidx(0), st));
+        MCP_CHECK(env_reset(h, K, fmax(1), fidx(1), st));
+    }
     PfCand* final_cand = running + 2;
     double kernel_ms = 0;
+    bool env_slot1 = false;
 
     if (p->space == MCP_DEVICE) {
-        job.first = p->first_index;
-        job.P = P;
-        job.w_in = p->weights_in;
-        job.w_out = out->weights;
-        job.ret_out = out->returns;
-        job.risk_out = out->risks;
-        job.sharpe_out = out->sharpes;
-        job.acc_out = out->accepted;
+        // one launch, unless the envelope needs (risk, return) scratch: then chunks of 2^26
+        const bool env_scratch = K > 0 && (!out->returns || !out->risks);
+        const uint64_t chunk = env_scratch ? std::min<uint64_t>(P, 1ull << 26) : P;
+        unsigned char* scratch = nullptr;
+        if (env_scratch) MCP_CHECK(mcp_dev_reserve(h, 9, 2 * chunk * es, (void**)&scratch));
         job.cands = cands;
         job.stream = st;
         MCP_CUDA(h, cudaEventRecord(h->ev[0], st));
-        MCP_CHECK(pf_launch(h, job));
+        for (uint64_t r0 = 0; r0 < P; r0 += chunk) {
+            const uint64_t rows = std::min<uint64_t>(chunk, P - r0);
+            auto at = [&](void* q, size_t row_bytes) -> void* { return q ? (unsigned char*)q + r0 * row_bytes : nullptr; };
+            job.first = p->first_index + r0;
+            job.P = rows;
+            job.w_in = p->weights_in ? (const unsigned char*)p->weights_in + r0 * N * es : nullptr;
+            job.w_out = at(out->weights, (size_t)N * es);
+            job.ret_out = env_scratch ? (void*)scratch : at(out->returns, es);
+            job.risk_out = env_scratch ? (void*)(scratch + chunk * es) : at(out->risks, es);
+            job.sharpe_out = at(out->sharpes, es);
+            job.acc_out = (uint8_t*)at(out->accepted, 1);
+            MCP_CHECK(pf_launch(h, job));
+            MCP_CHECK(pf_reduce_launch(h, cands, job.blocks_used, running, r0 > 0 ? 1 : 0, st));
+            if (K > 0) MCP_CHECK(envelope_chunk(0, job, st));
+        }
         MCP_CUDA(h, cudaEventRecord(h->ev[1], st));
-        MCP_CHECK(pf_reduce_launch(h, cands, job.blocks_used, final_cand, 0, st));
+        MCP_CHECK(pf_reduce_launch(h, running, 1, final_cand, 0, st));
     } else {
         // ---- HOST space: two-slot chunk pipeline ----
         MCP_CUDA(h, cudaStreamSynchronize(st));           // the memset above must precede the side streams
         const bool want_w = out->weights != nullptr;
         const size_t in_row = supplied ? (size_t)N * es : 0;
-        const size_t out_row = (want_w ? (size_t)N * es : 0) + (out->returns ? es : 0) + (out->risks ? es : 0) +
+        const bool want_ret = out->returns != nullptr || K > 0, want_risk = out->risks != nullptr || K > 0;
+        const size_t out_row = (want_w ? (size_t)N * es : 0) + (want_ret ? es : 0) + (want_risk ? es : 0) +
                                (out->sharpes ? es : 0) + (out->accepted ? 1 : 0);
         uint64_t chunk = P;
         const size_t budget = (size_t)96 << 20;            // bytes per slot and direction
@@ -218,8 +257,8 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
                 return q;
             };
             unsigned char* dw = carve(want_w, (size_t)N * es);
-            unsigned char* dr = carve(out->returns != nullptr, es);
-            unsigned char* dk = carve(out->risks != nullptr, es);
+            unsigned char* dr = carve(want_ret, es);
+            unsigned char* dk = carve(want_risk, es);
             unsigned char* ds = carve(out->sharpes != nullptr, es);
             unsigned char* da = carve(out->accepted != nullptr, 1);
             job.first = p->first_index + r0;
@@ -237,9 +276,13 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
             MCP_CUDA(h, cudaEventRecord(h->ev[2 * s + 1], ss));
             timed[s] = true;
             MCP_CHECK(pf_reduce_launch(h, job.cands, job.blocks_used, running + s, used[s] ? 1 : 0, ss));
+            if (K > 0) {
+                MCP_CHECK(envelope_chunk(s, job, ss));
+                env_slot1 = env_slot1 || (s == 1 && n_chunks > 1);
+            }
             if (dw) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->weights + r0 * N * es, dw, rows * N * es, cudaMemcpyDeviceToHost, ss));
-            if (dr) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->returns + r0 * es, dr, rows * es, cudaMemcpyDeviceToHost, ss));
-            if (dk) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->risks + r0 * es, dk, rows * es, cudaMemcpyDeviceToHost, ss));
+            if (dr && out->returns) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->returns + r0 * es, dr, rows * es, cudaMemcpyDeviceToHost, ss));
+            if (dk && out->risks) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->risks + r0 * es, dk, rows * es, cudaMemcpyDeviceToHost, ss));
             if (ds) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->sharpes + r0 * es, ds, rows * es, cudaMemcpyDeviceToHost, ss));
             if (da) MCP_CUDA(h, cudaMemcpyAsync(out->accepted + r0, da, rows, cudaMemcpyDeviceToHost, ss));
             used[s] = true;
@@ -272,6 +315,18 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
     out->n_accepted = n_acc;
     out->kernel_ms = kernel_ms;
     h->last_ms = kernel_ms;
+    if (K > 0) {
+        if (env_slot1) MCP_CHECK(env_fold(h, K, fmax(1), fidx(1), fmax(0), fidx(0), st));
+        std::vector<unsigned long long> hb(2 * (size_t)K);
+        MCP_CUDA(h, cudaMemcpyAsync(hb.data(), fmax(0), sizeof(unsigned long long) * K, cudaMemcpyDeviceToHost, st));
+        MCP_CUDA(h, cudaMemcpyAsync(hb.data() + K, fidx(0), sizeof(unsigned long long) * K, cudaMemcpyDeviceToHost, st));
+        MCP_CUDA(h, cudaStreamSynchronize(st));
+        for (int b = 0; b < K; ++b) {
+            if (hb[b] == 0ull) continue;                 // empty bin: -inf / MCP_NO_INDEX
+            out->bin_best_return[b] = mcp_key_to_value(hb[b], p->dtype);
+            out->bin_best_index[b] = hb[K + b];
+        }
+    }
     if (n_acc == 0 || fin.idx_s == MCP_NO_INDEX) return MCP_OK;
     out->risk_min = fin.rmin;
     out->risk_max = fin.rmax;

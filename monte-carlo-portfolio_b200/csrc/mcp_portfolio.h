@@ -63,6 +63,14 @@ struct PfReplay {
 // merges n per-CTA candidates (and the running record when accumulate != 0) into *acc
 int pf_reduce_launch(mcp_context* h, const PfCand* cands, int n, PfCand* acc, int accumulate, cudaStream_t st);
 
+// frontier envelope post-pass (mcp_envelope.cu): bins are (order-preserving return key, global index)
+constexpr int ENV_MAX_BINS = 4096;
+int env_reset(mcp_context* h, int K, unsigned long long* mx, unsigned long long* ix, cudaStream_t st);
+int env_chunk(mcp_context* h, int dtype, const void* risk, const void* ret, uint64_t n, uint64_t base, double lo, double hi, int K,
+              unsigned long long* cmax, unsigned long long* cidx, cudaStream_t st);
+int env_fold(mcp_context* h, int K, const unsigned long long* cmax, const unsigned long long* cidx, unsigned long long* fmax,
+             unsigned long long* fidx, cudaStream_t st);
+
 int pf_small_launch(mcp_context* h, PfJob& job);
 int pf_small_replay(mcp_context* h, const PfJob& job, const PfReplay& rp);
 int pf_large_launch(mcp_context* h, PfJob& job);

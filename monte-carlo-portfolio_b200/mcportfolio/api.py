@@ -178,7 +178,7 @@ def _selection_dict(sel, wbuf, first_index, positions):
 def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, risk_free=0.0, risk_target=0.30,
                         min_weights=None, max_weights=None, weights=None, seed=0, dtype="float32",
                         return_arrays=True, first_index=0, keep_last=False, max_tries=100,
-                        device=None, out=None) -> PortfolioResult:
+                        device=None, out=None, n_bins=0, risk_range=None) -> PortfolioResult:
     """Random-weight portfolio sweep: the loop of app.py:699-722 in one call.
 
     weights=None      flat-Dirichlet weights generated in-kernel (Philox4x32-10, counter =
@@ -192,6 +192,8 @@ def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, risk_free=0.0
     return_arrays     False: selections only, zero HBM write-back (C3 sizes).
     out               optional dict of preallocated arrays ('weights', 'returns', 'risks',
                       'sharpes', 'accepted') to reuse pinned buffers across calls.
+    n_bins, risk_range  frontier envelope: per risk bin over [lo, hi] the maximum return and the
+                      first global index attaining it -> result.extra['envelope'].
     Returns a PortfolioResult; arrays hold accepted portfolios only (P' <= P rows).
     """
     mu, sigma, n = _mu_sigma(mean_returns, cov_matrix)
@@ -232,6 +234,11 @@ def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, risk_free=0.0
     params.space = MCP_DEVICE if device_mode or return_arrays == "device" else MCP_HOST
     params.weights_in = _ptr(w_in)
     params.weights_recheck = _ptr(recheck)
+    n_bins = int(n_bins)
+    if n_bins:
+        if risk_range is None or not (np.isfinite(risk_range[0]) and np.isfinite(risk_range[1]) and risk_range[1] > risk_range[0]):
+            raise ValueError("the envelope needs risk_range=(lo, hi) with finite lo < hi")
+        params.n_bins, params.risk_lo, params.risk_hi = n_bins, float(risk_range[0]), float(risk_range[1])
 
     res = PortfolioOut()
     arrays = {}
@@ -252,6 +259,10 @@ def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, risk_free=0.0
                 arrays[name] = a if a is not None else np.empty(shape, dtype=dt)
         for name in ("weights", "returns", "risks", "sharpes", "accepted"):
             setattr(res, name, _ptr(arrays[name]))
+    bin_ret = np.empty(n_bins)
+    bin_idx = np.empty(n_bins, dtype=np.uint64)
+    if n_bins:
+        res.bin_best_return, res.bin_best_index = bin_ret.ctypes.data, bin_idx.ctypes.data
     ws = np.empty(n)
     wt = np.empty(n)
     res.max_sharpe.weights = ws.ctypes.data
@@ -277,13 +288,19 @@ def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, risk_free=0.0
             arrays[name] = arrays[name][mask]
     elif return_arrays:
         positions = _Identity()
+    extra = {}
+    if n_bins:
+        idx = bin_idx.astype(np.int64)
+        idx[bin_idx == np.uint64(MCP_NO_INDEX)] = -1
+        extra["envelope"] = {"edges": np.linspace(params.risk_lo, params.risk_hi, n_bins + 1),
+                             "best_return": bin_ret, "best_index": idx}
     return PortfolioResult(
         risks=arrays.get("risks"), returns=arrays.get("returns"), weights=arrays.get("weights"),
         sharpes=arrays.get("sharpes"),
         max_sharpe=_selection_dict(res.max_sharpe, ws, int(first_index), positions),
         target_risk=_selection_dict(res.target_risk, wt, int(first_index), positions),
         n_requested=P, n_accepted=n_acc, risk_range=(res.risk_min, res.risk_max),
-        kernel_ms=res.kernel_ms, accepted=arrays.get("accepted"))
+        kernel_ms=res.kernel_ms, accepted=arrays.get("accepted"), extra=extra)
 
 
 class _Identity:
@@ -308,6 +325,27 @@ def efficient_frontier(mean_returns, cov_matrix, points=200, min_weights=None, m
     results[1] = r.returns
     results[2] = r.sharpes
     return results, np.asarray(r.weights, dtype=np.float64)
+
+
+def frontier_envelope(mean_returns, cov_matrix, n_portfolios, n_bins=512, *, risk_range=None, **kw):
+    """Efficient-frontier envelope binned by risk (config C5), plus the two picks.
+
+    Replaces the reference's scatter of every portfolio (app.py:726-736).  With risk_range=None
+    a first sweep (no write-back) finds the attained [risk_min, risk_max]; the counter-based
+    generator then reproduces exactly the same portfolios for the binning sweep.
+    Returns the PortfolioResult of the binning sweep; result.extra['envelope'] holds
+    'edges' (n_bins + 1), 'best_return' (-inf for empty bins) and 'best_index' (global, -1 if empty).
+    """
+    kw.setdefault("return_arrays", False)
+    if risk_range is None:
+        probe = simulate_portfolios(mean_returns, cov_matrix, n_portfolios, **{**kw, "return_arrays": False})
+        if probe.n_accepted == 0:
+            raise ValueError("no portfolio satisfied the bounds; the envelope is empty")
+        lo, hi = probe.risk_range
+        if not hi > lo:
+            hi = lo + max(abs(lo), 1.0) * 1e-6
+        risk_range = (lo, hi)
+    return simulate_portfolios(mean_returns, cov_matrix, n_portfolios, n_bins=n_bins, risk_range=risk_range, **kw)
 
 
 # ------------------------------------------------------------------------------------------

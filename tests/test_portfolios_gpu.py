@@ -328,3 +328,61 @@ def test_large_n_sharding_invariance_and_tail_tiles(mcp):
     near = min(parts, key=lambda r: (r.target_risk["key"], r.target_risk["global_index"]))
     assert near.target_risk["global_index"] == whole.target_risk["global_index"]
     assert sum(p.n_accepted for p in parts) == P
+
+
+# ---- frontier envelope (config C5) -------------------------------------------
+
+def _envelope_oracle(risks, returns, n_bins, lo, hi, dtype):
+    """oracle.paths_np.envelope evaluated in the kernel's arithmetic type for the bin index."""
+    T = np.float32 if dtype == "float32" else np.float64
+    from oracle import paths_np
+    r = np.asarray(risks, dtype=T)
+    scale = T(n_bins / (hi - lo))
+    b = np.floor((r - T(lo)) * scale).astype(np.int64)
+    b[(r == T(hi)) | (b >= n_bins)] = n_bins - 1
+    ok = (r >= T(lo)) & (r <= T(hi))
+    best = np.full(n_bins, -np.inf)
+    idx = np.full(n_bins, -1, dtype=np.int64)
+    ret = np.asarray(returns, dtype=np.float64)
+    for i in np.nonzero(ok)[0]:
+        if ret[i] > best[b[i]]:
+            best[b[i]], idx[b[i]] = ret[i], i
+    return best, idx
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("n,P", [(16, 200_000), (64, 20_000)])
+def test_envelope_matches_oracle(mcp, n, P, dtype):
+    mu, sigma = synthetic_inputs(n)
+    full = mcp.simulate_portfolios(mu, sigma, P, risk_free=0.03, seed=2, dtype=dtype)
+    lo, hi = float(full.risks.min()), float(full.risks.max())
+    K = 64
+    r = mcp.frontier_envelope(mu, sigma, P, K, risk_free=0.03, seed=2, dtype=dtype)
+    assert r.risk_range == (lo, hi)
+    env = r.extra["envelope"]
+    best, idx = _envelope_oracle(full.risks, full.returns, K, lo, hi, dtype)
+    assert np.array_equal(env["best_index"], idx)
+    assert np.array_equal(env["best_return"], best)
+    assert (idx >= 0).sum() > K // 2 and env["edges"].shape == (K + 1,)
+    # the FP64 run is also the plain numpy spec (oracle.paths_np.envelope)
+    if dtype == "float64":
+        from oracle import paths_np
+        b2, i2 = paths_np.envelope(full.risks, full.returns, K, lo, hi)
+        assert np.array_equal(i2, idx) and np.array_equal(b2, best)
+    # explicit range narrower than the data: out-of-range portfolios are ignored
+    mid = (lo + hi) / 2
+    r2 = mcp.simulate_portfolios(mu, sigma, P, risk_free=0.03, seed=2, dtype=dtype, n_bins=8, risk_range=(lo, mid),
+                                 return_arrays=False)
+    best2, idx2 = _envelope_oracle(full.risks, full.returns, 8, lo, mid, dtype)
+    assert np.array_equal(r2.extra["envelope"]["best_index"], idx2)
+
+
+def test_envelope_with_arrays_and_host_chunks(mcp):
+    """Envelope while arrays stream back through the two-slot HOST pipeline (several chunks)."""
+    n = 32
+    mu, sigma = synthetic_inputs(n, seed=4)
+    P = 1_500_001
+    r = mcp.simulate_portfolios(mu, sigma, P, risk_free=0.03, seed=9, n_bins=32, risk_range=(0.05, 0.5))
+    best, idx = _envelope_oracle(r.risks, r.returns, 32, 0.05, 0.5, "float32")
+    assert np.array_equal(r.extra["envelope"]["best_index"], idx)
+    assert np.array_equal(r.extra["envelope"]["best_return"], best)
