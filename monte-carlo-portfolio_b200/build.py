@@ -35,6 +35,7 @@ def translation_units():
            ("mcp_portfolio", "mcp_portfolio.cu", []),
            ("mcp_portfolio_large", "mcp_portfolio_large.cu", []),
            ("mcp_envelope", "mcp_envelope.cu", []),
+           ("mcp_recheck", "mcp_recheck.cu", []),
            ("mcp_paths", "mcp_paths.cu", []),
            ("mcp_quantile", "mcp_quantile.cu", []),
            ("mcp_historical", "mcp_historical.cu", [])]

@@ -138,7 +138,9 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
     size_t off_acc = off_run + sizeof(PfCand) * 4;                              // running[0..1], final
     size_t off_rec = off_acc + 64;
     size_t off_rows = off_rec + rec_doubles * sizeof(double);
-    size_t total = off_rows + (size_t)2 * N * 8 + 64;
+    size_t off_lists = (off_rows + (size_t)2 * N * 8 + 255) / 256 * 256;
+    const bool recheck = p->dtype == MCP_F32 && supplied && p->weights_recheck != nullptr;
+    size_t total = off_lists + (recheck ? sizeof(RcLists) : 0) + 64;
     unsigned char* base = nullptr;
     MCP_CHECK(mcp_dev_reserve(h, 0, total, (void**)&base));
     PfCand* cands = (PfCand*)(base + off_cands);
@@ -146,6 +148,13 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
     unsigned long long* d_acc = (unsigned long long*)(base + off_acc);
     double* d_rec = (double*)(base + off_rec);
     void* d_rows = base + off_rows;
+    RcLists* d_lists = (RcLists*)(base + off_lists);
+    double rf_mu = std::fabs(p->risk_free);
+    {
+        double m = 0;
+        for (int i = 0; i < N; ++i) m = std::max(m, std::fabs(mu[i]));
+        rf_mu += m;
+    }
     // envelope bins: running (f*) and per-chunk (c*) sets for each pipeline slot
     unsigned long long* env = nullptr;
     if (K > 0) MCP_CHECK(mcp_dev_reserve(h, 8, sizeof(unsigned long long) * 8 * (size_t)K, (void**)&env));
@@ -178,6 +187,7 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
 
     cudaStream_t st = h->stream;
     MCP_CUDA(h, cudaMemsetAsync(d_acc, 0, 8, st));
+    if (recheck) MCP_CUDA(h, cudaMemsetAsync(d_lists, 0, 16, st));
     if (K > 0) {
         MCP_CHECK(env_reset(h, K, fmax(0), fidx(0), st));
         MCP_CHECK(env_reset(h, K, fmax(1), fidx(1), st));
@@ -188,10 +198,11 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
 
     if (p->space == MCP_DEVICE) {
         // one launch, unless the envelope needs (risk, return) scratch: then chunks of 2^26
-        const bool env_scratch = K > 0 && (!out->returns || !out->risks);
-        const uint64_t chunk = env_scratch ? std::min<uint64_t>(P, 1ull << 26) : P;
+        const bool s_ret = K > 0 && !out->returns, s_risk = (K > 0 || recheck) && !out->risks, s_sharpe = recheck && !out->sharpes;
+        const bool any_scratch = s_ret || s_risk || s_sharpe;
+        const uint64_t chunk = any_scratch ? std::min<uint64_t>(P, 1ull << 26) : P;
         unsigned char* scratch = nullptr;
-        if (env_scratch) MCP_CHECK(mcp_dev_reserve(h, 9, 2 * chunk * es, (void**)&scratch));
+        if (any_scratch) MCP_CHECK(mcp_dev_reserve(h, 9, 3 * chunk * es, (void**)&scratch));
         job.cands = cands;
         job.stream = st;
         MCP_CUDA(h, cudaEventRecord(h->ev[0], st));
@@ -202,13 +213,14 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
             job.P = rows;
             job.w_in = p->weights_in ? (const unsigned char*)p->weights_in + r0 * N * es : nullptr;
             job.w_out = at(out->weights, (size_t)N * es);
-            job.ret_out = env_scratch ? (void*)scratch : at(out->returns, es);
-            job.risk_out = env_scratch ? (void*)(scratch + chunk * es) : at(out->risks, es);
-            job.sharpe_out = at(out->sharpes, es);
+            job.ret_out = s_ret ? (void*)scratch : at(out->returns, es);
+            job.risk_out = s_risk ? (void*)(scratch + chunk * es) : at(out->risks, es);
+            job.sharpe_out = s_sharpe ? (void*)(scratch + 2 * chunk * es) : at(out->sharpes, es);
             job.acc_out = (uint8_t*)at(out->accepted, 1);
             MCP_CHECK(pf_launch(h, job));
             MCP_CHECK(pf_reduce_launch(h, cands, job.blocks_used, running, r0 > 0 ? 1 : 0, st));
             if (K > 0) MCP_CHECK(envelope_chunk(0, job, st));
+            if (recheck) MCP_CHECK(rc_collect_launch(h, job.sharpe_out, job.risk_out, rows, job.first, running, rf_mu, p->risk_target, d_lists, st));
         }
         MCP_CUDA(h, cudaEventRecord(h->ev[1], st));
         MCP_CHECK(pf_reduce_launch(h, running, 1, final_cand, 0, st));
@@ -217,9 +229,10 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
         MCP_CUDA(h, cudaStreamSynchronize(st));           // the memset above must precede the side streams
         const bool want_w = out->weights != nullptr;
         const size_t in_row = supplied ? (size_t)N * es : 0;
-        const bool want_ret = out->returns != nullptr || K > 0, want_risk = out->risks != nullptr || K > 0;
+        const bool want_ret = out->returns != nullptr || K > 0, want_risk = out->risks != nullptr || K > 0 || recheck;
+        const bool want_sharpe = out->sharpes != nullptr || recheck;
         const size_t out_row = (want_w ? (size_t)N * es : 0) + (want_ret ? es : 0) + (want_risk ? es : 0) +
-                               (out->sharpes ? es : 0) + (out->accepted ? 1 : 0);
+                               (want_sharpe ? es : 0) + (out->accepted ? 1 : 0);
         uint64_t chunk = P;
         const size_t budget = (size_t)96 << 20;            // bytes per slot and direction
         if (in_row) chunk = std::min<uint64_t>(chunk, std::max<size_t>(budget / in_row, 1024));
@@ -259,7 +272,7 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
             unsigned char* dw = carve(want_w, (size_t)N * es);
             unsigned char* dr = carve(want_ret, es);
             unsigned char* dk = carve(want_risk, es);
-            unsigned char* ds = carve(out->sharpes != nullptr, es);
+            unsigned char* ds = carve(want_sharpe, es);
             unsigned char* da = carve(out->accepted != nullptr, 1);
             job.first = p->first_index + r0;
             job.P = rows;
@@ -280,10 +293,11 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
                 MCP_CHECK(envelope_chunk(s, job, ss));
                 env_slot1 = env_slot1 || (s == 1 && n_chunks > 1);
             }
+            if (recheck) MCP_CHECK(rc_collect_launch(h, ds, dk, rows, job.first, running + s, rf_mu, p->risk_target, d_lists, ss));
             if (dw) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->weights + r0 * N * es, dw, rows * N * es, cudaMemcpyDeviceToHost, ss));
             if (dr && out->returns) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->returns + r0 * es, dr, rows * es, cudaMemcpyDeviceToHost, ss));
             if (dk && out->risks) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->risks + r0 * es, dk, rows * es, cudaMemcpyDeviceToHost, ss));
-            if (ds) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->sharpes + r0 * es, ds, rows * es, cudaMemcpyDeviceToHost, ss));
+            if (ds && out->sharpes) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->sharpes + r0 * es, ds, rows * es, cudaMemcpyDeviceToHost, ss));
             if (da) MCP_CUDA(h, cudaMemcpyAsync(out->accepted + r0, da, rows, cudaMemcpyDeviceToHost, ss));
             used[s] = true;
         }
@@ -336,17 +350,27 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
     rp.idx[0] = fin.idx_s;
     rp.idx[1] = fin.idx_d;
     rp.rec = d_rec;
-    if (supplied) {
-        for (int k = 0; k < 2; ++k) {
-            const size_t row = (size_t)(rp.idx[k] - p->first_index) * N * es;
-            MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)d_rows + (size_t)k * N * es, (const unsigned char*)p->weights_in + row,
-                                        (size_t)N * es, p->space == MCP_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-        }
-        rp.rows = d_rows;
-    }
     job.first = p->first_index;
     job.P = P;
     job.stream = st;
+    const void* row_src = p->weights_in;
+    size_t row_es = es;
+    if (recheck) {
+        // FP32 screen -> FP64 decision among the near-ties; the records are then FP64 too
+        int overflow = 0;
+        MCP_CHECK(rc_decide(h, p, job, fin, rf_mu, d_lists, cands, max_blocks, d_acc, rp.idx, &overflow));
+        job.dtype = MCP_F64;
+        row_src = p->weights_recheck;
+        row_es = 8;
+    }
+    if (supplied) {
+        for (int k = 0; k < 2; ++k) {
+            const size_t row = (size_t)(rp.idx[k] - p->first_index) * N * row_es;
+            MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)d_rows + (size_t)k * N * row_es, (const unsigned char*)row_src + row,
+                                        (size_t)N * row_es, p->space == MCP_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        }
+        rp.rows = d_rows;
+    }
     MCP_CHECK(pf_replay(h, job, rp));
     std::vector<double> rec(rec_doubles);
     MCP_CUDA(h, cudaMemcpyAsync(rec.data(), d_rec, rec_doubles * sizeof(double), cudaMemcpyDeviceToHost, st));

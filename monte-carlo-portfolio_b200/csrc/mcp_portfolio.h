@@ -71,6 +71,20 @@ int env_chunk(mcp_context* h, int dtype, const void* risk, const void* ret, uint
 int env_fold(mcp_context* h, int K, const unsigned long long* cmax, const unsigned long long* cidx, unsigned long long* fmax,
              unsigned long long* fidx, cudaStream_t st);
 
+// FP32 near-tie recheck (mcp_recheck.cu)
+constexpr unsigned RC_CAP = 8192;
+struct RcLists {
+    unsigned int count[2];
+    unsigned int pad[2];
+    unsigned long long idx[2][RC_CAP];
+    float key[2][RC_CAP];
+};
+int rc_collect_launch(mcp_context* h, const void* sharpe, const void* risk, uint64_t n, uint64_t base, const PfCand* running,
+                      double rf_mu, double target, RcLists* lists, cudaStream_t st);
+int rc_decide(mcp_context* h, const mcp_portfolio_params* p, const PfJob& job32, const PfCand& fin, double rf_mu,
+              RcLists* d_lists, PfCand* d_cand_scratch, int max_blocks, unsigned long long* d_acc_scratch, uint64_t out_idx[2],
+              int* overflow);
+
 int pf_small_launch(mcp_context* h, PfJob& job);
 int pf_small_replay(mcp_context* h, const PfJob& job, const PfReplay& rp);
 int pf_large_launch(mcp_context* h, PfJob& job);

@@ -187,7 +187,9 @@ def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, risk_free=0.0
                       unless keep_last, which is efficient_frontier's behaviour, app.py:277).
     weights=(P, N)    supplied-weights (parity) mode: evaluated as given, no RNG.  numpy
                       array (HOST space, copies inside the call) or CUDA torch tensor
-                      (DEVICE space, no copies; arrays come back as torch tensors).
+                      (DEVICE space, no copies; arrays come back as torch tensors).  With
+                      dtype='float32' and FP64 weights the FP32 sweep screens and the picks are
+                      decided in FP64 among the near-ties (same index as the FP64 reference).
     risk_free         subtracted raw, as app.py:711 (pass 3.0 for the app's default widget value).
     return_arrays     False: selections only, zero HBM write-back (C3 sizes).
     out               optional dict of preallocated arrays ('weights', 'returns', 'risks',
@@ -212,6 +214,8 @@ def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, risk_free=0.0
             import torch
             want = torch.float32 if code == MCP_F32 else torch.float64
             w_in = weights.to(want).contiguous()
+            if code == MCP_F32 and weights.dtype == torch.float64:
+                recheck = weights.contiguous()
             shape = tuple(w_in.shape)
         else:
             src = np.asarray(weights)

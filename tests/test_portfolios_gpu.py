@@ -72,7 +72,7 @@ def test_supplied_weights_all_small_n(mcp, n, dtype):
     P = 3001                                    # ragged: not a multiple of the CTA tile
     W = rng.dirichlet(np.ones(n), size=P)
     r = mcp.simulate_portfolios(mu, sigma, P, weights=W, risk_free=0.03, risk_target=0.25, dtype=dtype)
-    check_against_oracle(r, W, mu, sigma, 0.03, 0.25, dtype, same_index=(dtype == "float64"))
+    check_against_oracle(r, W, mu, sigma, 0.03, 0.25, dtype)
 
 
 def test_edge_sizes(mcp):
@@ -97,9 +97,8 @@ def test_first_occurrence_tie_break(mcp):
         r = mcp.simulate_portfolios(mu, sigma, len(W), weights=W, dtype=dtype, risk_free=0.03)
         assert r.max_sharpe["index"] < 50 and r.target_risk["index"] < 50
         want = ref.evaluate(W, mu, sigma, 0.03, 0.30)
-        if dtype == "float64":
-            assert r.max_sharpe["index"] == want["max_sharpe"]["index"]
-            assert r.target_risk["index"] == want["target_risk"]["index"]
+        assert r.max_sharpe["index"] == want["max_sharpe"]["index"]
+        assert r.target_risk["index"] == want["target_risk"]["index"]
 
 
 @pytest.mark.parametrize("dtype,atol", [("float32", 2e-6), ("float64", 1e-12)])
@@ -269,7 +268,7 @@ def test_large_n_supplied_weights(mcp, n, dtype):
     P = 1000 if n <= 256 else 300
     W = np.random.RandomState(n).dirichlet(np.ones(n), size=P)
     r = mcp.simulate_portfolios(mu, sigma, P, weights=W, risk_free=0.03, risk_target=0.03, dtype=dtype)
-    check_against_oracle(r, W, mu, sigma, 0.03, 0.03, dtype, same_index=(dtype == "float64"))
+    check_against_oracle(r, W, mu, sigma, 0.03, 0.03, dtype)
 
 
 @pytest.mark.parametrize("dtype,atol", [("float32", 1e-6), ("float64", 1e-12)])
@@ -386,3 +385,46 @@ def test_envelope_with_arrays_and_host_chunks(mcp):
     best, idx = _envelope_oracle(r.risks, r.returns, 32, 0.05, 0.5, "float32")
     assert np.array_equal(r.extra["envelope"]["best_index"], idx)
     assert np.array_equal(r.extra["envelope"]["best_return"], best)
+
+
+# ---- FP32 screen + FP64 decision: the same selected index as the FP64 reference ------------------
+
+@pytest.mark.parametrize("n", [2, 16, 64])
+@pytest.mark.parametrize("space", ["host", "device"])
+def test_fp32_near_ties_pick_the_fp64_index(mcp, n, space):
+    """Rows that are identical after rounding to FP32 but differ in FP64: np.argmax on the FP64
+    values picks the later, slightly better row; the plain FP32 sweep would pick the earlier one."""
+    mu, sigma = synthetic_inputs(n, seed=5)
+    rng = np.random.RandomState(7)
+    P = 50_000
+    W = rng.dirichlet(np.ones(n), size=P)
+    base = ref.evaluate(W, mu, sigma, 0.03, 0.30)
+    i_s, i_d = base["max_sharpe"]["index"], base["target_risk"]["index"]
+    # plant FP64-only improvements at higher indices
+    def nudge(row, key_fn, better):
+        best, out = key_fn(row), row
+        for _ in range(200):
+            cand = row + rng.standard_normal(n) * 1e-11
+            cand = np.abs(cand) / np.abs(cand).sum()
+            if np.array_equal(cand.astype(np.float32), row.astype(np.float32)) and better(key_fn(cand), best):
+                best, out = key_fn(cand), cand
+        return out
+    sharpe_of = lambda w: ref.portfolio_metrics(w[None], mu, sigma, 0.03)[2][0]
+    dist_of = lambda w: abs(ref.portfolio_metrics(w[None], mu, sigma, 0.03)[1][0] - 0.30)
+    W[P - 10] = nudge(W[i_s], sharpe_of, lambda a, b: a > b)
+    W[P - 5] = nudge(W[i_d], dist_of, lambda a, b: a < b)
+    want = ref.evaluate(W, mu, sigma, 0.03, 0.30)
+    assert want["max_sharpe"]["index"] == P - 10 and want["target_risk"]["index"] == P - 5
+    if space == "device":
+        import torch
+        arg = torch.from_numpy(W).cuda()
+    else:
+        arg = W
+    r = mcp.simulate_portfolios(mu, sigma, P, weights=arg, risk_free=0.03, dtype="float32")
+    assert r.max_sharpe["index"] == P - 10
+    assert r.target_risk["index"] == P - 5
+    assert np.isclose(r.max_sharpe["sharpe"], want["max_sharpe"]["sharpe"], rtol=1e-12)     # FP64 record
+    assert np.allclose(r.max_sharpe["weights"], W[P - 10], rtol=0, atol=0)
+    # without the FP64 copy the FP32 screen alone decides (first occurrence among FP32 ties)
+    r32 = mcp.simulate_portfolios(mu, sigma, P, weights=W.astype(np.float32), risk_free=0.03, dtype="float32")
+    assert r32.max_sharpe["index"] == i_s and r32.target_risk["index"] == i_d
