@@ -216,7 +216,7 @@ int mcp_historical_var(mcp_handle h, const mcp_hist_params* params,
                        const double* returns_matrix_host /* [T, N] */, mcp_hist_out* out);
 
 /* ---- microbenchmarks used as roofline denominators (bench.py) ------------------------- */
-int mcp_measure_fma_peak(mcp_handle h, int dtype, double* tflops);
+int mcp_measure_fma_peak(mcp_handle h, int dtype /* MCP_F32 | MCP_F64 | 2 = packed FP32x2 (FFMA2) */, double* tflops);
 
 #ifdef __cplusplus
 }

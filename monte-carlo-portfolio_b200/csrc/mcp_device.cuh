@@ -73,6 +73,19 @@ template <> struct Math<double> {
     static __device__ __forceinline__ double unit_frac(uint32_t x) { return (double)x * 0x1p-32; }
 };
 
+// ---- packed FP32x2 (Blackwell FFMA2): one instruction = two FMAs, operands may be register
+// pairs, uniform-register pairs (constant bank) or a broadcast scalar.  The fused sweep is
+// issue-bound, so halving the FFMA count is worth more than any pipe-level trick.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+    unsigned long long rc = *reinterpret_cast<unsigned long long*>(&c);
+    unsigned long long rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 bcast2(float x) { return make_float2(x, x); }
+
 // ---- (key, index) argmax with first-occurrence tie-break ---------------------------------
 // `better(a, ia, b, ib)`: does candidate a beat b?  Larger key wins; equal keys -> lower index.
 template <typename T>

@@ -13,7 +13,8 @@
 //                A warp owns one pair of 16-column groups (g, G-1-g): its K-extent is uniform
 //                across the warp (no divergence) and all warps do the same 16(G+1) k-steps.
 //                Per k-step a lane does one LDS.64 (its 2 portfolios) + 8 broadcast LDS.128
-//                (S' row slices) for 64 FFMA: 2 portfolios x 32 columns of accumulators;
+//                (S' row slices) for 32 FFMA2 (packed FP32x2: the float2 of the lane's two
+//                portfolios times a broadcast S' element) = 64 FMAs on 2 x 32 accumulators;
 //   3. EPILOGUE  multiplies the accumulators with W again (row-dot), and reduces q, sum(e) and
 //                e.mu over the 8 warps through shared memory in a fixed order (deterministic,
 //                independent of the portfolio's slot in the tile -> replays are bit-identical);
@@ -136,11 +137,12 @@ __global__ void __launch_bounds__(LG_THREADS, 1) large_sweep(const LargeArgs a) 
             __syncthreads();
 
             // ---- 2. Y' = W S' over the lower triangle: 2 portfolios x (16 + 16) columns per lane ----
-            float qp[2] = {0.f, 0.f}, sp[2] = {0.f, 0.f}, rp[2] = {0.f, 0.f};
+            // accumulators are float2 = this lane's two portfolios: every FFMA2 does both (packed FP32x2)
+            float2 qp = make_float2(0.f, 0.f), sp = make_float2(0.f, 0.f), rp = make_float2(0.f, 0.f);
             if (has_pair) {
-                float accA[2][LG_CG], accB[2][LG_CG];
+                float2 accA[LG_CG], accB[LG_CG];
 #pragma unroll
-                for (int c = 0; c < LG_CG; ++c) { accA[0][c] = accA[1][c] = accB[0][c] = accB[1][c] = 0.f; }
+                for (int c = 0; c < LG_CG; ++c) { accA[c] = make_float2(0.f, 0.f); accB[c] = make_float2(0.f, 0.f); }
                 const float* wrow = sW + 2 * lane;
                 for (int kblk = 0; kblk <= gB; ++kblk) {          // 16 rows sharing one row length
                     const int rowlen = a.np - LG_CG * kblk;
@@ -156,26 +158,18 @@ __global__ void __launch_bounds__(LG_THREADS, 1) large_sweep(const LargeArgs a) 
 #pragma unroll
                             for (int v = 0; v < 4; ++v) {
                                 const float4 s4 = sb[v];
-                                accB[0][4 * v + 0] = fmaf(w2.x, s4.x, accB[0][4 * v + 0]);
-                                accB[0][4 * v + 1] = fmaf(w2.x, s4.y, accB[0][4 * v + 1]);
-                                accB[0][4 * v + 2] = fmaf(w2.x, s4.z, accB[0][4 * v + 2]);
-                                accB[0][4 * v + 3] = fmaf(w2.x, s4.w, accB[0][4 * v + 3]);
-                                accB[1][4 * v + 0] = fmaf(w2.y, s4.x, accB[1][4 * v + 0]);
-                                accB[1][4 * v + 1] = fmaf(w2.y, s4.y, accB[1][4 * v + 1]);
-                                accB[1][4 * v + 2] = fmaf(w2.y, s4.z, accB[1][4 * v + 2]);
-                                accB[1][4 * v + 3] = fmaf(w2.y, s4.w, accB[1][4 * v + 3]);
+                                accB[4 * v + 0] = fma2(w2, bcast2(s4.x), accB[4 * v + 0]);
+                                accB[4 * v + 1] = fma2(w2, bcast2(s4.y), accB[4 * v + 1]);
+                                accB[4 * v + 2] = fma2(w2, bcast2(s4.z), accB[4 * v + 2]);
+                                accB[4 * v + 3] = fma2(w2, bcast2(s4.w), accB[4 * v + 3]);
                             }
 #pragma unroll
                             for (int v = 0; v < 4; ++v) {
                                 const float4 s4 = sa[v];
-                                accA[0][4 * v + 0] = fmaf(w2.x, s4.x, accA[0][4 * v + 0]);
-                                accA[0][4 * v + 1] = fmaf(w2.x, s4.y, accA[0][4 * v + 1]);
-                                accA[0][4 * v + 2] = fmaf(w2.x, s4.z, accA[0][4 * v + 2]);
-                                accA[0][4 * v + 3] = fmaf(w2.x, s4.w, accA[0][4 * v + 3]);
-                                accA[1][4 * v + 0] = fmaf(w2.y, s4.x, accA[1][4 * v + 0]);
-                                accA[1][4 * v + 1] = fmaf(w2.y, s4.y, accA[1][4 * v + 1]);
-                                accA[1][4 * v + 2] = fmaf(w2.y, s4.z, accA[1][4 * v + 2]);
-                                accA[1][4 * v + 3] = fmaf(w2.y, s4.w, accA[1][4 * v + 3]);
+                                accA[4 * v + 0] = fma2(w2, bcast2(s4.x), accA[4 * v + 0]);
+                                accA[4 * v + 1] = fma2(w2, bcast2(s4.y), accA[4 * v + 1]);
+                                accA[4 * v + 2] = fma2(w2, bcast2(s4.z), accA[4 * v + 2]);
+                                accA[4 * v + 3] = fma2(w2, bcast2(s4.w), accA[4 * v + 3]);
                             }
                         }
                     } else {
@@ -186,14 +180,10 @@ __global__ void __launch_bounds__(LG_THREADS, 1) large_sweep(const LargeArgs a) 
 #pragma unroll
                             for (int v = 0; v < 4; ++v) {
                                 const float4 s4 = sb[v];
-                                accB[0][4 * v + 0] = fmaf(w2.x, s4.x, accB[0][4 * v + 0]);
-                                accB[0][4 * v + 1] = fmaf(w2.x, s4.y, accB[0][4 * v + 1]);
-                                accB[0][4 * v + 2] = fmaf(w2.x, s4.z, accB[0][4 * v + 2]);
-                                accB[0][4 * v + 3] = fmaf(w2.x, s4.w, accB[0][4 * v + 3]);
-                                accB[1][4 * v + 0] = fmaf(w2.y, s4.x, accB[1][4 * v + 0]);
-                                accB[1][4 * v + 1] = fmaf(w2.y, s4.y, accB[1][4 * v + 1]);
-                                accB[1][4 * v + 2] = fmaf(w2.y, s4.z, accB[1][4 * v + 2]);
-                                accB[1][4 * v + 3] = fmaf(w2.y, s4.w, accB[1][4 * v + 3]);
+                                accB[4 * v + 0] = fma2(w2, bcast2(s4.x), accB[4 * v + 0]);
+                                accB[4 * v + 1] = fma2(w2, bcast2(s4.y), accB[4 * v + 1]);
+                                accB[4 * v + 2] = fma2(w2, bcast2(s4.z), accB[4 * v + 2]);
+                                accB[4 * v + 3] = fma2(w2, bcast2(s4.w), accB[4 * v + 3]);
                             }
                         }
                     }
@@ -204,17 +194,17 @@ __global__ void __launch_bounds__(LG_THREADS, 1) large_sweep(const LargeArgs a) 
                     const int ja = LG_CG * gA + c, jb = LG_CG * gB + c;
                     const float2 wa = *reinterpret_cast<const float2*>(wrow + (size_t)ja * LG_WSTRIDE);
                     const float2 wb = *reinterpret_cast<const float2*>(wrow + (size_t)jb * LG_WSTRIDE);
-                    const float ma = sMu[ja], mb = sMu[jb];
-                    qp[0] = fmaf(accA[0][c], wa.x, qp[0]); qp[1] = fmaf(accA[1][c], wa.y, qp[1]);
-                    qp[0] = fmaf(accB[0][c], wb.x, qp[0]); qp[1] = fmaf(accB[1][c], wb.y, qp[1]);
-                    sp[0] += wa.x; sp[1] += wa.y; sp[0] += wb.x; sp[1] += wb.y;
-                    rp[0] = fmaf(ma, wa.x, rp[0]); rp[1] = fmaf(ma, wa.y, rp[1]);
-                    rp[0] = fmaf(mb, wb.x, rp[0]); rp[1] = fmaf(mb, wb.y, rp[1]);
+                    qp = fma2(accA[c], wa, qp);
+                    qp = fma2(accB[c], wb, qp);
+                    sp = fma2(wa, bcast2(1.0f), sp);
+                    sp = fma2(wb, bcast2(1.0f), sp);
+                    rp = fma2(bcast2(sMu[ja]), wa, rp);
+                    rp = fma2(bcast2(sMu[jb]), wb, rp);
                 }
             }
-            *reinterpret_cast<float2*>(sRedQ + warp * LG_TP + 2 * lane) = make_float2(qp[0], qp[1]);
-            *reinterpret_cast<float2*>(sRedS + warp * LG_TP + 2 * lane) = make_float2(sp[0], sp[1]);
-            *reinterpret_cast<float2*>(sRedR + warp * LG_TP + 2 * lane) = make_float2(rp[0], rp[1]);
+            *reinterpret_cast<float2*>(sRedQ + warp * LG_TP + 2 * lane) = qp;
+            *reinterpret_cast<float2*>(sRedS + warp * LG_TP + 2 * lane) = sp;
+            *reinterpret_cast<float2*>(sRedR + warp * LG_TP + 2 * lane) = rp;
             __syncthreads();
 
             // ---- 4a. sum(e) per portfolio (fixed order) ----

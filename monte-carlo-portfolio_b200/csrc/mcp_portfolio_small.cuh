@@ -24,6 +24,7 @@ struct SmallArgs {
     T sig[NP * (NP + 1) / 2];   // row i holds j = 0..i; off-diagonals doubled
     T mu[NP];
     T mask[NP];                 // 1 for real assets, 0 for padded ones
+    T nmu[NP], nmask[NP];       // -mu, -mask: the packed path works on l = lg2(U) = -e
     T lo[NP], hi[NP];
     T rf, target;
     int n;                      // real asset count (<= NP); padded assets carry weight 0
@@ -266,6 +267,124 @@ __global__ void __launch_bounds__(PF_BLOCK) small_sweep(const __grid_constant__ 
     }
 }
 
+// ---- packed FP32x2 variant of the Philox / no-bounds / no-weight-write sweep (the C3 kernel) ----
+// Two portfolios share every instruction of the arithmetic: l2[i] = (lg2 U_i of portfolio A,
+// of portfolio B).  It works on l = lg2(U) = -e so that no negation is ever materialised:
+// q = l' S l (= e' S e), s = sum(-mask_i l_i), r = sum(-mu_i l_i).  Every value is bit-identical
+// to the scalar path (IEEE fma per lane, same operation order), so small_replay reproduces it.
+template <int NP, int K>
+__global__ void __launch_bounds__(PF_BLOCK) small_sweep_packed(const __grid_constant__ SmallArgs<float, NP> a) {
+    static_assert(K % 2 == 0, "packed sweep pairs portfolios");
+    constexpr int KP = K / 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t n_sub = (a.P + PF_BLOCK - 1) / PF_BLOCK;
+    const uint64_t n_tiles = (n_sub + K - 1) / K;
+    constexpr uint32_t NONE = 0xffffffffu;
+    float best_s = -Math<float>::inf(), best_d = -Math<float>::inf();
+    uint32_t sub_s = NONE, sub_d = NONE;
+    float rmin = Math<float>::inf(), rmax = -Math<float>::inf();
+    uint32_t n_acc = 0;
+
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t local0 = tile * (uint64_t)(K * PF_BLOCK) + threadIdx.x;
+        float2 l2[KP][NP];
+        float2 s2[KP];
+#pragma unroll
+        for (int kp = 0; kp < KP; ++kp) {
+            const uint64_t ga = a.first + local0 + (uint64_t)(2 * kp) * PF_BLOCK, gb = ga + PF_BLOCK;
+            s2[kp] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int b = 0; b < NP / 4; ++b) {
+                uint32_t xa[4], xb[4];
+                philox4x32_10((uint32_t)ga, (uint32_t)(ga >> 32), 0u, STREAM_WEIGHTS | (uint32_t)b, a.k0, a.k1, xa);
+                philox4x32_10((uint32_t)gb, (uint32_t)(gb >> 32), 0u, STREAM_WEIGHTS | (uint32_t)b, a.k0, a.k1, xb);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = 4 * b + k;
+                    const float2 f = make_float2(__uint_as_float((xa[k] & 0x007fffffu) | 0x3f800000u),
+                                                 __uint_as_float((xb[k] & 0x007fffffu) | 0x3f800000u));
+                    const float2 u = fma2(f, bcast2(-1.0f), bcast2(2.0f));            // U = 2 - f in (0, 1]
+                    l2[kp][i] = make_float2(Math<float>::lg2(u.x), Math<float>::lg2(u.y));
+                    s2[kp] = fma2(l2[kp][i], bcast2(a.nmask[i]), s2[kp]);
+                }
+            }
+        }
+        float2 q2[KP], r2[KP];
+#pragma unroll
+        for (int kp = 0; kp < KP; ++kp) { q2[kp] = make_float2(0.f, 0.f); r2[kp] = make_float2(0.f, 0.f); }
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            float2 t[KP];
+#pragma unroll
+            for (int kp = 0; kp < KP; ++kp) t[kp] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                const float2 sij = bcast2(a.sig[i * (i + 1) / 2 + j]);
+#pragma unroll
+                for (int kp = 0; kp < KP; ++kp) t[kp] = fma2(sij, l2[kp][j], t[kp]);
+            }
+            const float2 nmu = bcast2(a.nmu[i]);
+#pragma unroll
+            for (int kp = 0; kp < KP; ++kp) {
+                q2[kp] = fma2(l2[kp][i], t[kp], q2[kp]);
+                r2[kp] = fma2(nmu, l2[kp][i], r2[kp]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const uint64_t local = local0 + (uint64_t)k * PF_BLOCK;
+            const bool active = local < a.P;
+            const float q = (k & 1) ? q2[k / 2].y : q2[k / 2].x;
+            const float r = (k & 1) ? r2[k / 2].y : r2[k / 2].x;
+            const float s = (k & 1) ? s2[k / 2].y : s2[k / 2].x;
+            float ret, risk, sharpe;
+            metrics_from<float>(q, r, s, a.rf, false, ret, risk, sharpe);
+            if (active) {
+                const uint32_t sub = (uint32_t)(tile * K + k);
+                ++n_acc;
+                if (sharpe > best_s) { best_s = sharpe; sub_s = sub; }
+                const float d = -fabsf(risk - a.target);
+                if (d > best_d) { best_d = d; sub_d = sub; }
+                rmin = fminf(rmin, risk);
+                rmax = fmaxf(rmax, risk);
+                if (a.ret_out != nullptr) a.ret_out[local] = ret;
+                if (a.risk_out != nullptr) a.risk_out[local] = risk;
+                if (a.sharpe_out != nullptr) a.sharpe_out[local] = sharpe;
+                if (a.acc_out != nullptr) a.acc_out[local] = 1;
+            }
+        }
+    }
+
+    uint64_t idx_s = sub_s == NONE ? MCP_NO_INDEX : a.first + (uint64_t)sub_s * PF_BLOCK + threadIdx.x;
+    uint64_t idx_d = sub_d == NONE ? MCP_NO_INDEX : a.first + (uint64_t)sub_d * PF_BLOCK + threadIdx.x;
+    warp_argmax<float>(best_s, idx_s);
+    warp_argmax<float>(best_d, idx_d);
+    rmin = warp_min<float>(rmin);
+    rmax = warp_max<float>(rmax);
+    n_acc = __reduce_add_sync(0xffffffffu, n_acc);
+    __shared__ PfCand wc[PF_BLOCK / 32];
+    __shared__ unsigned int wacc[PF_BLOCK / 32];
+    if (lane == 0) {
+        wc[warp] = PfCand{(double)best_s, idx_s, (double)best_d, idx_d, (double)rmin, (double)rmax};
+        wacc[warp] = n_acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        PfCand b = wc[0];
+        unsigned long long acc = wacc[0];
+        for (int w = 1; w < PF_BLOCK / 32; ++w) {
+            const PfCand o = wc[w];
+            if (cand_better<double>(o.key_s, o.idx_s, b.key_s, b.idx_s)) { b.key_s = o.key_s; b.idx_s = o.idx_s; }
+            if (cand_better<double>(o.key_d, o.idx_d, b.key_d, b.idx_d)) { b.key_d = o.key_d; b.idx_d = o.idx_d; }
+            b.rmin = o.rmin < b.rmin ? o.rmin : b.rmin;
+            b.rmax = o.rmax > b.rmax ? o.rmax : b.rmax;
+            acc += wacc[w];
+        }
+        a.cands[blockIdx.x] = b;
+        if (acc) atomicAdd(a.n_accepted, acc);
+    }
+}
+
 // Re-evaluates the selected portfolios with exactly the sweep's arithmetic and emits
 // (index, key, ret, risk, sharpe, weights[N]) records in FP64.
 template <typename T, int NP>
@@ -315,6 +434,8 @@ static void fill_small_args(const PfJob& job, SmallArgs<T, NP>& a) {
         }
         a.mu[i] = i < n ? (T)job.mu[i] : (T)0;
         a.mask[i] = i < n ? (T)1 : (T)0;
+        a.nmu[i] = -a.mu[i];
+        a.nmask[i] = -a.mask[i];
         a.lo[i] = (i < n && job.lo) ? (T)job.lo[i] : (T)-1e30;
         a.hi[i] = (i < n && job.hi) ? (T)job.hi[i] : (T)1e30;
     }
@@ -360,6 +481,24 @@ static int small_launch_k(mcp_context* h, PfJob& job, const SmallArgs<T, NP>& a)
     return MCP_OK;
 }
 
+template <int NP, int K>
+static int small_launch_packed(mcp_context* h, PfJob& job, const SmallArgs<float, NP>& a) {
+    auto kern = small_sweep_packed<NP, K>;
+    int per_sm = 0;
+    MCP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PF_BLOCK, 0));
+    if (per_sm < 1) return mcp_fail(h, MCP_ERR_CUDA, "small_sweep_packed<N=%d>: zero occupancy", NP);
+    const uint64_t n_tiles = ((job.P + PF_BLOCK - 1) / PF_BLOCK + K - 1) / K;
+    uint64_t grid = (uint64_t)h->prop.multiProcessorCount * per_sm;
+    if (grid > n_tiles) grid = n_tiles;
+    if (grid > (uint64_t)job.max_blocks) grid = job.max_blocks;
+    if (grid < 1) grid = 1;
+    job.blocks_used = (int)grid;
+    kern<<<(unsigned)grid, PF_BLOCK, 0, job.stream>>>(a);
+    MCP_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return MCP_OK;
+}
+
 template <typename T, int NP>
 int pf_small_launch_t(mcp_context* h, PfJob& job) {
     SmallArgs<T, NP> a;
@@ -367,6 +506,9 @@ int pf_small_launch_t(mcp_context* h, PfJob& job) {
     // K portfolios per thread only when nothing streams through HBM: with supplied weights or
     // weight write-back the kernel is memory-side bound and the extra registers only cost occupancy
     constexpr int K = SweepK<T, NP>::value;
+    if constexpr (sizeof(T) == 4 && K % 2 == 0) {
+        if (job.w_in == nullptr && job.w_out == nullptr && !job.bounds) return small_launch_packed<NP, K>(h, job, a);
+    }
     if (K > 1 && job.w_in == nullptr && job.w_out == nullptr) return small_launch_k<T, NP, K>(h, job, a);
     return small_launch_k<T, NP, 1>(h, job, a);
 }

@@ -73,7 +73,7 @@ class Engine:
         check(self._h, lib().mcp_synchronize(self._h))
 
     def measure_fma_peak(self, dtype="float32") -> float:
-        code, _ = _dtype(dtype)
+        code = 2 if dtype == "float32x2" else _dtype(dtype)[0]
         out = C.c_double()
         check(self._h, lib().mcp_measure_fma_peak(self._h, code, C.byref(out)))
         return out.value

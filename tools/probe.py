@@ -30,6 +30,7 @@ def main():
     out = {"device": eng.info()}
     out["fma_peak_f32_tflops"] = eng.measure_fma_peak("float32")
     out["fma_peak_f64_tflops"] = eng.measure_fma_peak("float64")
+    out["fma_peak_f32x2_tflops"] = eng.measure_fma_peak("float32x2")
     print(json.dumps(out), flush=True)
     for n in (16, 8, 32, 14):
         mu, sigma = inputs(n)
