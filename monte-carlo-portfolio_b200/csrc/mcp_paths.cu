@@ -113,6 +113,61 @@ __global__ void __launch_bounds__(PATH_BLOCK) path_kernel(const __grid_constant_
     }
 }
 
+// Packed FP32x2 variant (Philox mode): a thread carries TWO paths in float2 lanes, so the
+// L z mat-vec, the compounding and the Box-Muller scaling issue one FFMA2 per two FMAs.  The
+// kernel is issue-bound (FMA / ALU / XU pipes all < 55 % busy), so this is the lever that matters.
+template <int NP>
+__global__ void __launch_bounds__(PATH_BLOCK) path_kernel_packed(const __grid_constant__ PathArgs<float, NP> a) {
+    const uint64_t n_sub = (a.M + PATH_BLOCK - 1) / PATH_BLOCK;
+    const uint64_t n_tiles = (n_sub + 1) / 2;
+    const float kPi = 3.14159265358979323846f;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t mA = tile * (2 * PATH_BLOCK) + threadIdx.x, mB = mA + PATH_BLOCK;
+        const uint64_t gA = a.first + mA, gB = a.first + mB;
+        float2 V[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) V[i] = make_float2(1.f, 1.f);
+        for (int s = 0; s < a.n_steps; ++s) {
+            float2 z[NP];
+#pragma unroll
+            for (int b = 0; b < NP / 4; ++b) {
+                uint32_t xa[4], xb[4];
+                philox4x32_10((uint32_t)gA, (uint32_t)(gA >> 32), (uint32_t)s, STREAM_NORMALS | (uint32_t)b, a.k0, a.k1, xa);
+                philox4x32_10((uint32_t)gB, (uint32_t)(gB >> 32), (uint32_t)s, STREAM_NORMALS | (uint32_t)b, a.k0, a.k1, xb);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float2 f1 = make_float2(__uint_as_float((xa[2 * k] & 0x007fffffu) | 0x3f800000u),
+                                                  __uint_as_float((xb[2 * k] & 0x007fffffu) | 0x3f800000u));
+                    const float2 u1 = fma2(f1, bcast2(-1.0f), bcast2(2.0f));                      // (0, 1]
+                    const float2 t = fma2(make_float2(Math<float>::lg2(u1.x), Math<float>::lg2(u1.y)),
+                                          bcast2(PathConst<float>::neg2ln2()), bcast2(0.0f));     // -2 ln U1
+                    const float2 r = make_float2(Math<float>::sqrt(t.x), Math<float>::sqrt(t.y));
+                    const float2 f2 = make_float2(__uint_as_float((xa[2 * k + 1] & 0x007fffffu) | 0x40000000u),
+                                                  __uint_as_float((xb[2 * k + 1] & 0x007fffffu) | 0x40000000u));
+                    const float2 c = fma2(f2, bcast2(1.0f), bcast2(-3.0f));                       // 2f - 1 in [-1, 1)
+                    const float2 th = fma2(c, bcast2(kPi), bcast2(0.0f));
+                    const float2 cs = make_float2(Math<float>::cosf_(th.x), Math<float>::cosf_(th.y));
+                    const float2 sn = make_float2(Math<float>::sinf_(th.x), Math<float>::sinf_(th.y));
+                    z[4 * b + 2 * k] = fma2(r, cs, bcast2(0.0f));
+                    z[4 * b + 2 * k + 1] = fma2(r, sn, bcast2(0.0f));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                float2 r = bcast2(a.drift[i]);
+#pragma unroll
+                for (int j = 0; j <= i; ++j) r = fma2(bcast2(a.lp[i * (i + 1) / 2 + j]), z[j], r);
+                V[i] = fma2(V[i], r, V[i]);                                                      // V *= (1 + r)
+            }
+        }
+        float2 x = bcast2(-1.0f);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) x = fma2(bcast2(a.w[i]), V[i], x);
+        if (mA < a.M) a.terminal[mA] = x.x;
+        if (mB < a.M) a.terminal[mB] = x.y;
+    }
+}
+
 // host: lower Cholesky factor (FP64), row-major n x n; returns false if not positive definite
 static bool cholesky_lower(const double* sigma, int n, std::vector<double>& L) {
     L.assign((size_t)n * n, 0.0);
@@ -151,11 +206,15 @@ static int path_launch_t(mcp_context* h, const mcp_path_params* p, const double*
     a.z_in = (const T*)z_dev;
     a.terminal = (T*)term_dev;
     void (*kern)(PathArgs<T, NP>) = z_dev ? path_kernel<T, NP, 1> : path_kernel<T, NP, 0>;
+    int per_thread = 1;
+    if constexpr (sizeof(T) == 4 && NP <= 16) {
+        if (!z_dev) { kern = path_kernel_packed<NP>; per_thread = 2; }
+    }
     int per_sm = 0;
     MCP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PATH_BLOCK, 0));
     if (per_sm < 1) return mcp_fail(h, MCP_ERR_CUDA, "path_kernel<N=%d>: zero occupancy", NP);
     uint64_t grid = (uint64_t)h->prop.multiProcessorCount * per_sm;
-    const uint64_t need = (p->n_paths + PATH_BLOCK - 1) / PATH_BLOCK;
+    const uint64_t need = (p->n_paths + (uint64_t)PATH_BLOCK * per_thread - 1) / ((uint64_t)PATH_BLOCK * per_thread);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, PATH_BLOCK, 0, st>>>(a);
