@@ -102,6 +102,35 @@ __device__ __forceinline__ bool draw_accepted(const SmallArgs<T, NP>& a, uint64_
     return ok || (a.keep_last != 0);
 }
 
+// ---- warp-tile staging with 128-bit accesses (float, n % 4 == 0, 16-byte aligned base) ----
+// A warp owns 32 consecutive rows = 32*n contiguous floats in global memory.  Shared-memory row
+// stride n + 4 floats keeps rows 16-byte aligned and makes the per-thread row accesses
+// (LDS.128 / STS.128, one quarter-warp per phase) bank-conflict-free.
+__device__ __forceinline__ void warp_tile_store_vec(const float* stage, int vstride, float* dst, int rows, int n, int lane) {
+    const int upr = n >> 2;                    // float4 units per row
+    const int total = rows * upr;
+    int r = lane / upr, c = lane - r * upr;
+    const int dr = 32 / upr, dc = 32 - dr * upr;
+    for (int u = lane; u < total; u += 32) {
+        const float4 v = *reinterpret_cast<const float4*>(stage + r * vstride + 4 * c);
+        __stcs(reinterpret_cast<float4*>(dst) + u, v);          // streaming store: written once, never re-read
+        r += dr; c += dc;
+        if (c >= upr) { c -= upr; ++r; }
+    }
+}
+__device__ __forceinline__ void warp_tile_load_vec(float* stage, int vstride, const float* src, int rows, int n, int lane) {
+    const int upr = n >> 2;
+    const int total = rows * upr;
+    int r = lane / upr, c = lane - r * upr;
+    const int dr = 32 / upr, dc = 32 - dr * upr;
+    for (int u = lane; u < total; u += 32) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(src) + u);
+        *reinterpret_cast<float4*>(stage + r * vstride + 4 * c) = v;
+        r += dr; c += dc;
+        if (c >= upr) { c -= upr; ++r; }
+    }
+}
+
 // K portfolios per thread and iteration: every Sigma / mu operand fetched from the constant
 // bank (LDCU -> uniform register) feeds K FFMAs, the K Philox / lg2 chains are independent
 // (ILP), and the loop / index overhead is paid once per K portfolios.
@@ -135,7 +164,10 @@ template <typename T, int NP, int K, int SRC /*0 Philox, 1 supplied*/, bool BOUN
 __global__ void __launch_bounds__(PF_BLOCK) small_sweep(const __grid_constant__ SmallArgs<T, NP> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int stride = a.n | 1;                                  // odd row stride: conflict-free
+    // 128-bit staging when rows are float4-tileable (see warp_tile_*_vec), else odd scalar stride
+    const bool vec = sizeof(T) == 4 && (a.n & 3) == 0 && (reinterpret_cast<uintptr_t>(a.w_in) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(a.w_out) & 15) == 0;
+    const int stride = vec ? a.n + 4 : (a.n | 1);
     T* stage = reinterpret_cast<T*>(smem_raw) + (size_t)warp * 32 * stride;
     const int q32 = 32 / a.n, m32 = 32 % a.n;
 
@@ -164,17 +196,32 @@ __global__ void __launch_bounds__(PF_BLOCK) small_sweep(const __grid_constant__ 
                 const uint64_t warp_row0 = local - lane;
                 const int rows = warp_row0 >= a.P ? 0 : (int)((a.P - warp_row0) < 32 ? (a.P - warp_row0) : 32);
                 const T* src = a.w_in + warp_row0 * (uint64_t)a.n;
-                const int total = rows * a.n;
-                int rr = lane / a.n, cc = lane % a.n;
-                for (int f = lane; f < total; f += 32) {
-                    stage[rr * stride + cc] = src[f];
-                    rr += q32; cc += m32;
-                    if (cc >= a.n) { cc -= a.n; ++rr; }
-                }
-                __syncwarp();
+                if constexpr (sizeof(T) == 4) {
+                    if (vec) {
+                        warp_tile_load_vec(reinterpret_cast<float*>(stage), stride, reinterpret_cast<const float*>(src), rows, a.n, lane);
+                        __syncwarp();
 #pragma unroll
-                for (int i = 0; i < NP; ++i) e[k][i] = (active && i < a.n) ? stage[lane * stride + i] : (T)0;
-                __syncwarp();
+                        for (int i = 0; i < NP; i += 4) {
+                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (active && i < a.n) v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(stage) + lane * stride + i);
+                            e[k][i] = v.x; e[k][i + 1] = v.y; e[k][i + 2] = v.z; e[k][i + 3] = v.w;
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (!vec) {
+                    const int total = rows * a.n;
+                    int rr = lane / a.n, cc = lane % a.n;
+                    for (int f = lane; f < total; f += 32) {
+                        stage[rr * stride + cc] = src[f];
+                        rr += q32; cc += m32;
+                        if (cc >= a.n) { cc -= a.n; ++rr; }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) e[k][i] = (active && i < a.n) ? stage[lane * stride + i] : (T)0;
+                    __syncwarp();
+                }
                 if (BOUNDS) accepted[k] = active && (in_bounds<T, NP>(a, e[k], (T)1) || a.keep_last != 0);
             } else if (BOUNDS) {
                 if (active) accepted[k] = draw_accepted<T, NP, true>(a, a.first + local, e[k], s[k]);
@@ -216,19 +263,34 @@ __global__ void __launch_bounds__(PF_BLOCK) small_sweep(const __grid_constant__ 
             }
             if (a.w_out != nullptr) {
                 const T inv = SRC == 1 ? (T)1 : Math<T>::rcp(s[k]);
-#pragma unroll
-                for (int i = 0; i < NP; ++i)
-                    if (i < a.n) stage[lane * stride + i] = e[k][i] * inv;
-                __syncwarp();
                 const uint64_t warp_row0 = local - lane;
                 const int rows = warp_row0 >= a.P ? 0 : (int)((a.P - warp_row0) < 32 ? (a.P - warp_row0) : 32);
                 T* dst = a.w_out + warp_row0 * (uint64_t)a.n;
-                const int total = rows * a.n;
-                int rr = lane / a.n, cc = lane % a.n;
-                for (int f = lane; f < total; f += 32) {
-                    dst[f] = stage[rr * stride + cc];
-                    rr += q32; cc += m32;
-                    if (cc >= a.n) { cc -= a.n; ++rr; }
+                bool done = false;
+                if constexpr (sizeof(T) == 4) {
+                    if (vec) {
+#pragma unroll
+                        for (int i = 0; i < NP; i += 4)
+                            if (i < a.n)
+                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(stage) + lane * stride + i) =
+                                    make_float4(e[k][i] * inv, e[k][i + 1] * inv, e[k][i + 2] * inv, e[k][i + 3] * inv);
+                        __syncwarp();
+                        warp_tile_store_vec(reinterpret_cast<const float*>(stage), stride, reinterpret_cast<float*>(dst), rows, a.n, lane);
+                        done = true;
+                    }
+                }
+                if (!done) {
+#pragma unroll
+                    for (int i = 0; i < NP; ++i)
+                        if (i < a.n) stage[lane * stride + i] = e[k][i] * inv;
+                    __syncwarp();
+                    const int total = rows * a.n;
+                    int rr = lane / a.n, cc = lane % a.n;
+                    for (int f = lane; f < total; f += 32) {
+                        dst[f] = stage[rr * stride + cc];
+                        rr += q32; cc += m32;
+                        if (cc >= a.n) { cc -= a.n; ++rr; }
+                    }
                 }
                 __syncwarp();
             }
@@ -276,7 +338,12 @@ template <int NP, int K>
 __global__ void __launch_bounds__(PF_BLOCK) small_sweep_packed(const __grid_constant__ SmallArgs<float, NP> a) {
     static_assert(K % 2 == 0, "packed sweep pairs portfolios");
     constexpr int KP = K / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool vec = (a.n & 3) == 0 && (reinterpret_cast<uintptr_t>(a.w_out) & 15) == 0;
+    const int stride = vec ? a.n + 4 : (a.n | 1);
+    float* stage = reinterpret_cast<float*>(smem_raw) + (size_t)warp * 32 * stride;
+    const int q32 = 32 / a.n, m32 = 32 % a.n;
     const uint64_t n_sub = (a.P + PF_BLOCK - 1) / PF_BLOCK;
     const uint64_t n_tiles = (n_sub + K - 1) / K;
     constexpr uint32_t NONE = 0xffffffffu;
@@ -351,6 +418,41 @@ __global__ void __launch_bounds__(PF_BLOCK) small_sweep_packed(const __grid_cons
                 if (a.risk_out != nullptr) a.risk_out[local] = risk;
                 if (a.sharpe_out != nullptr) a.sharpe_out[local] = sharpe;
                 if (a.acc_out != nullptr) a.acc_out[local] = 1;
+            }
+            if (a.w_out != nullptr) {
+                // w_i = e_i / s = l_i * (-1 / s): stage this thread's row, then the warp streams the tile out
+                const float ninv = -Math<float>::rcp(s);
+                const uint64_t warp_row0 = local - lane;
+                const int rows = warp_row0 >= a.P ? 0 : (int)((a.P - warp_row0) < 32 ? (a.P - warp_row0) : 32);
+                float* dst = a.w_out + warp_row0 * (uint64_t)a.n;
+                if (vec) {
+#pragma unroll
+                    for (int i = 0; i < NP; i += 4) {
+                        if (i < a.n) {
+                            float4 w4;
+                            w4.x = ((k & 1) ? l2[k / 2][i + 0].y : l2[k / 2][i + 0].x) * ninv;
+                            w4.y = ((k & 1) ? l2[k / 2][i + 1].y : l2[k / 2][i + 1].x) * ninv;
+                            w4.z = ((k & 1) ? l2[k / 2][i + 2].y : l2[k / 2][i + 2].x) * ninv;
+                            w4.w = ((k & 1) ? l2[k / 2][i + 3].y : l2[k / 2][i + 3].x) * ninv;
+                            *reinterpret_cast<float4*>(stage + lane * stride + i) = w4;
+                        }
+                    }
+                    __syncwarp();
+                    warp_tile_store_vec(stage, stride, dst, rows, a.n, lane);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NP; ++i)
+                        if (i < a.n) stage[lane * stride + i] = ((k & 1) ? l2[k / 2][i].y : l2[k / 2][i].x) * ninv;
+                    __syncwarp();
+                    const int total = rows * a.n;
+                    int rr = lane / a.n, cc = lane % a.n;
+                    for (int f = lane; f < total; f += 32) {
+                        dst[f] = stage[rr * stride + cc];
+                        rr += q32; cc += m32;
+                        if (cc >= a.n) { cc -= a.n; ++rr; }
+                    }
+                }
+                __syncwarp();
             }
         }
     }
@@ -464,7 +566,7 @@ static int small_launch_k(mcp_context* h, PfJob& job, const SmallArgs<T, NP>& a)
     if (job.w_in) kern = job.bounds ? small_sweep<T, NP, K, 1, true> : small_sweep<T, NP, K, 1, false>;
     else kern = job.bounds ? small_sweep<T, NP, K, 0, true> : small_sweep<T, NP, K, 0, false>;
     const bool staging = job.w_in != nullptr || job.w_out != nullptr;
-    const size_t smem = staging ? (size_t)(PF_BLOCK / 32) * 32 * (job.n | 1) * sizeof(T) : 0;
+    const size_t smem = staging ? (size_t)(PF_BLOCK / 32) * 32 * (job.n + 4) * sizeof(T) : 0;
     if (smem > 48 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     MCP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PF_BLOCK, smem));
@@ -484,8 +586,10 @@ static int small_launch_k(mcp_context* h, PfJob& job, const SmallArgs<T, NP>& a)
 template <int NP, int K>
 static int small_launch_packed(mcp_context* h, PfJob& job, const SmallArgs<float, NP>& a) {
     auto kern = small_sweep_packed<NP, K>;
+    const size_t smem = job.w_out ? (size_t)(PF_BLOCK / 32) * 32 * (job.n + 4) * sizeof(float) : 0;
+    if (smem > 48 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    MCP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PF_BLOCK, 0));
+    MCP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PF_BLOCK, smem));
     if (per_sm < 1) return mcp_fail(h, MCP_ERR_CUDA, "small_sweep_packed<N=%d>: zero occupancy", NP);
     const uint64_t n_tiles = ((job.P + PF_BLOCK - 1) / PF_BLOCK + K - 1) / K;
     uint64_t grid = (uint64_t)h->prop.multiProcessorCount * per_sm;
@@ -493,7 +597,7 @@ static int small_launch_packed(mcp_context* h, PfJob& job, const SmallArgs<float
     if (grid > (uint64_t)job.max_blocks) grid = job.max_blocks;
     if (grid < 1) grid = 1;
     job.blocks_used = (int)grid;
-    kern<<<(unsigned)grid, PF_BLOCK, 0, job.stream>>>(a);
+    kern<<<(unsigned)grid, PF_BLOCK, smem, job.stream>>>(a);
     MCP_CUDA(h, cudaGetLastError());
     h->launches++;
     return MCP_OK;
@@ -507,7 +611,7 @@ int pf_small_launch_t(mcp_context* h, PfJob& job) {
     // weight write-back the kernel is memory-side bound and the extra registers only cost occupancy
     constexpr int K = SweepK<T, NP>::value;
     if constexpr (sizeof(T) == 4 && K % 2 == 0) {
-        if (job.w_in == nullptr && job.w_out == nullptr && !job.bounds) return small_launch_packed<NP, K>(h, job, a);
+        if (job.w_in == nullptr && !job.bounds) return small_launch_packed<NP, K>(h, job, a);
     }
     if (K > 1 && job.w_in == nullptr && job.w_out == nullptr) return small_launch_k<T, NP, K>(h, job, a);
     return small_launch_k<T, NP, 1>(h, job, a);

@@ -26,3 +26,8 @@ for _ in range(2):
 print("paths", 1_000_000 * 252 / o["kernel_ms"] * 1e3, "path-steps/s", o["stats"])
 r64 = mcp.simulate_portfolios(mu, sigma, 100_000_000, risk_free=0.03, seed=0, return_arrays=False, dtype="float64")
 print("sweep f64", 100_000_000 / r64.kernel_ms * 1e3, "pf/s")
+
+mu256, sigma256 = synthetic_inputs(256)
+for _ in range(2):
+    r256 = mcp.simulate_portfolios(mu256, sigma256, 4_000_000, risk_free=0.03, seed=0, return_arrays=False)
+print("sweep N=256", 4_000_000 / r256.kernel_ms * 1e3, "pf/s")
