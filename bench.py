@@ -39,6 +39,9 @@ N_ASSETS = 16
 P_TOTAL = 10_000_000_000          # C3
 M_PATHS = 10_000_000              # C4
 N_STEPS = 252
+N_LARGE = 256                     # C5
+P_LARGE = 1_000_000_000
+N_BINS = 512
 RISK_FREE, RISK_TARGET, SEED = 0.03, 0.30, 0
 
 
@@ -252,6 +255,38 @@ def run_ours(args):
     paths_kernel_s = statistics.mean(p_kms) * 1e-3
     my_paths = mdist.shard_range(m_total, rank, world)[1]
 
+    # ---- third workload: C5 envelope, N = 256 (two sweeps per step: risk range, then binning) ----
+    env_line = None
+    if args.envelope_portfolios > 0:
+        mu_l, sigma_l = synthetic_inputs(N_LARGE)
+        pl = args.envelope_portfolios
+
+        def envelope():
+            if world > 1:
+                return mdist.frontier_envelope_sharded(mu_l, sigma_l, pl, N_BINS, risk_free=RISK_FREE, risk_target=RISK_TARGET,
+                                                       seed=SEED, dtype="float32", device=local)
+            return mcp.frontier_envelope(mu_l, sigma_l, pl, N_BINS, risk_free=RISK_FREE, risk_target=RISK_TARGET, seed=SEED,
+                                         dtype="float32", device=local)
+
+        e_steps = max(1, min(args.steps, 2))
+        e_dev_s, e_host_s, e_kms, e_res = timed(envelope, e_steps, 1)
+        my_pl = mdist.shard_range(pl, rank, world)[1]
+        env = e_res.extra["envelope"]
+        env_line = {"metric": "portfolios/sec (256 assets, envelope)", "value": pl * e_steps / e_dev_s, "unit": "portfolios/s",
+                    "ms_per_step": e_dev_s / e_steps * 1e3, "steps": e_steps, "warmup": 1,
+                    "config": {"workload": f"C5: synthetic 256-asset covariance, {pl:.0e} portfolios, frontier envelope in {N_BINS} risk "
+                                           "bins + 30%-risk pick; one step = range sweep + binning sweep (each portfolio evaluated twice)",
+                               "n_assets": N_LARGE, "n_bins": N_BINS},
+                    "e2e": {"value": pl * e_steps / e_host_s, "unit": "portfolios/s", "h2d_bytes_per_step": 2 * 8 * (N_LARGE + N_LARGE ** 2),
+                            "d2h_bytes_per_step": 2 * (2 * (5 + N_LARGE) * 8 + 56) + 16 * N_BINS},
+                    "filled_bins": int((env["best_index"] >= 0).sum()),
+                    "target_risk": {"index": e_res.target_risk["global_index"], "risk": e_res.target_risk["risk"]},
+                    "roofline": {"bound": "fp32-simt", "kernel": "large_sweep (tiled, FFMA2)", "unit": "TFLOP/s",
+                                 "achieved": my_pl * flops_per_portfolio(N_LARGE) / (statistics.mean(e_kms) * 1e-3) / 1e12,
+                                 "algorithmic_flop_per_portfolio": flops_per_portfolio(N_LARGE),
+                                 "kernel_ms": statistics.mean(e_kms),
+                                 "note": "kernel_ms = the binning sweep of one step (the range sweep costs the same)"}}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -266,7 +301,10 @@ def run_ours(args):
     if os.path.isfile(tpath):
         with open(tpath) as fh:
             traffic = json.load(fh).get("small_sweep_f32_16_rng")
-    roofline = {"bound": "fp32-simt", "kernel": "small_sweep<float,16,Philox,no-bounds>", "achieved": achieved,
+    if env_line:
+        env_line["roofline"]["peak"] = fma_peak
+        env_line["roofline"]["frac"] = env_line["roofline"]["achieved"] / fma_peak
+    roofline = {"bound": "fp32-simt", "kernel": "small_sweep_packed<16,4> (Philox, FFMA2, no write-back)", "achieved": achieved,
                 "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak, "traffic": traffic,
                 "peak_source": "FFMA-chain microbenchmark (mcp_measure_fma_peak) run in this process; "
                                "MEASURED_PEAKS.json has no SIMT figure",
@@ -275,7 +313,7 @@ def run_ours(args):
                 "note": "RNG mode without write-back does 0 algorithmic HBM bytes; Philox (IMAD) and lg2 (MUFU) work "
                         "is not counted as flops"}
     p_achieved = my_paths * N_STEPS * flops_per_path_step(n) / paths_kernel_s / 1e12
-    paths_roofline = {"bound": "fp32-simt", "kernel": "path_kernel<float,16,Philox>", "achieved": p_achieved, "peak": fma_peak,
+    paths_roofline = {"bound": "fp32-simt", "kernel": "path_kernel_packed<16> (Philox, FFMA2)", "achieved": p_achieved, "peak": fma_peak,
                       "unit": "TFLOP/s", "frac": p_achieved / fma_peak, "traffic": None,
                       "algorithmic_flop_per_path_step": flops_per_path_step(n), "kernel_ms": paths_kernel_s * 1e3}
 
@@ -286,7 +324,7 @@ def run_ours(args):
         for _ in range(2):
             r = mcp.simulate_portfolios(mu, sigma, Pw, risk_free=RISK_FREE, seed=SEED, return_arrays="device", device=local)
         gbs = Pw * (n + 3) * 4 / (r.kernel_ms * 1e-3) / 1e9
-        wb = {"bound": "hbm", "kernel": "small_sweep<float,16,Philox> + write-back", "achieved": gbs, "peak": peaks["hbm_gbs"],
+        wb = {"bound": "hbm", "kernel": "small_sweep_packed<16,4> + write-back of all arrays", "achieved": gbs, "peak": peaks["hbm_gbs"],
               "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "peak_source": peaks["source"],
               "algorithmic_bytes_per_portfolio": (n + 3) * 4, "portfolios_per_launch": Pw, "kernel_ms": r.kernel_ms}
         del r
@@ -352,6 +390,7 @@ def run_ours(args):
                           "h2d_bytes_per_step": 8 * (2 * n + n * n), "d2h_bytes_per_step": 4 * 8},
                   "stats": {str(a): list(v) for a, v in p_res["stats"].items()},
                   "roofline": paths_roofline, "cpu_baseline": cpu_paths},
+        "envelope": env_line,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -366,6 +405,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--portfolios", type=int, default=P_TOTAL, help="portfolios per step (default: C3's 1e10)")
     ap.add_argument("--paths", type=int, default=M_PATHS, help="paths per step (default: C4's 1e7)")
+    ap.add_argument("--envelope-portfolios", type=int, default=P_LARGE, help="C5 portfolios per step (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

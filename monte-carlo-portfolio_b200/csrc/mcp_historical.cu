@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(HV_BLOCK) hist_var_kernel(const HistArgs<T> a)
 template <typename T, int VPL>
 static int hist_launch_t(mcp_context* h, const HistArgs<T>& a, size_t smem, int max_blocks, int* blocks, cudaStream_t st) {
     auto kern = hist_var_kernel<T, VPL>;
-    if (smem > 48 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     MCP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HV_BLOCK, smem));
     if (per_sm < 1) return mcp_fail(h, MCP_ERR_INVALID, "mcp_historical_var: returns matrix does not fit in shared memory (%zu B)", smem);

@@ -546,7 +546,7 @@ static int large_launch_generic(mcp_context* h, PfJob& job) {
     a.k0 = (uint32_t)job.seed; a.k1 = (uint32_t)(job.seed >> 32);
     a.rf = (T)job.rf; a.target = (T)job.target;
     const size_t smem = (size_t)GEN_WARPS * np * sizeof(T);
-    if (smem > 48 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(generic_sweep<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(generic_sweep<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     MCP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, generic_sweep<T>, GEN_THREADS, smem));
     if (per_sm < 1) return mcp_fail(h, MCP_ERR_CUDA, "generic_sweep: zero occupancy (smem %zu B)", smem);

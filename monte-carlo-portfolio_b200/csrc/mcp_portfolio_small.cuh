@@ -14,6 +14,8 @@
 // Supplied-weights mode stages each warp's 32 rows through padded shared memory so global
 // loads / stores are fully coalesced while each thread still owns one row.
 #pragma once
+#include <cstdlib>
+
 #include "mcp_device.cuh"
 #include "mcp_portfolio.h"
 
@@ -567,7 +569,7 @@ static int small_launch_k(mcp_context* h, PfJob& job, const SmallArgs<T, NP>& a)
     else kern = job.bounds ? small_sweep<T, NP, K, 0, true> : small_sweep<T, NP, K, 0, false>;
     const bool staging = job.w_in != nullptr || job.w_out != nullptr;
     const size_t smem = staging ? (size_t)(PF_BLOCK / 32) * 32 * (job.n + 4) * sizeof(T) : 0;
-    if (smem > 48 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     MCP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PF_BLOCK, smem));
     if (per_sm < 1) return mcp_fail(h, MCP_ERR_CUDA, "small_sweep<N=%d>: zero occupancy (smem %zu B)", NP, smem);
@@ -587,7 +589,7 @@ template <int NP, int K>
 static int small_launch_packed(mcp_context* h, PfJob& job, const SmallArgs<float, NP>& a) {
     auto kern = small_sweep_packed<NP, K>;
     const size_t smem = job.w_out ? (size_t)(PF_BLOCK / 32) * 32 * (job.n + 4) * sizeof(float) : 0;
-    if (smem > 48 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     MCP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PF_BLOCK, smem));
     if (per_sm < 1) return mcp_fail(h, MCP_ERR_CUDA, "small_sweep_packed<N=%d>: zero occupancy", NP);
@@ -611,7 +613,13 @@ int pf_small_launch_t(mcp_context* h, PfJob& job) {
     // weight write-back the kernel is memory-side bound and the extra registers only cost occupancy
     constexpr int K = SweepK<T, NP>::value;
     if constexpr (sizeof(T) == 4 && K % 2 == 0) {
-        if (job.w_in == nullptr && !job.bounds) return small_launch_packed<NP, K>(h, job, a);
+        if (job.w_in == nullptr && !job.bounds) {
+            if constexpr (K == 4) {
+                static const int k_override = getenv("MCP_SWEEP_K") ? atoi(getenv("MCP_SWEEP_K")) : 0;   // tuning knob
+                if (k_override == 2) return small_launch_packed<NP, 2>(h, job, a);
+            }
+            return small_launch_packed<NP, K>(h, job, a);
+        }
     }
     if (K > 1 && job.w_in == nullptr && job.w_out == nullptr) return small_launch_k<T, NP, K>(h, job, a);
     return small_launch_k<T, NP, 1>(h, job, a);

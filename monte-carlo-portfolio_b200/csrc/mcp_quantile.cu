@@ -205,11 +205,11 @@ int mcp_select_hist(mcp_handle h, const void* values_dev, int dtype, uint64_t n,
     for (int k = 0; k < s->n_slots; ++k) slots.prefix[k] = s->slot_prefix[k];
     const size_t smem = sizeof(unsigned int) * s->n_slots * nb;
     if (dtype == MCP_F64) {
-        if (smem > 48 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(select_hist_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(select_hist_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         select_hist_kernel<double><<<grid_for(h, n, 4), SEL_BLOCK, smem, st>>>((const double*)values_dev, n, s->n_slots, slots, shift, bits,
                                                                                 (unsigned long long*)hist_dev);
     } else {
-        if (smem > 48 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(select_hist_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(select_hist_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         select_hist_kernel<float><<<grid_for(h, n, 4), SEL_BLOCK, smem, st>>>((const float*)values_dev, n, s->n_slots, slots, shift, bits,
                                                                                (unsigned long long*)hist_dev);
     }

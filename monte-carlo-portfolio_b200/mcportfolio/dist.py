@@ -109,6 +109,60 @@ def simulate_portfolios_sharded(mean_returns, cov_matrix, n_portfolios, *, group
     return r
 
 
+def frontier_envelope_sharded(mean_returns, cov_matrix, n_portfolios, n_bins=512, *, risk_range=None, group=None, **kw):
+    """`frontier_envelope` over the whole job (C5).  Two sweeps of this rank's block: the first
+    finds the attained risk range (all-reduced min / max), the second bins; the per-rank bins
+    (n_bins x (return, global index)) are all-gathered and merged (larger return, then lower
+    index), so every rank ends with the envelope of the WHOLE job."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    first, count = shard_range(n_portfolios, rank, world)
+    n = len(np.asarray(mean_returns))
+    eng = api.get_engine(kw.get("device"))
+    nccl = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", eng.device) if nccl else torch.device("cpu")
+    kw = dict(kw, return_arrays=False)
+    if risk_range is None:
+        probe = api.simulate_portfolios(mean_returns, cov_matrix, count, first_index=first, **kw)
+        lo, hi = probe.risk_range if probe.n_accepted else (float("inf"), float("-inf"))
+        t = torch.tensor([-lo, hi], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        lo, hi = -float(t[0]), float(t[1])
+        if not hi > lo:
+            hi = lo + max(abs(lo), 1.0) * 1e-6
+        risk_range = (lo, hi)
+    r = api.simulate_portfolios(mean_returns, cov_matrix, count, first_index=first, n_bins=n_bins,
+                                risk_range=risk_range, **kw)
+    env = r.extra["envelope"]
+    ret = torch.from_numpy(np.ascontiguousarray(env["best_return"])).to(dev)
+    idx = torch.from_numpy(np.ascontiguousarray(env["best_index"])).to(dev)
+    g_ret = [torch.empty_like(ret) for _ in range(world)]
+    g_idx = [torch.empty_like(idx) for _ in range(world)]
+    dist.all_gather(g_ret, ret, group=group)
+    dist.all_gather(g_idx, idx, group=group)
+    env["best_return"], env["best_index"] = merge_envelopes([t.cpu().numpy() for t in g_ret], [t.cpu().numpy() for t in g_idx])
+    for name, larger in (("max_sharpe", True), ("target_risk", False)):
+        rec = getattr(r, name)
+        if rec is not None:
+            rec = dict(rec, index=rec["global_index"])
+        setattr(r, name, merge_records(all_gather_records(rec, n, dev if nccl else None, group), larger))
+    r.extra["risk_range_global"] = risk_range
+    return r
+
+
+def merge_envelopes(returns_list, index_list):
+    """Per bin: the larger return wins, ties go to the lower global index; -1 marks an empty bin."""
+    best = np.array(returns_list[0], dtype=np.float64, copy=True)
+    idx = np.array(index_list[0], dtype=np.int64, copy=True)
+    for r, i in zip(returns_list[1:], index_list[1:]):
+        r = np.asarray(r, dtype=np.float64)
+        i = np.asarray(i, dtype=np.int64)
+        take = (i >= 0) & ((idx < 0) | (r > best) | ((r == best) & (i < idx)))
+        best[take], idx[take] = r[take], i[take]
+    return best, idx
+
+
 # ---- VaR / CVaR merge ------------------------------------------------------------------------
 
 class _DeviceBuffer:

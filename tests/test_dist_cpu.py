@@ -39,6 +39,16 @@ def test_merge_records_first_occurrence():
     assert unpack_record(*pack_record(big, 2))["global_index"] == 2**40 + 12345
 
 
+def test_merge_envelopes():
+    from mcportfolio.dist import merge_envelopes
+    a_r, a_i = np.array([1.0, -np.inf, 3.0, 2.0]), np.array([5, -1, 7, 9])
+    b_r, b_i = np.array([1.0, 4.0, 2.5, -np.inf]), np.array([2, 11, 8, -1])
+    best, idx = merge_envelopes([a_r, b_r], [a_i, b_i])
+    assert list(idx) == [2, 11, 7, 9] and list(best) == [1.0, 4.0, 3.0, 2.0]
+    best2, idx2 = merge_envelopes([b_r, a_r], [b_i, a_i])                 # order-independent
+    assert list(idx2) == list(idx) and list(best2) == list(best)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
