@@ -1,0 +1,60 @@
+"""CPU tier: the ingest mirror (f3) -- investing.com CSV format, thousands separators, aliases."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+CSV_A = ('﻿"Date","Price","Open","High","Low","Vol.","Change %"\n'
+         '"03/16/2025","86,493.0","86,397.0","95,283.0","81,740.0","10.27K","0.13%"\n'
+         '"03/09/2025","86,382.5","96,721.0","96,767.0","78,651.0","18.69K","-10.69%"\n'
+         '"03/02/2025","96,700.0","94,000.0","99,000.0","93,000.0","9.1K","2.9%"\n'
+         '"02/23/2025","950.25","94,000.0","99,000.0","93,000.0","9.1K","2.9%"\n')
+CSV_B = ('exported by somebody\nsecond junk line\nDate,Close\n2025-02-23,10.0\n2025-03-02,11.0\n2025-03-09,bad\n'
+         '2025-03-16,12.1\nnot a date,5\n')
+
+
+def test_read_price_csv_handles_bom_quotes_and_thousands():
+    from mcportfolio import data
+    df = data.read_price_csv(io.StringIO(CSV_A))
+    assert list(df.columns) == ["Date", "Price"] and len(df) == 4
+    assert df["Price"].tolist() == [86493.0, 86382.5, 96700.0, 950.25]          # the reference would keep only 950.25
+    assert str(df["Date"].iloc[0].date()) == "2025-03-16"
+
+
+def test_header_sniffing_and_bad_rows():
+    from mcportfolio import data
+    df = data.read_price_csv(io.StringIO(CSV_B))
+    assert df["Price"].tolist() == [10.0, 11.0, 12.1] and len(df) == 3
+    with pytest.raises(ValueError, match="date"):
+        data.read_price_csv(io.StringIO("a,b\n1,2\n3,4\n"))
+    with pytest.raises(ValueError, match="no valid rows"):
+        data.read_price_csv(io.StringIO("Date,Price\nxx,yy\n"))
+
+
+def test_price_frame_join_resample_and_returns():
+    from mcportfolio import data
+    a = data.read_price_csv(io.StringIO(CSV_A))
+    b = data.read_price_csv(io.StringIO(CSV_B))
+    prices = data.price_frame([a, b], ["A", "A"], rule="W")                     # duplicate names get a suffix
+    assert list(prices.columns) == ["A", "A (2)"]
+    assert len(prices) == 3                                                     # 03/09 has no valid B price -> inner join drops it
+    r = data.returns_matrix(prices).to_numpy()
+    assert np.all(r[0] == 0.0) and np.isclose(r[1, 1], 0.1)
+    mu, sigma = data.mu_sigma(r, 52)
+    assert mu.shape == (2,) and sigma.shape == (2, 2) and np.allclose(sigma, sigma.T)
+    for rule in ("M", "Q"):                                                     # the app's aliases work on pandas >= 2.2
+        assert len(data.price_frame([a, b], ["A", "B"], rule=rule)) >= 1
+
+
+@pytest.mark.needs_reference
+def test_c1_files_reproduce_the_golden_inputs():
+    from mcportfolio import data
+    d = "/root/reference/data"
+    R, names, mu, sigma = data.load([os.path.join(d, "BTC_USD 7 Years Weekly.csv"), os.path.join(d, "ETH_USD 7 Years Weekly.csv")],
+                                    ["BTC", "ETH"], rule="W")
+    g = load_golden("c1_btc_eth.npz")
+    assert R.shape == (365, 2) and np.allclose(R, g["returns_matrix"], rtol=0, atol=0)
+    assert np.allclose(mu, g["mu"], rtol=1e-13) and np.allclose(sigma, g["sigma"], rtol=1e-13)
