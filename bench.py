@@ -175,6 +175,11 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # keep stdout clean for the ONE JSON line: libraries (NCCL prints its version banner on
+    # stdout) write to fd 1, so fd 1 is pointed at stderr and the line goes to the saved fd
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
@@ -393,7 +398,7 @@ def run_ours(args):
                   "roofline": paths_roofline, "cpu_baseline": cpu_paths},
         "envelope": env_line,
     }
-    print(json.dumps(line), flush=True)
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

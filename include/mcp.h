@@ -215,6 +215,14 @@ typedef struct {
 int mcp_historical_var(mcp_handle h, const mcp_hist_params* params,
                        const double* returns_matrix_host /* [T, N] */, mcp_hist_out* out);
 
+/* ---- per-asset statistics (app.py:231-263 as combined by calc_asset_stats, 286-335) ---------
+ * returns_host: [T, N] FP64 row-major periodic returns.  stats_out: [N][MCP_STATS_FIELDS] FP64:
+ * 0 sharpe, 1 sortino, 2 volatility_ann, 3 total_return_ann, 4 mean_ann, 5 mean_period,
+ * 6 std_period (ddof=1), 7 min_period, 8 max_period, 9 max_drawdown, 10 var, 11 cvar.          */
+#define MCP_STATS_FIELDS 12
+int mcp_asset_stats(mcp_handle h, const double* returns_host, int n_periods, int n_assets, double risk_free,
+                    double annual_factor, double alpha, double* stats_out);
+
 /* ---- microbenchmarks used as roofline denominators (bench.py) ------------------------- */
 int mcp_measure_fma_peak(mcp_handle h, int dtype /* MCP_F32 | MCP_F64 | 2 = packed FP32x2 (FFMA2) */, double* tflops);
 

@@ -38,7 +38,8 @@ def translation_units():
            ("mcp_recheck", "mcp_recheck.cu", []),
            ("mcp_paths", "mcp_paths.cu", []),
            ("mcp_quantile", "mcp_quantile.cu", []),
-           ("mcp_historical", "mcp_historical.cu", [])]
+           ("mcp_historical", "mcp_historical.cu", []),
+           ("mcp_stats", "mcp_stats.cu", [])]
     for t, tag in (("float", "f32"), ("double", "f64")):
         for np_ in SMALL_NP:
             tus.append((f"mcp_small_{tag}_{np_}", "mcp_portfolio_small_inst.cu",

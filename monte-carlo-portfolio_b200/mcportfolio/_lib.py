@@ -110,6 +110,7 @@ SYMBOLS = {
                                   C.c_void_p]),
     "mcp_key_to_value": (C.c_double, [C.c_uint64, C.c_int]),
     "mcp_historical_var": (C.c_int, [C.c_void_p, C.POINTER(HistParams), C.c_void_p, C.POINTER(HistOut)]),
+    "mcp_asset_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p]),
     "mcp_measure_fma_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
 }
 

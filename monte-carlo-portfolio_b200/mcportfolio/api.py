@@ -544,3 +544,31 @@ def simulate_method(returns_matrix, method="Monte Carlo", n_portfolios=2500, *, 
             metrics, opt = -hv["cvar"], hv["best_cvar"]["index"]
     return {"risks": r.risks, "returns": r.returns, "weights": r.weights, "metrics": metrics,
             "opt_idx": int(opt), "opt_weights": np.asarray(r.weights[opt], dtype=np.float64)}
+
+
+STATS_FIELDS = ("sharpe", "sortino", "volatility_ann", "total_return_ann", "mean_ann", "mean_month",
+                "std_month", "min_month", "max_month", "max_drawdown", "var_95", "cvar_95")
+
+
+def asset_stats(returns_matrix, *, annual_factor=12, risk_free=0.0, alpha=0.95, device=None):
+    """Per-asset statistics of a (T, N) returns matrix: `calc_asset_stats` (app.py:286-335).
+
+    Returns a list of N dicts with the reference's keys (plus min_ann / max_ann / std_ann /
+    implied_vol, which app.py:301-310 derives from the same numbers)."""
+    R = np.ascontiguousarray(np.asarray(returns_matrix, dtype=np.float64))
+    if R.ndim == 1:
+        R = R[:, None]
+    if R.ndim != 2 or R.shape[0] < 1:
+        raise ValueError(f"returns_matrix must be (T, N) with T >= 1, got {R.shape}")
+    T, n = R.shape
+    out = np.empty((n, len(STATS_FIELDS)))
+    eng = get_engine(device)
+    check(eng.handle, lib().mcp_asset_stats(eng.handle, R.ctypes.data, T, n, float(risk_free), float(annual_factor),
+                                            float(alpha), out.ctypes.data))
+    res = []
+    for row in out:
+        d = dict(zip(STATS_FIELDS, (float(v) for v in row)))
+        d["implied_vol"] = d["std_ann"] = d["volatility_ann"]
+        d["min_ann"], d["max_ann"] = d["min_month"] * annual_factor, d["max_month"] * annual_factor
+        res.append(d)
+    return res

@@ -174,10 +174,19 @@ def main():
                         opt_var=res["VaR"]["opt_idx"], opt_cvar=res["CVaR"]["opt_idx"])
 
     # ---------------- per-asset stats (f2) verbatim: max_drawdown holds the only cumprod ----
-    stats = {"max_drawdown": [float(fns["max_drawdown"](pd.Series(R[:, j]))) for j in range(2)],
-             "annual_return": [float(fns["annual_return"](pd.Series(R[:, j]), 52)) for j in range(2)]}
+    def ref_stats(col, rf, A):
+        ser = pd.Series(col)
+        return {"sharpe": float(fns["sharpe_ratio"](ser, rf, A)), "sortino": float(fns["sortino_ratio"](ser, rf, A)),
+                "volatility_ann": float(fns["annual_volatility"](ser, A)), "total_return_ann": float(fns["annual_return"](ser, A)),
+                "mean_ann": float(np.mean(ser) * A), "mean_month": float(np.mean(ser)), "std_month": float(np.std(ser, ddof=1)),
+                "min_month": float(np.min(ser)), "max_month": float(np.max(ser)),
+                "max_drawdown": float(fns["max_drawdown"](ser)), "var_95": float(fns["var"](ser, 0.95)),
+                "cvar_95": float(fns["cvar"](ser, 0.95))}
+    stats = {"c1": {"risk_free": 0.03, "ann_factor": 52, "assets": [ref_stats(R[1:, j], 0.03, 52) for j in range(2)]},
+             "c2": {"risk_free": 0.0, "ann_factor": 252, "assets": [ref_stats(R2[1:, j], 0.0, 252) for j in range(R2.shape[1])]}}
     with open(os.path.join(GOLDEN, "asset_stats.json"), "w") as fh:
-        json.dump({"meta": meta, "c1": stats}, fh)
+        json.dump({"meta": meta, "note": "reference functions app.py:231-263 on the returns columns without the leading "
+                   "fillna(0) row (calc_asset_stats uses .dropna(), app.py:288)", **stats}, fh)
 
     with open(os.path.join(GOLDEN, "META.json"), "w") as fh:
         json.dump({**meta, "c1_shape": list(R.shape), "c2_shape": list(R2.shape),

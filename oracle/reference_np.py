@@ -58,6 +58,28 @@ def cvar(returns, alpha: float = 0.95) -> float:
 
 
 # --------------------------------------------------------------------------
+# f2  per-asset statistics                                app.py:231-256, 286-335
+# --------------------------------------------------------------------------
+
+def asset_stats(returns, risk_free=0.0, ann_factor=12, alpha=0.95):
+    """The statistics `calc_asset_stats` (app.py:286-335) derives from one returns series."""
+    r = np.asarray(returns, dtype=np.float64)
+    excess = r - risk_free / ann_factor                                   # app.py:232
+    std = np.std(r, ddof=1) if len(r) > 1 else np.nan
+    sharpe = 0.0 if np.std(excess, ddof=1) == 0 else np.mean(excess) / np.std(excess, ddof=1) * np.sqrt(ann_factor)
+    neg = excess[excess < 0]                                              # app.py:242-243
+    down = np.std(neg, ddof=1) if len(neg) > 0 else 0.0001
+    cum = np.cumprod(1 + r)                                               # app.py:253-256
+    peak = np.maximum.accumulate(cum)
+    return {"sharpe": sharpe, "sortino": np.mean(excess) / down * np.sqrt(ann_factor),
+            "volatility_ann": std * np.sqrt(ann_factor),
+            "total_return_ann": np.prod(1 + r) ** (ann_factor / len(r)) - 1,      # app.py:249
+            "mean_ann": np.mean(r) * ann_factor, "mean_month": np.mean(r), "std_month": std,
+            "min_month": np.min(r), "max_month": np.max(r), "max_drawdown": np.min((cum - peak) / peak),
+            "var_95": var(r, alpha), "cvar_95": cvar(r, alpha)}
+
+
+# --------------------------------------------------------------------------
 # a1  mu / Sigma estimation                               app.py:658-667, 679-680
 # --------------------------------------------------------------------------
 

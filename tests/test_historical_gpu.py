@@ -88,3 +88,31 @@ def test_methods_like_the_app(mcp, c1):
     assert np.allclose([ew["risks"][0], ew["returns"][0], ew["metrics"][0]], c1["ew_rf3"], rtol=1e-9)
     with pytest.raises(IndexError):
         mcp.simulate_method(R, "Equal Weight", annual_factor=52, min_weights=np.array([0.6, 0.0]))
+
+
+def test_asset_stats_kernel(mcp, c1, c2):
+    """f2: per-asset statistics (app.py:231-263, 286-335) against the reference functions' outputs."""
+    import json, os
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "asset_stats.json")) as fh:
+        g = json.load(fh)
+    for tag, R in (("c1", c1["returns_matrix"]), ("c2", c2["returns_matrix"])):
+        spec = g[tag]
+        got = mcp.asset_stats(R[1:], annual_factor=spec["ann_factor"], risk_free=spec["risk_free"])
+        assert len(got) == R.shape[1]
+        for j, want in enumerate(spec["assets"]):
+            for k, v in want.items():
+                assert got[j][k] == pytest.approx(v, rel=1e-10, abs=1e-14), (tag, j, k)
+    # odd lengths, a single period, all-positive series (no downside -> 0.0001, app.py:243)
+    rng = np.random.default_rng(3)
+    for T in (1, 2, 31, 33, 1000):
+        R = np.abs(rng.standard_normal((T, 3))) * 0.01
+        R[:, 1] *= -1
+        got = mcp.asset_stats(R, annual_factor=12, risk_free=0.0)
+        for j in range(3):
+            want = ref.asset_stats(R[:, j], 0.0, 12)
+            for k in ("total_return_ann", "max_drawdown", "mean_ann", "min_month", "max_month", "var_95", "cvar_95"):
+                assert got[j][k] == pytest.approx(want[k], rel=1e-10, abs=1e-14), (T, j, k)
+            if T > 2:
+                assert got[j]["sharpe"] == pytest.approx(want["sharpe"], rel=1e-9)
+                assert got[j]["sortino"] == pytest.approx(want["sortino"], rel=1e-9)

@@ -183,3 +183,14 @@ def test_envelope_oracle():
     rets = np.array([1.0, 2.0, 3.0, 3.0, 0.5, 9.0, 9.0])
     best, idx = paths_np.envelope(risks, rets, 2, 0.1, 0.3)
     assert list(idx) == [1, 2] and list(best) == [2.0, 3.0]
+
+
+def test_asset_stats_against_reference_functions(c1, c2):
+    with open(os.path.join(GOLDEN, "asset_stats.json")) as fh:
+        g = json.load(fh)
+    for tag, R in (("c1", c1["returns_matrix"]), ("c2", c2["returns_matrix"])):
+        spec = g[tag]
+        for j, want in enumerate(spec["assets"]):
+            got = ref.asset_stats(R[1:, j], spec["risk_free"], spec["ann_factor"])
+            for k, v in want.items():
+                assert got[k] == pytest.approx(v, rel=1e-12, abs=1e-15), (tag, j, k)
