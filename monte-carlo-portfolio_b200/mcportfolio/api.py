@@ -530,20 +530,23 @@ def simulate_method(returns_matrix, method="Monte Carlo", n_portfolios=2500, *, 
             raise IndexError("equal weights violate the bounds: the reference's arrays are empty (app.py:687, 747)")
         return {"risks": r.risks, "returns": r.returns, "weights": r.weights, "metrics": r.sharpes,
                 "opt_idx": 0, "opt_weights": np.asarray(r.weights[0], dtype=np.float64)}
+    historical = method in ("VaR", "CVaR")
+    # the VaR / CVaR methods keep the weights on the device between the sweep and the historical kernel
     r = simulate_portfolios(mu, sigma, int(n_portfolios), risk_free=risk_free, min_weights=min_weights,
-                            max_weights=max_weights, seed=seed, dtype=dtype, device=device)
+                            max_weights=max_weights, seed=seed, dtype=dtype, device=device,
+                            return_arrays="device" if historical else True)
     if r.n_accepted == 0:
         raise ValueError("no portfolio satisfied the bounds (the reference raises at argmax of an empty array, app.py:747)")
-    if method in ("Monte Carlo", "MPT"):
+    if not historical:
         metrics, opt = r.sharpes, r.max_sharpe["index"]
+        risks, returns, weights = r.risks, r.returns, r.weights
     else:
         hv = historical_var_cvar(R, r.weights, alpha, dtype=dtype, device=device)
-        if method == "VaR":
-            metrics, opt = -hv["var"], hv["best_var"]["index"]
-        else:
-            metrics, opt = -hv["cvar"], hv["best_cvar"]["index"]
-    return {"risks": r.risks, "returns": r.returns, "weights": r.weights, "metrics": metrics,
-            "opt_idx": int(opt), "opt_weights": np.asarray(r.weights[opt], dtype=np.float64)}
+        key, pick = ("var", "best_var") if method == "VaR" else ("cvar", "best_cvar")
+        metrics, opt = (-hv[key]).cpu().numpy(), hv[pick]["index"]
+        risks, returns, weights = r.risks.cpu().numpy(), r.returns.cpu().numpy(), r.weights.cpu().numpy()
+    return {"risks": risks, "returns": returns, "weights": weights, "metrics": metrics,
+            "opt_idx": int(opt), "opt_weights": np.asarray(weights[opt], dtype=np.float64)}
 
 
 STATS_FIELDS = ("sharpe", "sortino", "volatility_ann", "total_return_ann", "mean_ann", "mean_month",
