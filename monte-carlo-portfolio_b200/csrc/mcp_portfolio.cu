@@ -174,7 +174,19 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
     job.dtype = p->dtype;
     job.max_tries = p->max_tries;
     job.keep_last = p->keep_last;
-    job.bounds = p->min_weights != nullptr || p->max_weights != nullptr;
+    // weights always lie in [0, 1]: the app's default bounds 0 / 1 (app.py:453-454) can never reject,
+    // so only bounds that bite switch the rejection machinery on
+    job.bounds = supplied && (p->min_weights != nullptr || p->max_weights != nullptr);   // supplied rows may be anything
+    for (int i = 0; i < N; ++i) {
+        if (p->min_weights) {
+            MCP_REQUIRE(h, !std::isnan(p->min_weights[i]), "mcp_portfolios: min_weights[%d] is NaN", i);
+            job.bounds = job.bounds || p->min_weights[i] > 0.0;
+        }
+        if (p->max_weights) {
+            MCP_REQUIRE(h, !std::isnan(p->max_weights[i]), "mcp_portfolios: max_weights[%d] is NaN", i);
+            job.bounds = job.bounds || p->max_weights[i] < 1.0;
+        }
+    }
     job.seed = p->seed;
     job.rf = p->risk_free;
     job.target = p->risk_target;

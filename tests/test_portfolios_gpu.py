@@ -428,3 +428,16 @@ def test_fp32_near_ties_pick_the_fp64_index(mcp, n, space):
     # without the FP64 copy the FP32 screen alone decides (first occurrence among FP32 ties)
     r32 = mcp.simulate_portfolios(mu, sigma, P, weights=W.astype(np.float32), risk_free=0.03, dtype="float32")
     assert r32.max_sharpe["index"] == i_s and r32.target_risk["index"] == i_d
+
+
+def test_default_app_bounds_cost_nothing(mcp, synth16):
+    """The app always passes min = 0 / max = 1 (app.py:453-454): identical results to no bounds."""
+    mu, sigma = synth16
+    a = mcp.simulate_portfolios(mu, sigma, 100_000, risk_free=0.03, seed=6)
+    b = mcp.simulate_portfolios(mu, sigma, 100_000, risk_free=0.03, seed=6, min_weights=np.zeros(16), max_weights=np.ones(16))
+    assert np.array_equal(a.weights, b.weights) and np.array_equal(a.sharpes, b.sharpes)
+    assert a.max_sharpe["index"] == b.max_sharpe["index"] and b.n_accepted == 100_000
+    # supplied rows outside [0, 1] are still checked against explicit bounds
+    W = np.array([[0.5, 0.5] + [0.0] * 14, [1.5, -0.5] + [0.0] * 14])
+    r = mcp.simulate_portfolios(mu, sigma, 2, weights=W, min_weights=np.zeros(16), max_weights=np.ones(16), dtype="float64")
+    assert r.n_accepted == 1 and len(r.risks) == 1
