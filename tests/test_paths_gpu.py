@@ -109,3 +109,30 @@ def test_cholesky_failure_is_reported(mcp):
     bad = np.array([[1.0, 2.0], [2.0, 1.0]])
     with pytest.raises(mcp.McpError, match="positive definite"):
         mcp.simulate_paths(mu, bad, np.array([0.5, 0.5]), 10, 5)
+
+
+def test_rng_normals_distribution(mcp):
+    """Statistical tier for the in-kernel Box-Muller normals: with L = I, one step and dt = 1 the
+    terminal value of asset i is z_i, so the kernel's normals can be tested directly: moments,
+    independence across assets and a KS test of the marginal against the exact normal CDF."""
+    from math import erf
+    n, M = 16, 1_000_000
+    sigma = np.eye(n)
+    mu = np.zeros(n)
+    cols = []
+    for i in (0, 1, 7, 15):
+        w = np.zeros(n); w[i] = 1.0
+        x = mcp.simulate_paths(mu, sigma, w, M, 1, dt=1.0, seed=11, return_terminal=True)["terminal"].astype(np.float64)
+        cols.append(x)
+        assert abs(x.mean()) < 4.5 / np.sqrt(M) and abs(x.var() - 1) < 5 * np.sqrt(2 / M)
+        assert abs(((x - x.mean()) ** 3).mean()) < 0.02 and abs(((x - x.mean()) ** 4).mean() - 3) < 0.05
+        xs = np.sort(x[:200_000])
+        cdf = 0.5 * (1 + np.vectorize(erf)(xs / np.sqrt(2)))
+        ks = np.abs(cdf - (np.arange(len(xs)) + 0.5) / len(xs)).max()
+        assert ks < 1.63 / np.sqrt(len(xs)) * 1.3
+    c = np.corrcoef(np.stack(cols))
+    assert np.abs(c - np.eye(4)).max() < 5 / np.sqrt(M)          # (z0, z1) share a Box-Muller pair: still uncorrelated
+    # consecutive steps are independent: two-step compounding variance of log(1 + r) adds up
+    w = np.zeros(n); w[3] = 1.0
+    x2 = mcp.simulate_paths(mu, 1e-4 * sigma, w, M, 2, dt=1.0, seed=12, return_terminal=True)["terminal"].astype(np.float64)
+    assert np.isclose(x2.var(), 2e-4, rtol=0.01)

@@ -441,3 +441,20 @@ def test_default_app_bounds_cost_nothing(mcp, synth16):
     W = np.array([[0.5, 0.5] + [0.0] * 14, [1.5, -0.5] + [0.0] * 14])
     r = mcp.simulate_portfolios(mu, sigma, 2, weights=W, min_weights=np.zeros(16), max_weights=np.ones(16), dtype="float64")
     assert r.n_accepted == 1 and len(r.risks) == 1
+
+
+def test_rng_weight_histogram_chi_square(mcp):
+    """A single coordinate of a flat Dirichlet(N) is Beta(1, N-1): chi-square over 64 equal-mass bins,
+    for N = 4 and N = 16, and pairwise sums (w_i + w_j ~ Beta(2, N-2)) to catch cross-asset correlation."""
+    for N in (4, 16):
+        mu, sigma = synthetic_inputs(N)
+        P = 4_000_000
+        W = mcp.simulate_portfolios(mu, sigma, P, seed=21).weights.astype(np.float64)
+        edges = 1 - (1 - np.linspace(0, 1, 65)) ** (1 / (N - 1))                   # Beta(1, N-1) quantiles
+        for col in (0, N - 1):
+            counts = np.histogram(W[:, col], bins=edges)[0]
+            chi2 = ((counts - P / 64) ** 2 / (P / 64)).sum()
+            assert chi2 < 63 + 5 * np.sqrt(2 * 63), (N, col, chi2)
+        s = W[:, 0] + W[:, 1]                                                       # Beta(2, N-2): mean 2/N
+        assert abs(s.mean() - 2 / N) < 5 * np.sqrt(2 * (N - 2) / (N * N * (N + 1)) / P)
+        assert np.isclose(s.var(), 2 * (N - 2) / (N * N * (N + 1)), rtol=0.01)
