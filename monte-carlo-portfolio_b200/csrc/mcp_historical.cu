@@ -8,10 +8,11 @@
 // One warp per portfolio.  The returns matrix R (T x N) sits in shared memory, transposed and
 // padded so that lanes reading consecutive periods hit consecutive banks; the portfolio's
 // weights are a shared-memory broadcast.  Each lane owns periods lane, lane+32, ... of the
-// series in registers.  The two order statistics np.percentile needs are found exactly by an
-// MSB-first bitwise radix select on order-preserving keys with warp vote/reduce primitives
-// (32 or 64 REDUX rounds), the tail mean by a warp reduction; the selections reuse the
-// (key, first index) argmax machinery of the sweep.
+// series in registers.  The two order statistics np.percentile needs are found exactly on
+// order-preserving integer keys: for lower-tail ranks (k < 40, the reference's 5 % tail) by
+// sorting each lane's values and popping the warp-wide minimum k+1 times (shuffle min + ballot),
+// otherwise by an MSB-first bitwise radix select (32 or 64 REDUX rounds).  The tail mean is a
+// warp reduction; the selections reuse the (key, first index) argmax machinery of the sweep.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -24,6 +25,11 @@ namespace mcp {
 
 constexpr int HV_BLOCK = 256;
 constexpr int HV_WARPS = HV_BLOCK / 32;
+constexpr int HV_EXTRACT_MAX = 40;        // ranks below this are found by repeated warp-min extraction
+
+template <typename K> __device__ __forceinline__ K shfl_xor_key(K v, int m);
+template <> __device__ __forceinline__ uint32_t shfl_xor_key<uint32_t>(uint32_t v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <> __device__ __forceinline__ uint64_t shfl_xor_key<uint64_t>(uint64_t v, int m) { return __shfl_xor_sync(0xffffffffu, (unsigned long long)v, m); }
 
 template <typename T> struct HKey;
 template <> struct HKey<float> {
@@ -92,31 +98,65 @@ __global__ void __launch_bounds__(HV_BLOCK) hist_var_kernel(const HistArgs<T> a)
             const bool valid = lane + 32 * v < a.T_;
             key[v] = valid ? HKey<T>::to_key(x[v]) : ~(K)0;      // padding sorts last
         }
-        // ---- k_lo-th smallest key: MSB-first, count keys with the candidate prefix and bit 0 ----
-        K prefix = 0;
-        int rank = a.k_lo;
+        T v_lo, v_hi;
+        if (a.k_hi < HV_EXTRACT_MAX) {
+            // ---- lower-tail ranks (the reference's alpha = 0.95: k = 18 of T = 365): sort each lane's
+            // values once, then pop the warp-wide minimum k_hi + 1 times (5 shuffles + a register shift each)
+            K y[VPL];
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) y[v] = key[v];
+#pragma unroll
+            for (int round = 0; round < VPL; ++round) {          // odd-even transposition sort (ascending)
+#pragma unroll
+                for (int v = round & 1; v + 1 < VPL; v += 2) {
+                    const K lo = y[v] < y[v + 1] ? y[v] : y[v + 1], hi = y[v] < y[v + 1] ? y[v + 1] : y[v];
+                    y[v] = lo; y[v + 1] = hi;
+                }
+            }
+            K k_at_lo = 0, k_at_hi = 0;
 #pragma unroll 1
-        for (int b = HKey<T>::BITS - 1; b >= 0; --b) {
-            const K himask = b == HKey<T>::BITS - 1 ? (K)0 : (K)(~(K)0 << (b + 1));
-            int c = 0;
+            for (int r = 0; r <= a.k_hi; ++r) {
+                K m = y[0];
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) c += ((key[v] & himask) == prefix && !((key[v] >> b) & 1)) ? 1 : 0;
-            c = __reduce_add_sync(0xffffffffu, c);
-            if (rank >= c) { rank -= c; prefix |= (K)1 << b; }
-        }
-        const T v_lo = HKey<T>::from_key(prefix);
-        // (k_lo+1)-th: v_lo again if it is repeated far enough, else the smallest value above it
-        int le = 0;
-        T above = Math<T>::inf();
+                for (int d = 16; d >= 1; d >>= 1) { const K o = shfl_xor_key<K>(m, d); m = o < m ? o : m; }
+                if (r == a.k_lo) k_at_lo = m;
+                k_at_hi = m;
+                const unsigned owners = __ballot_sync(0xffffffffu, y[0] == m);
+                if (lane == __ffs(owners) - 1) {
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-            const bool valid = lane + 32 * v < a.T_;
-            le += (valid && key[v] <= prefix) ? 1 : 0;
-            if (valid && key[v] > prefix && x[v] < above) above = x[v];
+                    for (int v = 0; v + 1 < VPL; ++v) y[v] = y[v + 1];
+                    y[VPL - 1] = ~(K)0;
+                }
+            }
+            v_lo = HKey<T>::from_key(k_at_lo);
+            v_hi = HKey<T>::from_key(k_at_hi);
+        } else {
+            // ---- any rank: MSB-first radix select, count keys with the candidate prefix and bit 0 ----
+            K prefix = 0;
+            int rank = a.k_lo;
+#pragma unroll 1
+            for (int b = HKey<T>::BITS - 1; b >= 0; --b) {
+                const K himask = b == HKey<T>::BITS - 1 ? (K)0 : (K)(~(K)0 << (b + 1));
+                int c = 0;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) c += ((key[v] & himask) == prefix && !((key[v] >> b) & 1)) ? 1 : 0;
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (rank >= c) { rank -= c; prefix |= (K)1 << b; }
+            }
+            v_lo = HKey<T>::from_key(prefix);
+            // (k_lo+1)-th: v_lo again if it is repeated far enough, else the smallest value above it
+            int le = 0;
+            T above = Math<T>::inf();
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const bool valid = lane + 32 * v < a.T_;
+                le += (valid && key[v] <= prefix) ? 1 : 0;
+                if (valid && key[v] > prefix && x[v] < above) above = x[v];
+            }
+            le = __reduce_add_sync(0xffffffffu, le);
+            above = warp_min<T>(above);
+            v_hi = (a.k_hi == a.k_lo || le >= a.k_hi + 1) ? v_lo : above;
         }
-        le = __reduce_add_sync(0xffffffffu, le);
-        above = warp_min<T>(above);
-        const T v_hi = (a.k_hi == a.k_lo || le >= a.k_hi + 1) ? v_lo : above;
         // numpy _lerp
         const T diff = v_hi - v_lo;
         T var = v_lo + diff * a.gamma;
