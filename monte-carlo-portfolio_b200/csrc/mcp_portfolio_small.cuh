@@ -108,6 +108,29 @@ __device__ __forceinline__ bool draw_accepted(const SmallArgs<T, NP>& a, uint64_
 // A warp owns 32 consecutive rows = 32*n contiguous floats in global memory.  Shared-memory row
 // stride n + 4 floats keeps rows 16-byte aligned and makes the per-thread row accesses
 // (LDS.128 / STS.128, one quarter-warp per phase) bank-conflict-free.
+// compile-time row length (the common n == NP case): 32 / (N/4) rows per step, fixed column,
+// immediate offsets -- one LDS.128 + one STG.128 per step and nothing else
+template <int N>
+__device__ __forceinline__ void warp_tile_store_vec_ct(const float* stage, float* dst, int rows, int lane) {
+    constexpr int UPR = N / 4, VS = N + 4, RPS = 32 / UPR;       // N in {4, 8, 16, 32}: UPR divides 32
+    const int r0 = lane / UPR, c = lane % UPR;
+    const float* src = stage + r0 * VS + 4 * c;
+    float4* out = reinterpret_cast<float4*>(dst) + lane;
+#pragma unroll
+    for (int k = 0; k < UPR; ++k)
+        if (r0 + k * RPS < rows) __stcs(out + 32 * k, *reinterpret_cast<const float4*>(src + k * RPS * VS));
+}
+template <int N>
+__device__ __forceinline__ void warp_tile_load_vec_ct(float* stage, const float* src, int rows, int lane) {
+    constexpr int UPR = N / 4, VS = N + 4, RPS = 32 / UPR;
+    const int r0 = lane / UPR, c = lane % UPR;
+    float* dstp = stage + r0 * VS + 4 * c;
+    const float4* in = reinterpret_cast<const float4*>(src) + lane;
+#pragma unroll
+    for (int k = 0; k < UPR; ++k)
+        if (r0 + k * RPS < rows) *reinterpret_cast<float4*>(dstp + k * RPS * VS) = __ldcs(in + 32 * k);
+}
+
 __device__ __forceinline__ void warp_tile_store_vec(const float* stage, int vstride, float* dst, int rows, int n, int lane) {
     const int upr = n >> 2;                    // float4 units per row
     const int total = rows * upr;
@@ -200,7 +223,12 @@ __global__ void __launch_bounds__(PF_BLOCK) small_sweep(const __grid_constant__ 
                 const T* src = a.w_in + warp_row0 * (uint64_t)a.n;
                 if constexpr (sizeof(T) == 4) {
                     if (vec) {
-                        warp_tile_load_vec(reinterpret_cast<float*>(stage), stride, reinterpret_cast<const float*>(src), rows, a.n, lane);
+                        if constexpr (NP == 4 || NP == 8 || NP == 16 || NP == 32) {
+                            if (a.n == NP) warp_tile_load_vec_ct<NP>(reinterpret_cast<float*>(stage), reinterpret_cast<const float*>(src), rows, lane);
+                            else warp_tile_load_vec(reinterpret_cast<float*>(stage), stride, reinterpret_cast<const float*>(src), rows, a.n, lane);
+                        } else {
+                            warp_tile_load_vec(reinterpret_cast<float*>(stage), stride, reinterpret_cast<const float*>(src), rows, a.n, lane);
+                        }
                         __syncwarp();
 #pragma unroll
                         for (int i = 0; i < NP; i += 4) {
@@ -277,7 +305,12 @@ __global__ void __launch_bounds__(PF_BLOCK) small_sweep(const __grid_constant__ 
                                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(stage) + lane * stride + i) =
                                     make_float4(e[k][i] * inv, e[k][i + 1] * inv, e[k][i + 2] * inv, e[k][i + 3] * inv);
                         __syncwarp();
-                        warp_tile_store_vec(reinterpret_cast<const float*>(stage), stride, reinterpret_cast<float*>(dst), rows, a.n, lane);
+                        if constexpr (NP == 4 || NP == 8 || NP == 16 || NP == 32) {
+                            if (a.n == NP) warp_tile_store_vec_ct<NP>(reinterpret_cast<const float*>(stage), reinterpret_cast<float*>(dst), rows, lane);
+                            else warp_tile_store_vec(reinterpret_cast<const float*>(stage), stride, reinterpret_cast<float*>(dst), rows, a.n, lane);
+                        } else {
+                            warp_tile_store_vec(reinterpret_cast<const float*>(stage), stride, reinterpret_cast<float*>(dst), rows, a.n, lane);
+                        }
                         done = true;
                     }
                 }
@@ -440,7 +473,12 @@ __global__ void __launch_bounds__(PF_BLOCK) small_sweep_packed(const __grid_cons
                         }
                     }
                     __syncwarp();
-                    warp_tile_store_vec(stage, stride, dst, rows, a.n, lane);
+                    if constexpr (NP == 4 || NP == 8 || NP == 16 || NP == 32) {
+                        if (a.n == NP) warp_tile_store_vec_ct<NP>(stage, dst, rows, lane);
+                        else warp_tile_store_vec(stage, stride, dst, rows, a.n, lane);
+                    } else {
+                        warp_tile_store_vec(stage, stride, dst, rows, a.n, lane);
+                    }
                 } else {
 #pragma unroll
                     for (int i = 0; i < NP; ++i)
