@@ -100,7 +100,7 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
     MCP_REQUIRE(h, p->n_assets >= 1 && p->n_assets <= 4096, "mcp_portfolios: n_assets=%d out of range [1, 4096]", p->n_assets);
     MCP_REQUIRE(h, p->dtype == MCP_F32 || p->dtype == MCP_F64, "mcp_portfolios: bad dtype %d", p->dtype);
     MCP_REQUIRE(h, p->space == MCP_HOST || p->space == MCP_DEVICE, "mcp_portfolios: bad space %d", p->space);
-    MCP_REQUIRE(h, p->n_portfolios <= (1ull << 40), "mcp_portfolios: n_portfolios=%llu exceeds 2^40 per call; shard the range",
+    MCP_REQUIRE(h, p->n_portfolios <= (1ull << 39), "mcp_portfolios: n_portfolios=%llu exceeds 2^39 per call; shard the range",
                 (unsigned long long)p->n_portfolios);
     MCP_REQUIRE(h, p->max_tries >= 1, "mcp_portfolios: max_tries must be >= 1");
     const int N = p->n_assets;
