@@ -392,6 +392,23 @@ def run_ours(args):
                                                      "shuffles / votes, no flops) is most of the instruction stream"}}}
         del Wd
 
+    # ---- the app's own size: one rerun of tab 3 = 5 methods x 2500 portfolios (app.py:681-682) ----
+    app_line = None
+    if world == 1:
+        Ra = np.random.default_rng(1).standard_normal((365, n)) * 0.05
+        def rerun():
+            for m in mcp.METHODS:
+                mcp.simulate_method(Ra, m, 2500, annual_factor=52, risk_free=3.0, seed=SEED, device=local)
+        for _ in range(3):
+            rerun()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            rerun()
+        app_ms = (time.perf_counter() - t0) / 10 * 1e3
+        app_line = {"workload": "one Streamlit rerun of the Monte Carlo tab: 5 methods x 2500 portfolios (app.py:671-722), T=365, N=16, "
+                                "all arrays to host, picks per method", "ms_per_rerun": app_ms,
+                    "reference_note": "SURVEY.md 3.1 measured 9.0 s per rerun for the reference on one core"}
+
     # ---- CPU baseline on this box's host cores (bounded sample) ----
     cpu, cpu_paths, verbatim = None, None, None
     if world == 1 and not args.no_cpu_baseline:
@@ -437,6 +454,7 @@ def run_ours(args):
                   "roofline": paths_roofline, "quantile_roofline": quantile_roofline, "cpu_baseline": cpu_paths},
         "envelope": env_line,
         "historical": hist_line,
+        "app_rerun": app_line,
     }
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:

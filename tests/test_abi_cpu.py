@@ -124,3 +124,21 @@ def test_select_rank_out_of_population_is_an_error(mcp):
     hist[0, 3] = 5                                     # only 5 elements, rank 10 requested
     assert L.mcp_select_advance(C.byref(st), hist.ctypes.data) != 0
     assert L.mcp_select_init(C.byref(st), 16, r.ctypes.data, 1) != 0
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` prints ONE JSON line with the contract's keys (CPU only)."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
