@@ -1,0 +1,64 @@
+"""GPU tier: randomised shapes (hypothesis) through the C ABI against the oracle -- every kernel
+family (register kernel N <= 32, tiled N <= 256, generic), ragged sizes, both dtypes."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+from conftest import synthetic_inputs
+from oracle import paths_np, philox_np, reference_np as ref
+
+pytestmark = pytest.mark.gpu
+RTOL = {"float64": 1e-6, "float32": 1e-4}
+
+
+@pytest.fixture(scope="module")
+def mcp():
+    import mcportfolio
+    mcportfolio.build()
+    return mcportfolio
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(n=st.integers(1, 70), P=st.integers(1, 700), dtype=st.sampled_from(["float32", "float64"]),
+       seed=st.integers(0, 2**40), first=st.integers(0, 2**45), rf=st.sampled_from([0.0, 0.03, 3.0]))
+def test_rng_sweep_any_shape(mcp, n, P, dtype, seed, first, rf):
+    mu, sigma = synthetic_inputs(n, seed=n)
+    r = mcp.simulate_portfolios(mu, sigma, P, risk_free=rf, seed=seed, first_index=first, dtype=dtype)
+    W, _ = philox_np.dirichlet_weights(first, P, n, seed, dtype)
+    s = philox_np.exponentials(np.arange(first, first + P, dtype=np.uint64), 0, n, seed, dtype).sum(1, keepdims=True)
+    assert np.all(np.abs(r.weights - W) <= (2e-6 + 6e-7 / s if dtype == "float32" else 1e-12))
+    own = ref.evaluate(np.asarray(r.weights, dtype=np.float64), mu, sigma, rf, 0.30)
+    tol = RTOL[dtype]
+    assert np.allclose(r.risks, own["risks"], rtol=tol) and np.allclose(r.returns, own["returns"], rtol=tol, atol=tol * 1e-2)
+    assert np.allclose(r.sharpes, own["sharpes"], rtol=tol, atol=tol * (1 + abs(rf)) * 10)
+    assert r.max_sharpe["index"] == int(np.argmax(r.sharpes))
+    assert r.target_risk["index"] == int(np.argmin(np.abs(r.risks - r.risks.dtype.type(0.30))))
+    assert r.max_sharpe["global_index"] == first + r.max_sharpe["index"] and r.n_accepted == P
+
+
+@settings(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(n=st.integers(1, 70), P=st.integers(1, 500), dtype=st.sampled_from(["float32", "float64"]), seed=st.integers(0, 1000))
+def test_supplied_sweep_any_shape(mcp, n, P, dtype, seed):
+    mu, sigma = synthetic_inputs(n, seed=n + 1)
+    W = np.random.RandomState(seed).dirichlet(np.ones(n), size=P)
+    r = mcp.simulate_portfolios(mu, sigma, P, weights=W, risk_free=0.03, risk_target=0.2, dtype=dtype)
+    want = ref.evaluate(W, mu, sigma, 0.03, 0.2)
+    tol = RTOL[dtype]
+    assert np.allclose(r.risks, want["risks"], rtol=tol) and np.allclose(r.sharpes, want["sharpes"], rtol=tol, atol=tol)
+    assert r.max_sharpe["index"] == want["max_sharpe"]["index"]
+    assert r.target_risk["index"] == want["target_risk"]["index"]
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(n=st.integers(1, 32), M=st.integers(1, 300), S=st.integers(1, 40), dtype=st.sampled_from(["float32", "float64"]),
+       seed=st.integers(0, 2**30), first=st.integers(0, 2**40))
+def test_paths_any_shape(mcp, n, M, S, dtype, seed, first):
+    mu, sigma = synthetic_inputs(n, seed=n + 2)
+    w = np.random.default_rng(seed).dirichlet(np.ones(n))
+    out = mcp.simulate_paths(mu, sigma, w, M, S, seed=seed, first_index=first, dtype=dtype, alphas=(0.95, 0.5))
+    Z = philox_np.normals(first, M, S, n, seed, dtype)
+    want = paths_np.terminal_returns(mu, sigma, w, Z)
+    assert np.allclose(out["terminal"] + 1, want + 1, rtol=3e-4 if dtype == "float32" else 1e-9)
+    x = out["terminal"].astype(np.float64)
+    for a, (v, c) in out["stats"].items():
+        assert v == ref.var(x, a) and np.isclose(c, ref.cvar(x, a), rtol=1e-12, atol=1e-300)
