@@ -6,6 +6,7 @@ TEST INFRASTRUCTURE (see ``oracle/__init__.py``).  Run once here
 
 What is executed verbatim from ``/root/reference/app.py`` (read at run time,
 never copied into the repo):
+  * 164-193  ``calc_option_return`` / ``calc_options_series`` (option overlay, row f4)
   * 231-284  ``var``, ``cvar``, ``efficient_frontier`` ... (via ``ref_loader``)
   * 671-677  the ``simulation_methods`` table (the ``opt_crit`` lambdas)
   * 679-680  mu / Sigma estimation
@@ -74,6 +75,31 @@ def run_reference_methods(returns, names, annual_factor, user_rf, n_portfolios, 
     out["_mu"] = ns["mean_returns"].to_numpy()
     out["_sigma"] = ns["cov_matrix"].to_numpy()
     return out
+
+
+def make_option_overlay():
+    """f4: the reference's calc_options_series (app.py:182-193) on a price walk with a planted 0."""
+    with open(ref_loader.REFERENCE_APP, encoding="utf-8") as fh:
+        lines = fh.readlines()
+    ns = {"np": np, "pd": pd}
+    exec(compile(_slice(lines, 164, 193), ref_loader.REFERENCE_APP, "exec"), ns)
+    rng = np.random.default_rng(164)
+    prices = np.round(100.0 * np.cumprod(1 + 0.04 * rng.standard_normal(40)), 2)
+    prices[5] = 0.0                                          # exercises the prev_price != 0 guard
+    cases = {
+        "protective_put": [["خرید دارایی", 0, 0, 1.0], ["خرید پوت", 95.0, 2.5, 1.0]],
+        "covered_call": [["خرید دارایی", 0, 0, 1.0], ["فروش کال", 110.0, 3.0, 1.0]],
+        "collar": [["خرید دارایی", 0, 0, 1.0], ["خرید پوت", 90.0, 2.0, 1.0], ["فروش کال", 115.0, 1.5, 1.0]],
+        "short_all": [["فروش دارایی", 0, 0, 0.5], ["فروش فیوچرز", 0, 0, 0.25], ["فروش پوت", 100.0, 4.0, 2.0],
+                      ["خرید کال", 105.0, 1.0, 0.75]],
+        "unknown": [["چیز دیگر", 1, 1, 1]],
+    }
+    out = [{"name": k, "legs": legs,
+            "returns": ns["calc_options_series"]([tuple(l) for l in legs], pd.Series(prices)).to_numpy().tolist()}
+           for k, legs in cases.items()]
+    with open(os.path.join(GOLDEN, "option_overlay.json"), "w", encoding="utf-8") as fh:
+        json.dump({"note": "calc_options_series (app.py:182-193) executed verbatim by oracle/make_golden.py",
+                   "prices": prices.tolist(), "cases": out}, fh, ensure_ascii=False)
 
 
 def main():
@@ -187,6 +213,8 @@ def main():
     with open(os.path.join(GOLDEN, "asset_stats.json"), "w") as fh:
         json.dump({"meta": meta, "note": "reference functions app.py:231-263 on the returns columns without the leading "
                    "fillna(0) row (calc_asset_stats uses .dropna(), app.py:288)", **stats}, fh)
+
+    make_option_overlay()
 
     with open(os.path.join(GOLDEN, "META.json"), "w") as fh:
         json.dump({**meta, "c1_shape": list(R.shape), "c2_shape": list(R2.shape),

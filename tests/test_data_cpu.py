@@ -58,3 +58,34 @@ def test_c1_files_reproduce_the_golden_inputs():
     g = load_golden("c1_btc_eth.npz")
     assert R.shape == (365, 2) and np.allclose(R, g["returns_matrix"], rtol=0, atol=0)
     assert np.allclose(mu, g["mu"], rtol=1e-13) and np.allclose(sigma, g["sigma"], rtol=1e-13)
+
+
+def test_option_overlay_matches_reference_lines():
+    """f4: calc_options_series (app.py:182-193) outputs recorded from the reference's own lines."""
+    import json
+    from conftest import GOLDEN
+    from mcportfolio.overlay import KINDS, option_overlay_returns
+    with open(os.path.join(GOLDEN, "option_overlay.json"), encoding="utf-8") as fh:
+        g = json.load(fh)
+    prices = np.array(g["prices"])
+    assert (prices == 0).any()                                   # the prev_price != 0 guard is exercised
+    for case in g["cases"]:
+        legs = [tuple(l) for l in case["legs"]]
+        got = option_overlay_returns(legs, prices)
+        assert np.allclose(got, case["returns"], rtol=1e-13, atol=1e-15), case["name"]
+        english = [(KINDS.get(k, k), s, p, q) for k, s, p, q in legs]
+        assert np.array_equal(option_overlay_returns(english, prices), got)
+    assert option_overlay_returns([], prices).tolist() == [0.0] * len(prices)
+    assert option_overlay_returns([("long_asset", 0, 0, 1)], prices[:1]).tolist() == [0.0]
+
+
+def test_returns_with_overlays_feeds_the_frame():
+    import pandas as pd
+    from mcportfolio.overlay import returns_with_overlays
+    idx = pd.date_range("2025-01-05", periods=5, freq="W")
+    prices = pd.DataFrame({"A": [10.0, 11.0, 12.1, 11.0, 12.0], "B": [5.0, 5.5, 5.0, 5.0, 6.0]}, index=idx)
+    r = returns_with_overlays(prices, {"A": [("long_asset", 0, 0, 1.0)]})
+    assert np.allclose(r["A"].to_numpy(), prices["A"].pct_change().fillna(0).to_numpy())     # long asset == pct_change
+    assert np.allclose(r["B"].to_numpy(), prices["B"].pct_change().fillna(0).to_numpy())
+    r2 = returns_with_overlays(prices, {"B": [("short_asset", 0, 0, 1.0)]})
+    assert np.allclose(r2["B"].to_numpy(), -prices["B"].pct_change().fillna(0).to_numpy())
