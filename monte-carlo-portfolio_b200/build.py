@@ -34,6 +34,7 @@ def translation_units():
     tus = [("mcp_context", "mcp_context.cu", []),
            ("mcp_portfolio", "mcp_portfolio.cu", []),
            ("mcp_portfolio_large", "mcp_portfolio_large.cu", []),
+           ("mcp_portfolio_large_tc", "mcp_portfolio_large_tc.cu", []),
            ("mcp_envelope", "mcp_envelope.cu", []),
            ("mcp_recheck", "mcp_recheck.cu", []),
            ("mcp_paths", "mcp_paths.cu", []),

@@ -26,8 +26,9 @@ struct mcp_context {
     double last_ms = 0.0;
     // device scratch (grow-only): [0] candidates/records, [1..2] pipeline slot inputs,
     // [3..4] pipeline slot outputs, [5] quantile histograms, [6] kernel constants, [7] replay,
-    // [8] envelope bins, [9..10] envelope risk/return scratch per slot
-    mcp_scratch dev[12];
+    // [8] envelope bins, [9..10] envelope risk/return scratch per slot, [11] recheck rows,
+    // [12..13] 1/sum(e) per portfolio of the tcgen05 sweep (per stream)
+    mcp_scratch dev[14];
     mcp_scratch pinned[4];
 };
 

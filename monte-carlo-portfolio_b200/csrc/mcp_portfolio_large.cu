@@ -560,6 +560,7 @@ static int large_launch_generic(mcp_context* h, PfJob& job) {
 }
 
 int pf_large_launch(mcp_context* h, PfJob& job) {
+    if (pf_large_tc_eligible(job)) return pf_large_launch_tc(h, job);
     if (use_tiled(job)) return large_launch_tiled(h, job);
     return job.dtype == MCP_F64 ? large_launch_generic<double>(h, job) : large_launch_generic<float>(h, job);
 }

@@ -1,0 +1,448 @@
+// Tensor-core portfolio sweep for 32 < N <= 256 assets in RNG mode (C5: N = 256, 1e9 portfolios).
+//
+// The quadratic form of 128 portfolios at a time is a GEMM: Y' = E S' with E [128 x N] the tile's
+// un-normalised exponentials and S' the lower triangle of Sigma with doubled off-diagonals, then
+// q_p = sum_j Y'_pj E_pj (app.py:709 restated on the triangle).  E never exists in shared or global
+// memory: it is produced by Philox in the registers of the thread that owns the row, written to
+// TENSOR MEMORY as the MMA's A operand (tcgen05.st), multiplied on the 5th-generation tensor cores
+// (tcgen05.mma, A from TMEM, B = S' from shared memory, FP32 accumulators in TMEM), and the same
+// thread reads its accumulator row back (tcgen05.ld) for the row-dot while E is still in registers.
+//
+// FP32 accuracy on TF32/BF16 tensor cores (split operands, all accumulation in FP32):
+//     E  = Ehi + Elo           Ehi = E with the low 13 mantissa bits cleared (a TF32 number), Elo = E - Ehi exact
+//     S' = Shi + Slo           Shi = TF32 round-to-nearest of S', Slo = BF16(S' - Shi)
+//     Y' = Ehi Shi (tf32) + Elo Shi (tf32) + bf16(E) Slo (bf16)       relative error per product ~ 2^-19
+// S' does not fit shared memory as two FP32 copies; Shi (144 KB) + Slo in BF16 (72 KB) does, because the
+// triangle is stored in 32-row K chunks: chunk c holds rows k in [32c, 32c+32) and only columns j < 32(c+1).
+//
+// Roles (448 threads, one CTA per SM, persistent over tiles of 128 portfolios):
+//   warps 0-11  three row groups of 128 threads (thread = portfolio row = TMEM lane).  Group g handles the
+//               CTA's K chunks n = g (mod 3): generate 32 exponentials -> split -> tcgen05.st into its A stage
+//               -> arrive on a_full[g]; wait d_done[g] -> tcgen05.ld the 32 finished accumulator columns
+//               -> row-dot.  Chunks run from the widest (c = C-1, all columns, overwrites the accumulator)
+//               to the narrowest, so column block c is final as soon as chunk c's MMAs complete and the
+//               epilogue of a tile overlaps its remaining MMAs.
+//   warp 12     TMEM allocation and the single-thread MMA issue loop (10 MMAs per chunk, tcgen05.commit).
+//   warp 13     finaliser: adds the three groups' partial (q, sum e, e.mu) in a fixed order, computes
+//               return / risk / Sharpe (app.py:708-711), tracks the selections, writes the arrays.
+// The Philox counter layout is the one of every other sweep kernel (global index / attempt 0 / 4-asset
+// block), so the weights are the same portfolios the SIMT kernels and oracle/philox_np.py produce.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <cuda_bf16.h>
+
+#include "mcp_device.cuh"
+#include "mcp_portfolio.h"
+
+namespace mcp {
+
+constexpr int TC_ROWS = 128;                 // portfolios per tile = TMEM lanes
+constexpr int TC_KC = 32;                    // K (assets) per chunk
+constexpr int TC_GROUPS = 3;                 // row groups = A stages
+constexpr int TC_THREADS = (4 * TC_GROUPS + 2) * 32;
+constexpr int TC_MMA_WARP = 4 * TC_GROUPS;
+constexpr int TC_FIN_WARP = 4 * TC_GROUPS + 1;
+constexpr int TC_MAX_N = 256;
+constexpr uint32_t TC_COL_A = 256;           // first TMEM column of the A stages (accumulator = columns 0..255)
+constexpr uint32_t TC_STAGE_COLS = 80;       // hi 32 + lo 32 + bf16 16
+constexpr int TC_PART_BUFS = 2;
+
+struct TcArgs {
+    const unsigned char* table;              // global: Shi image, Slo image (canonical UMMA layout), mu[np]
+    float* w_out;                            // raw exponentials (scaled by inv_out afterwards) or null
+    float* inv_out;                          // 1 / sum(e) per portfolio (only with w_out)
+    float* ret_out;
+    float* risk_out;
+    float* sharpe_out;
+    uint8_t* acc_out;
+    PfCand* cands;
+    unsigned long long* n_accepted;
+    uint64_t first, P;
+    int n, np;
+    uint32_t k0, k1;
+    float rf, target;
+};
+
+__host__ __device__ inline uint32_t tc_hi_off(int c) { return 2048u * (uint32_t)(c * (c + 1)); }     // bytes before chunk c
+__host__ __device__ inline uint32_t tc_lo_off(int c) { return 1024u * (uint32_t)(c * (c + 1)); }
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    const uint32_t addr = smem_u32(b);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* b) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+#define TC_R32(v) "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),   \
+                  "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),     \
+                  "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
+                 "%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr), TC_R32(v) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]),
+                 "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,"
+                 "%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                   "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+                   "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor, cute/arch/mma_sm100_desc.hpp): c_format [4,6) = 1 (F32); a_format [7,10) and
+// b_format [10,13): 1 = BF16, 2 = TF32; a/b major bits 15/16 = 0 (K-major); n_dim [17,23) = N >> 3; m_dim [24,29) = M >> 4
+__device__ __forceinline__ uint32_t tc_idesc(uint32_t fmt, uint32_t N) { return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24); }
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), K-major, no swizzle: start >> 4 [0,14); LBO >> 4 [16,30) = byte distance
+// between the two 8x16-byte core matrices along K; SBO >> 4 [32,46) = distance between 8-row groups along N; version 1 at [46,48)
+__device__ __forceinline__ uint64_t tc_sdesc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) | ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) large_sweep_tc(const TcArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int C = a.np / TC_KC;                                         // K chunks per tile (2..8)
+    const uint32_t hi_bytes = tc_hi_off(C), lo_bytes = tc_lo_off(C);
+    unsigned char* sHi = smem;
+    unsigned char* sLo = smem + hi_bytes;
+    float* sMu = reinterpret_cast<float*>(sLo + lo_bytes);                                       // [np]
+    float* sPart = sMu + a.np;                                                                  // [bufs][groups][3][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sPart + TC_PART_BUFS * TC_GROUPS * 3 * TC_ROWS);
+    uint64_t* a_full = bars;                       // [3]  128 arrivals: the group's A stage is in TMEM
+    uint64_t* d_done = bars + 3;                   // [3]  tcgen05.commit: the stage's MMAs are complete
+    uint64_t* drained = bars + 6;                  // [1]  128 * C arrivals: every accumulator column of the tile was read
+    uint64_t* part_full = bars + 7;                // [2]  384 arrivals
+    uint64_t* part_free = bars + 9;                // [2]  1 arrival (finaliser)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    {   // S' images + mu: one 16-byte copy loop (the table is laid out exactly like this shared-memory block)
+        const uint32_t bytes = hi_bytes + lo_bytes + (uint32_t)a.np * 4u;
+        const uint4* src = reinterpret_cast<const uint4*>(a.table);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        for (uint32_t i = tid; i < bytes / 16; i += TC_THREADS) dst[i] = src[i];
+    }
+    if (tid == 0) {
+        for (int g = 0; g < TC_GROUPS; ++g) { mbar_init(&a_full[g], TC_ROWS); mbar_init(&d_done[g], 1); }
+        mbar_init(drained, (uint32_t)(TC_ROWS * C));
+        for (int b = 0; b < TC_PART_BUFS; ++b) { mbar_init(&part_full[b], TC_GROUPS * TC_ROWS); mbar_init(&part_free[b], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == TC_MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes of S' -> visible to the MMA (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const uint64_t n_tiles = (a.P + TC_ROWS - 1) / TC_ROWS;
+
+    if (warp < TC_MMA_WARP) {
+        // ================= row groups: generate -> A stage -> (MMA) -> accumulator row-dot =================
+        const int g = warp >> 2, row = tid & (TC_ROWS - 1);
+        const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+        const uint32_t stage = lane_base + TC_COL_A + TC_STAGE_COLS * (uint32_t)g;
+        uint32_t k = 0;                                  // chunks this group has produced (barrier parity)
+        uint32_t first_mod = 0;                          // (tl * C) mod 3
+        uint32_t tl = 0;
+        for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+            const uint64_t p0 = tile * TC_ROWS;
+            const uint64_t gidx = a.first + p0 + (uint64_t)row;
+            const uint32_t c0 = (uint32_t)gidx, c1 = (uint32_t)(gidx >> 32);
+            const bool live = p0 + (uint64_t)row < a.P;
+            float q = 0.f, s = 0.f, r = 0.f;
+            for (int ci = (int)((g + 3u - first_mod) % 3u); ci < C; ci += TC_GROUPS, ++k) {
+                const int c = C - 1 - ci;
+                // ---- generate the row's 32 exponentials of chunk c (Philox blocks 8c .. 8c+7) ----
+                float e[TC_KC];
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    uint32_t x[4];
+                    philox4x32_10(c0, c1, 0u, STREAM_WEIGHTS | (uint32_t)(8 * c + m), a.k0, a.k1, x);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int i = TC_KC * c + 4 * m + t;
+                        const float v = -Math<float>::lg2(Math<float>::unit_open0(x[t]));
+                        e[4 * m + t] = i < a.n ? v : 0.f;
+                    }
+                }
+                const float4* mu4 = reinterpret_cast<const float4*>(sMu + TC_KC * c);
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const float4 u = mu4[m];
+                    s += (e[4 * m] + e[4 * m + 1]) + (e[4 * m + 2] + e[4 * m + 3]);
+                    r = fmaf(e[4 * m], u.x, r);
+                    r = fmaf(e[4 * m + 1], u.y, r);
+                    r = fmaf(e[4 * m + 2], u.z, r);
+                    r = fmaf(e[4 * m + 3], u.w, r);
+                }
+                if (a.w_out != nullptr && live) {
+                    float* dst = a.w_out + (p0 + (uint64_t)row) * (uint64_t)a.n + (uint64_t)(TC_KC * c);
+                    if ((a.n & 3) == 0) {
+#pragma unroll
+                        for (int m = 0; m < 8; ++m)
+                            if (TC_KC * c + 4 * m < a.n) reinterpret_cast<float4*>(dst)[m] = make_float4(e[4 * m], e[4 * m + 1], e[4 * m + 2], e[4 * m + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < TC_KC; ++j)
+                            if (TC_KC * c + j < a.n) dst[j] = e[j];
+                    }
+                }
+                // ---- split and store the A operand of this chunk ----
+                {
+                    uint32_t hi[TC_KC], lo[TC_KC], bf[TC_KC / 2];
+#pragma unroll
+                    for (int j = 0; j < TC_KC; ++j) {
+                        hi[j] = __float_as_uint(e[j]) & 0xffffe000u;
+                        lo[j] = __float_as_uint(e[j] - __uint_as_float(hi[j]));
+                    }
+#pragma unroll
+                    for (int j = 0; j < TC_KC / 2; ++j) {
+                        const __nv_bfloat162 p2 = __floats2bfloat162_rn(e[2 * j], e[2 * j + 1]);        // low half = even k
+                        bf[j] = *reinterpret_cast<const uint32_t*>(&p2);
+                    }
+                    tmem_st32(stage, hi);
+                    tmem_st32(stage + 32, lo);
+                    tmem_st16(stage + 64, bf);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                mbar_arrive(&a_full[g]);
+                // ---- accumulator columns [32c, 32c+32) are final once this chunk's MMAs completed ----
+                mbar_wait(&d_done[g], k & 1u);
+                tc_fence_after();
+                {
+                    uint32_t y[TC_KC];
+                    tmem_ld32(lane_base + (uint32_t)(TC_KC * c), y);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < TC_KC; ++j) q = fmaf(__uint_as_float(y[j]), e[j], q);
+                }
+                tc_fence_before();
+                mbar_arrive(drained);
+            }
+            // ---- this group's share of the tile -> finaliser ----
+            const uint32_t b = tl & 1u, use = tl >> 1;
+            if (use > 0) mbar_wait(&part_free[b], (use - 1u) & 1u);
+            float* part = sPart + ((size_t)(b * TC_GROUPS + (uint32_t)g) * 3) * TC_ROWS;
+            part[row] = q;
+            part[TC_ROWS + row] = s;
+            part[2 * TC_ROWS + row] = r;
+            mbar_arrive(&part_full[b]);
+            first_mod = (first_mod + (uint32_t)C) % 3u;
+        }
+    } else if (warp == TC_MMA_WARP) {
+        // ================= MMA issue: one thread =================
+        const uint32_t id_tf32_base = tc_idesc(2u, 0u), id_bf16_base = tc_idesc(1u, 0u);
+        uint32_t g = 0, cyc = 0;                         // chunk n = 3 * cyc + g belongs to group g, its cyc-th
+        uint32_t tl = 0;
+        for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+            for (int ci = 0; ci < C; ++ci) {
+                const int c = C - 1 - ci;
+                const uint32_t N = (uint32_t)(TC_KC * (c + 1));
+                mbar_wait(&a_full[g], cyc & 1u);
+                if (ci == 0 && tl > 0) mbar_wait(drained, (tl - 1u) & 1u);          // chunk C-1 overwrites the whole accumulator
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t lbo = (N / 8u) * 128u, sbo = 128u;
+                    const uint32_t a_hi = tmem + TC_COL_A + TC_STAGE_COLS * g, a_lo = a_hi + 32u, a_bf = a_hi + 64u;
+                    const uint32_t id32 = id_tf32_base | ((N >> 3) << 17), id16 = id_bf16_base | ((N >> 3) << 17);
+                    const uint32_t bhi = smem_u32(sHi) + tc_hi_off(c), blo = smem_u32(sLo) + tc_lo_off(c);
+#pragma unroll
+                    for (uint32_t ks = 0; ks < 4; ++ks) {
+                        const uint64_t bd = tc_sdesc(bhi + ks * 2u * lbo, lbo, sbo);
+                        mma_tf32_ts(tmem, a_hi + 8u * ks, bd, id32, (ci > 0 || ks > 0) ? 1u : 0u);
+                        mma_tf32_ts(tmem, a_lo + 8u * ks, bd, id32, 1u);
+                    }
+#pragma unroll
+                    for (uint32_t ks = 0; ks < 2; ++ks) {
+                        const uint64_t bd = tc_sdesc(blo + ks * 2u * lbo, lbo, sbo);
+                        mma_bf16_ts(tmem, a_bf + 8u * ks, bd, id16, 1u);
+                    }
+                    tc_commit(&d_done[g]);
+                }
+                __syncwarp();
+                if (++g == TC_GROUPS) { g = 0; ++cyc; }
+            }
+        }
+    } else {
+        // ================= finaliser =================
+        float best_s = -Math<float>::inf(), best_d = -Math<float>::inf();
+        uint64_t idx_s = MCP_NO_INDEX, idx_d = MCP_NO_INDEX;
+        float rmin = Math<float>::inf(), rmax = -Math<float>::inf();
+        unsigned int n_acc = 0;
+        uint32_t tl = 0;
+        for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+            const uint64_t p0 = tile * TC_ROWS;
+            const uint32_t b = tl & 1u, use = tl >> 1;
+            mbar_wait(&part_full[b], use & 1u);
+            const float* part = sPart + (size_t)(b * TC_GROUPS) * 3 * TC_ROWS;
+#pragma unroll
+            for (int it = 0; it < TC_ROWS / 32; ++it) {
+                const int row = 32 * it + lane;
+                const uint64_t local = p0 + (uint64_t)row;
+                float q = 0.f, s = 0.f, r = 0.f;
+#pragma unroll
+                for (int g = 0; g < TC_GROUPS; ++g) {
+                    q += part[(g * 3 + 0) * TC_ROWS + row];
+                    s += part[(g * 3 + 1) * TC_ROWS + row];
+                    r += part[(g * 3 + 2) * TC_ROWS + row];
+                }
+                if (local < a.P) {
+                    float ret, risk, sharpe;
+                    metrics_from<float>(q, r, s, a.rf, false, ret, risk, sharpe);
+                    ++n_acc;
+                    const uint64_t gi = a.first + local;
+                    if (sharpe > best_s) { best_s = sharpe; idx_s = gi; }          // rows ascend per lane: first occurrence kept
+                    const float d = -fabsf(risk - a.target);
+                    if (d > best_d) { best_d = d; idx_d = gi; }
+                    rmin = fminf(rmin, risk);
+                    rmax = fmaxf(rmax, risk);
+                    if (a.ret_out) a.ret_out[local] = ret;
+                    if (a.risk_out) a.risk_out[local] = risk;
+                    if (a.sharpe_out) a.sharpe_out[local] = sharpe;
+                    if (a.acc_out) a.acc_out[local] = 1;
+                    if (a.inv_out) a.inv_out[local] = Math<float>::rcp(s);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&part_free[b]);
+        }
+        warp_argmax<float>(best_s, idx_s);
+        warp_argmax<float>(best_d, idx_d);
+        rmin = warp_min<float>(rmin);
+        rmax = warp_max<float>(rmax);
+        n_acc = __reduce_add_sync(0xffffffffu, n_acc);
+        if (lane == 0) {
+            a.cands[blockIdx.x] = PfCand{(double)best_s, idx_s, (double)best_d, idx_d, (double)rmin, (double)rmax};
+            if (n_acc) atomicAdd(a.n_accepted, (unsigned long long)n_acc);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// w[p][i] *= inv[p]: turns the raw exponentials the sweep stored into weights (same e * rcp(sum e) as the SIMT kernels)
+__global__ void __launch_bounds__(256) tc_scale_rows(float* w, const float* inv, uint64_t P, int n) {
+    const uint64_t total = P * (uint64_t)n;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) w[i] *= inv[i / (uint64_t)n];
+}
+
+// ---- host side -------------------------------------------------------------------------------
+
+static inline float tf32_round(float x) {          // round-to-nearest-even onto 10 explicit mantissa bits
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u += 0x00000fffu + ((u >> 13) & 1u);
+    u &= 0xffffe000u;
+    float y;
+    memcpy(&y, &u, 4);
+    return y;
+}
+static inline uint16_t bf16_round(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u += 0x00007fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+bool pf_large_tc_eligible(const PfJob& job) {
+    static const bool enabled = [] {
+        const char* v = getenv("MCP_LARGE_TC");
+        return !(v && v[0] == '0');
+    }();
+    return enabled && job.dtype == MCP_F32 && job.n > PF_SMALL_MAX_N && job.n <= TC_MAX_N && job.w_in == nullptr && !job.bounds;
+}
+
+int pf_large_launch_tc(mcp_context* h, PfJob& job) {
+    const int n = job.n, np = std::max(64, (n + TC_KC - 1) / TC_KC * TC_KC), C = np / TC_KC;
+    const uint32_t hi_bytes = tc_hi_off(C), lo_bytes = tc_lo_off(C);
+    const size_t table_bytes = (size_t)hi_bytes + lo_bytes + (size_t)np * 4;
+    std::vector<unsigned char> host(table_bytes, 0);
+    // S'[k][j], j <= k: Sigma_kk on the diagonal, Sigma_kj + Sigma_jk below it (w' Sigma w = sum_k sum_{j<=k} w_k S'_kj w_j).
+    // Canonical K-major no-swizzle layout per chunk: [K core (4 tf32 / 8 bf16)][N group of 8][8 rows x 16 bytes].
+    for (int k = 0; k < n; ++k) {
+        const int c = k / TC_KC, kk = k % TC_KC, Nc = TC_KC * (c + 1);
+        for (int j = 0; j <= k; ++j) {
+            const double v = j == k ? job.sigma[(size_t)k * n + k] : job.sigma[(size_t)k * n + j] + job.sigma[(size_t)j * n + k];
+            const float shi = tf32_round((float)v);
+            const uint16_t slo = bf16_round((float)(v - (double)shi));
+            const size_t oh = (size_t)tc_hi_off(c) + ((size_t)(kk / 4) * (Nc / 8) + j / 8) * 128 + (j % 8) * 16 + (kk % 4) * 4;
+            const size_t ol = (size_t)hi_bytes + tc_lo_off(c) + ((size_t)(kk / 8) * (Nc / 8) + j / 8) * 128 + (j % 8) * 16 + (kk % 8) * 2;
+            memcpy(&host[oh], &shi, 4);
+            memcpy(&host[ol], &slo, 2);
+        }
+    }
+    float* hmu = reinterpret_cast<float*>(host.data() + hi_bytes + lo_bytes);
+    for (int i = 0; i < n; ++i) hmu[i] = (float)job.mu[i];
+    unsigned char* dev = nullptr;
+    MCP_CHECK(mcp_dev_reserve(h, 6, table_bytes, (void**)&dev));
+    MCP_CUDA(h, cudaMemcpyAsync(dev, host.data(), table_bytes, cudaMemcpyHostToDevice, job.stream));
+    MCP_CUDA(h, cudaStreamSynchronize(job.stream));        // `host` is pageable and dies at scope exit
+
+    TcArgs a;
+    a.table = dev;
+    a.w_out = (float*)job.w_out;
+    a.inv_out = nullptr;
+    if (a.w_out)      // two sweeps can be in flight in the HOST-space pipeline (one per side stream): one scratch each
+        MCP_CHECK(mcp_dev_reserve(h, job.stream == h->side_stream[1] ? 13 : 12, (size_t)job.P * sizeof(float), (void**)&a.inv_out));
+    a.ret_out = (float*)job.ret_out; a.risk_out = (float*)job.risk_out; a.sharpe_out = (float*)job.sharpe_out;
+    a.acc_out = job.acc_out; a.cands = job.cands; a.n_accepted = job.n_accepted;
+    a.first = job.first; a.P = job.P; a.n = n; a.np = np;
+    a.k0 = (uint32_t)job.seed; a.k1 = (uint32_t)(job.seed >> 32);
+    a.rf = (float)job.rf; a.target = (float)job.target;
+    const size_t smem = table_bytes + (size_t)TC_PART_BUFS * TC_GROUPS * 3 * TC_ROWS * sizeof(float) + 11 * sizeof(uint64_t) + 16;
+    if (smem > h->prop.sharedMemPerBlockOptin)
+        return mcp_fail(h, MCP_ERR_INVALID, "large_sweep_tc: N=%d needs %zu B of shared memory (max %zu)", n, smem, (size_t)h->prop.sharedMemPerBlockOptin);
+    MCP_CUDA(h, cudaFuncSetAttribute(large_sweep_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t n_tiles = (job.P + TC_ROWS - 1) / TC_ROWS;
+    uint64_t grid = std::min<uint64_t>((uint64_t)h->prop.multiProcessorCount, n_tiles);
+    grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, job.max_blocks));
+    job.blocks_used = (int)grid;
+    large_sweep_tc<<<(unsigned)grid, TC_THREADS, smem, job.stream>>>(a);
+    MCP_CUDA(h, cudaGetLastError());
+    h->launches++;
+    if (a.w_out) {
+        const uint64_t total = job.P * (uint64_t)n;
+        const unsigned blocks = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)h->prop.multiProcessorCount * 8);
+        tc_scale_rows<<<blocks, 256, 0, job.stream>>>(a.w_out, a.inv_out, job.P, n);
+        MCP_CUDA(h, cudaGetLastError());
+        h->launches++;
+    }
+    return MCP_OK;
+}
+
+}  // namespace mcp
