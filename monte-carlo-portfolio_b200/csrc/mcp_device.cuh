@@ -36,6 +36,36 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// FP32 streams spend 24 bits per uniform instead of a whole 32-bit word: uniform field i of a row is
+// bits [24 i, 24 i + 23) of the concatenation of its stream's Philox blocks 0, 1, 2, ... (word 0 of block 0
+// lowest).  Four fields share three words, so 16 uniforms cost 3 Philox calls instead of 4 (+11 % on the
+// N = 16 sweep); the price is two funnel shifts and a shift per four fields.  The FP64 kernels keep one
+// 32-bit word per uniform.  `f` holds the fields UNMASKED: unit_open0 / unit_frac / centred mask the low 23 bits.
+__device__ __forceinline__ void fields_from_triple(uint32_t a, uint32_t b, uint32_t c, uint32_t* f) {
+    f[0] = a;
+    f[1] = __funnelshift_r(a, b, 24);
+    f[2] = __funnelshift_r(b, c, 16);
+    f[3] = c >> 8;
+}
+__host__ __device__ constexpr int philox_blocks_for_fields(int nf) { return (3 * ((nf + 3) / 4) + 3) / 4; }
+
+// NF fields (multiple of 4) that start at a block boundary: field 0 = bit 0 of block `c3 & 0xffffff`.
+template <int NF>
+__device__ __forceinline__ void philox_fields(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t (&f)[NF]) {
+    static_assert(NF % 4 == 0, "fields come in groups of four");
+    constexpr int NB = philox_blocks_for_fields(NF);
+    uint32_t w[4 * NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        uint32_t x[4];
+        philox4x32_10(c0, c1, c2, c3 + (uint32_t)b, k0, k1, x);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[4 * b + k] = x[k];
+    }
+#pragma unroll
+    for (int t = 0; t < NF / 4; ++t) fields_from_triple(w[3 * t], w[3 * t + 1], w[3 * t + 2], &f[4 * t]);
+}
+
 // ---- math wrappers ---------------------------------------------------------------------
 // FP32 uses the MUFU approximations directly (lg2 / rcp / rsqrt / sin / cos: <= 2 ulp-class
 // error, far inside the 1e-4 parity tolerance); FP64 uses the IEEE library routines.

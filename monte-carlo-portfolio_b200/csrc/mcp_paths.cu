@@ -48,17 +48,30 @@ template <> struct PathConst<double> {
 
 template <typename T, int NP>
 __device__ __forceinline__ void draw_normals(const PathArgs<T, NP>& a, uint32_t c0, uint32_t c1, uint32_t step, T (&z)[NP]) {
+    if constexpr (sizeof(T) == 4) {           // FP32: 24-bit fields (mcp_device.cuh), pair (2k, 2k+1) -> normals (2k, 2k+1)
+        uint32_t f[NP];
+        philox_fields<NP>(c0, c1, step, STREAM_NORMALS, a.k0, a.k1, f);
 #pragma unroll
-    for (int b = 0; b < NP / 4; ++b) {
-        uint32_t x[4];
-        philox4x32_10(c0, c1, step, STREAM_NORMALS | (uint32_t)b, a.k0, a.k1, x);
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const T u1 = Math<T>::unit_open0(x[2 * k]);
+        for (int k = 0; k < NP / 2; ++k) {
+            const T u1 = Math<T>::unit_open0(f[2 * k]);
             const T r = Math<T>::sqrt(Math<T>::lg2(u1) * PathConst<T>::neg2ln2());
-            const T th = PathConst<T>::centred(x[2 * k + 1]) * PathConst<T>::pi();
-            z[4 * b + 2 * k] = r * Math<T>::cosf_(th);
-            z[4 * b + 2 * k + 1] = r * Math<T>::sinf_(th);
+            const T th = PathConst<T>::centred(f[2 * k + 1]) * PathConst<T>::pi();
+            z[2 * k] = r * Math<T>::cosf_(th);
+            z[2 * k + 1] = r * Math<T>::sinf_(th);
+        }
+    } else {
+#pragma unroll
+        for (int b = 0; b < NP / 4; ++b) {
+            uint32_t x[4];
+            philox4x32_10(c0, c1, step, STREAM_NORMALS | (uint32_t)b, a.k0, a.k1, x);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const T u1 = Math<T>::unit_open0(x[2 * k]);
+                const T r = Math<T>::sqrt(Math<T>::lg2(u1) * PathConst<T>::neg2ln2());
+                const T th = PathConst<T>::centred(x[2 * k + 1]) * PathConst<T>::pi();
+                z[4 * b + 2 * k] = r * Math<T>::cosf_(th);
+                z[4 * b + 2 * k + 1] = r * Math<T>::sinf_(th);
+            }
         }
     }
 }
@@ -129,28 +142,25 @@ __global__ void __launch_bounds__(PATH_BLOCK) path_kernel_packed(const __grid_co
         for (int i = 0; i < NP; ++i) V[i] = make_float2(1.f, 1.f);
         for (int s = 0; s < a.n_steps; ++s) {
             float2 z[NP];
+            uint32_t fa[NP], fb[NP];
+            philox_fields<NP>((uint32_t)gA, (uint32_t)(gA >> 32), (uint32_t)s, STREAM_NORMALS, a.k0, a.k1, fa);
+            philox_fields<NP>((uint32_t)gB, (uint32_t)(gB >> 32), (uint32_t)s, STREAM_NORMALS, a.k0, a.k1, fb);
 #pragma unroll
-            for (int b = 0; b < NP / 4; ++b) {
-                uint32_t xa[4], xb[4];
-                philox4x32_10((uint32_t)gA, (uint32_t)(gA >> 32), (uint32_t)s, STREAM_NORMALS | (uint32_t)b, a.k0, a.k1, xa);
-                philox4x32_10((uint32_t)gB, (uint32_t)(gB >> 32), (uint32_t)s, STREAM_NORMALS | (uint32_t)b, a.k0, a.k1, xb);
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const float2 f1 = make_float2(__uint_as_float((xa[2 * k] & 0x007fffffu) | 0x3f800000u),
-                                                  __uint_as_float((xb[2 * k] & 0x007fffffu) | 0x3f800000u));
-                    const float2 u1 = fma2(f1, bcast2(-1.0f), bcast2(2.0f));                      // (0, 1]
-                    const float2 t = fma2(make_float2(Math<float>::lg2(u1.x), Math<float>::lg2(u1.y)),
-                                          bcast2(PathConst<float>::neg2ln2()), bcast2(0.0f));     // -2 ln U1
-                    const float2 r = make_float2(Math<float>::sqrt(t.x), Math<float>::sqrt(t.y));
-                    const float2 f2 = make_float2(__uint_as_float((xa[2 * k + 1] & 0x007fffffu) | 0x40000000u),
-                                                  __uint_as_float((xb[2 * k + 1] & 0x007fffffu) | 0x40000000u));
-                    const float2 c = fma2(f2, bcast2(1.0f), bcast2(-3.0f));                       // 2f - 1 in [-1, 1)
-                    const float2 th = fma2(c, bcast2(kPi), bcast2(0.0f));
-                    const float2 cs = make_float2(Math<float>::cosf_(th.x), Math<float>::cosf_(th.y));
-                    const float2 sn = make_float2(Math<float>::sinf_(th.x), Math<float>::sinf_(th.y));
-                    z[4 * b + 2 * k] = fma2(r, cs, bcast2(0.0f));
-                    z[4 * b + 2 * k + 1] = fma2(r, sn, bcast2(0.0f));
-                }
+            for (int k = 0; k < NP / 2; ++k) {
+                const float2 f1 = make_float2(__uint_as_float((fa[2 * k] & 0x007fffffu) | 0x3f800000u),
+                                              __uint_as_float((fb[2 * k] & 0x007fffffu) | 0x3f800000u));
+                const float2 u1 = fma2(f1, bcast2(-1.0f), bcast2(2.0f));                      // (0, 1]
+                const float2 t = fma2(make_float2(Math<float>::lg2(u1.x), Math<float>::lg2(u1.y)),
+                                      bcast2(PathConst<float>::neg2ln2()), bcast2(0.0f));     // -2 ln U1
+                const float2 r = make_float2(Math<float>::sqrt(t.x), Math<float>::sqrt(t.y));
+                const float2 f2 = make_float2(__uint_as_float((fa[2 * k + 1] & 0x007fffffu) | 0x40000000u),
+                                              __uint_as_float((fb[2 * k + 1] & 0x007fffffu) | 0x40000000u));
+                const float2 c = fma2(f2, bcast2(1.0f), bcast2(-3.0f));                       // 2f - 1 in [-1, 1)
+                const float2 th = fma2(c, bcast2(kPi), bcast2(0.0f));
+                const float2 cs = make_float2(Math<float>::cosf_(th.x), Math<float>::cosf_(th.y));
+                const float2 sn = make_float2(Math<float>::sinf_(th.x), Math<float>::sinf_(th.y));
+                z[2 * k] = fma2(r, cs, bcast2(0.0f));
+                z[2 * k + 1] = fma2(r, sn, bcast2(0.0f));
             }
 #pragma unroll
             for (int i = 0; i < NP; ++i) {

@@ -4,7 +4,7 @@
 // works on a tile of 64 portfolios:
 //
 //   1. GENERATE  the tile's un-normalised exponentials e[p][i] (Philox4x32-10, same counter
-//                layout as the small kernel: global index / attempt / 4-asset block) straight
+//                layout and 24-bit fields as the small kernel: global index / attempt / block) straight
 //                into shared memory, asset-major (Wt[i][p], row stride 66 -> conflict-free
 //                writes by the 4 threads that share a portfolio and conflict-free LDS.64 reads);
 //   2. QUADRATIC FORM as a register-tiled SIMT "SGEMM with row-dot":  Y' = W S' restricted to the
@@ -121,14 +121,13 @@ __global__ void __launch_bounds__(LG_THREADS, 1) large_sweep(const LargeArgs a) 
                 const uint64_t gidx = a.first + p0 + gp;
                 const uint32_t c0 = (uint32_t)gidx, c1 = (uint32_t)(gidx >> 32);
                 const bool live = sState[gp] == ST_PENDING;
-                for (int m = 0; m < a.np / 16; ++m) {
-                    const int b = 4 * m + gc;
-                    uint32_t x[4];
-                    philox4x32_10(c0, c1, (uint32_t)attempt, STREAM_WEIGHTS | (uint32_t)b, a.k0, a.k1, x);
+                for (int G = gc; G < a.np / 16; G += 4) {          // 16-asset group = 16 fields = Philox blocks 3G .. 3G+2
+                    uint32_t f[16];
+                    philox_fields<16>(c0, c1, (uint32_t)attempt, STREAM_WEIGHTS | (uint32_t)(3 * G), a.k0, a.k1, f);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int i = 4 * b + k;
-                        const float e = -Math<float>::lg2(Math<float>::unit_open0(x[k]));
+                    for (int k = 0; k < 16; ++k) {
+                        const int i = 16 * G + k;
+                        const float e = -Math<float>::lg2(Math<float>::unit_open0(f[k]));
                         sW[i * LG_WSTRIDE + gp] = (live && i < a.n) ? e : 0.f;
                     }
                 }
@@ -365,9 +364,25 @@ __global__ void __launch_bounds__(GEN_THREADS) generic_sweep(const GenArgs<T> a)
                 s = (T)1;
             } else {
                 T part = (T)0;
-                for (int b = lane; b < a.np / 4; b += 32) {
+                for (int b = lane; b < a.np / 4; b += 32) {          // b = group of 4 assets
                     uint32_t x[4];
-                    philox4x32_10(c0, c1, (uint32_t)attempt, STREAM_WEIGHTS | (uint32_t)b, a.k0, a.k1, x);
+                    if constexpr (sizeof(T) == 4) {
+                        // 24-bit fields 4b .. 4b+3 = words 3b .. 3b+2 of the stream (one or two Philox blocks)
+                        const int w0 = 3 * b, b0 = w0 >> 2, b1 = (w0 + 2) >> 2;
+                        uint32_t y0[4], y1[4];
+                        philox4x32_10(c0, c1, (uint32_t)attempt, STREAM_WEIGHTS | (uint32_t)b0, a.k0, a.k1, y0);
+                        if (b1 != b0) philox4x32_10(c0, c1, (uint32_t)attempt, STREAM_WEIGHTS | (uint32_t)b1, a.k0, a.k1, y1);
+                        uint32_t w3[3];
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            const int wi = w0 + j, k4 = wi & 3;
+                            const uint32_t* src = (wi >> 2) == b0 ? y0 : y1;
+                            w3[j] = k4 == 0 ? src[0] : k4 == 1 ? src[1] : k4 == 2 ? src[2] : src[3];
+                        }
+                        fields_from_triple(w3[0], w3[1], w3[2], x);
+                    } else {
+                        philox4x32_10(c0, c1, (uint32_t)attempt, STREAM_WEIGHTS | (uint32_t)b, a.k0, a.k1, x);
+                    }
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int i = 4 * b + k;

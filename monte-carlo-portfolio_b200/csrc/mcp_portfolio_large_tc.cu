@@ -29,8 +29,8 @@
 // Measured on B200 (N = 256): 2.5-2.7e9 portfolios/s vs 5.9e8 for the SIMT kernel.  Ablation of the same launch:
 // without the MMAs 3.0e9, without Philox 3.0e9, without both 5.1e9 -- the generator's instruction stream and the
 // stage hand-off latency (3 stages fit beside the 256 accumulator columns) share the rest; the tensor pipe is ~46 % busy.
-// The Philox counter layout is the one of every other sweep kernel (global index / attempt 0 / 4-asset
-// block), so the weights are the same portfolios the SIMT kernels and oracle/philox_np.py produce.
+// The Philox counter layout and the 24-bit uniform fields are those of every other FP32 sweep kernel (global index /
+// attempt 0 / block; mcp_device.cuh), so the weights are the same portfolios the SIMT kernels and oracle/philox_np.py produce.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -203,14 +203,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) large_sweep_tc(const TcArgs a) 
             const bool live = p0 + (uint64_t)row < a.P;
             for (int ci = (int)((g + 3u - first_mod) % 3u); ci < C; ci += TC_GROUPS, ++k) {
                 const int c = C - 1 - ci;
-                // ---- the row's 32 values of chunk c: Philox blocks 8c .. 8c+7 ----
+                // ---- the row's 32 values of chunk c: 24-bit fields 32c .. 32c+31 = Philox blocks 6c .. 6c+5 ----
                 float l[TC_KC];
+                {
+                    uint32_t f[TC_KC];
+                    philox_fields<TC_KC>(c0, c1, 0u, STREAM_WEIGHTS | (uint32_t)(6 * c), a.k0, a.k1, f);
 #pragma unroll
-                for (int m = 0; m < 8; ++m) {
-                    uint32_t x[4];
-                    philox4x32_10(c0, c1, 0u, STREAM_WEIGHTS | (uint32_t)(8 * c + m), a.k0, a.k1, x);
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) l[4 * m + t] = Math<float>::lg2(Math<float>::unit_open0(x[t]));
+                    for (int j = 0; j < TC_KC; ++j) l[j] = Math<float>::lg2(Math<float>::unit_open0(f[j]));
                 }
                 const int i0 = TC_KC * c;
                 if (i0 + TC_KC > a.n) {                  // only the last chunk can reach past n (uniform branch)

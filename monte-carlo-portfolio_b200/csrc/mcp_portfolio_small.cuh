@@ -49,15 +49,25 @@ template <typename T, int NP>
 __device__ __forceinline__ void draw_exponentials(const SmallArgs<T, NP>& a, uint32_t c0, uint32_t c1,
                                                   uint32_t attempt, T (&e)[NP], T& s) {
     s = (T)0;
+    if constexpr (sizeof(T) == 4) {           // FP32: 24-bit fields, 3 Philox calls per 16 uniforms
+        uint32_t f[NP];
+        philox_fields<NP>(c0, c1, attempt, STREAM_WEIGHTS, a.k0, a.k1, f);
 #pragma unroll
-    for (int b = 0; b < NP / 4; ++b) {
-        uint32_t x[4];
-        philox4x32_10(c0, c1, attempt, STREAM_WEIGHTS | (uint32_t)b, a.k0, a.k1, x);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int i = 4 * b + k;
-            e[i] = -Math<T>::lg2(Math<T>::unit_open0(x[k]));
+        for (int i = 0; i < NP; ++i) {
+            e[i] = -Math<T>::lg2(Math<T>::unit_open0(f[i]));
             s = Math<T>::fma(e[i], a.mask[i], s);
+        }
+    } else {
+#pragma unroll
+        for (int b = 0; b < NP / 4; ++b) {
+            uint32_t x[4];
+            philox4x32_10(c0, c1, attempt, STREAM_WEIGHTS | (uint32_t)b, a.k0, a.k1, x);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = 4 * b + k;
+                e[i] = -Math<T>::lg2(Math<T>::unit_open0(x[k]));
+                s = Math<T>::fma(e[i], a.mask[i], s);
+            }
         }
     }
 }
@@ -395,20 +405,16 @@ __global__ void __launch_bounds__(PF_BLOCK) small_sweep_packed(const __grid_cons
         for (int kp = 0; kp < KP; ++kp) {
             const uint64_t ga = a.first + local0 + (uint64_t)(2 * kp) * PF_BLOCK, gb = ga + PF_BLOCK;
             s2[kp] = make_float2(0.f, 0.f);
+            uint32_t fa[NP], fb[NP];
+            philox_fields<NP>((uint32_t)ga, (uint32_t)(ga >> 32), 0u, STREAM_WEIGHTS, a.k0, a.k1, fa);
+            philox_fields<NP>((uint32_t)gb, (uint32_t)(gb >> 32), 0u, STREAM_WEIGHTS, a.k0, a.k1, fb);
 #pragma unroll
-            for (int b = 0; b < NP / 4; ++b) {
-                uint32_t xa[4], xb[4];
-                philox4x32_10((uint32_t)ga, (uint32_t)(ga >> 32), 0u, STREAM_WEIGHTS | (uint32_t)b, a.k0, a.k1, xa);
-                philox4x32_10((uint32_t)gb, (uint32_t)(gb >> 32), 0u, STREAM_WEIGHTS | (uint32_t)b, a.k0, a.k1, xb);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int i = 4 * b + k;
-                    const float2 f = make_float2(__uint_as_float((xa[k] & 0x007fffffu) | 0x3f800000u),
-                                                 __uint_as_float((xb[k] & 0x007fffffu) | 0x3f800000u));
-                    const float2 u = fma2(f, bcast2(-1.0f), bcast2(2.0f));            // U = 2 - f in (0, 1]
-                    l2[kp][i] = make_float2(Math<float>::lg2(u.x), Math<float>::lg2(u.y));
-                    s2[kp] = fma2(l2[kp][i], bcast2(a.nmask[i]), s2[kp]);
-                }
+            for (int i = 0; i < NP; ++i) {
+                const float2 f = make_float2(__uint_as_float((fa[i] & 0x007fffffu) | 0x3f800000u),
+                                             __uint_as_float((fb[i] & 0x007fffffu) | 0x3f800000u));
+                const float2 u = fma2(f, bcast2(-1.0f), bcast2(2.0f));            // U = 2 - f in (0, 1]
+                l2[kp][i] = make_float2(Math<float>::lg2(u.x), Math<float>::lg2(u.y));
+                s2[kp] = fma2(l2[kp][i], bcast2(a.nmask[i]), s2[kp]);
             }
         }
         float2 q2[KP], r2[KP];

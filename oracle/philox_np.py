@@ -14,9 +14,14 @@ to ``np.random.dirichlet(ones)`` is what the statistical tests check).
 Counter layout (128-bit counter, 64-bit key):
     c0, c1 = low / high 32 bits of the GLOBAL unit index (portfolio or path)
     c2     = sub-counter: rejection attempt (portfolios) or time step (paths)
-    c3     = (stream << 24) | block,  block = group of 4 outputs, asset i uses
-             output i%4 of block i//4;  stream 1 = weights, 2 = path normals
+    c3     = (stream << 24) | block;  stream 1 = weights, 2 = path normals
     key    = low / high 32 bits of the seed
+
+Uniforms per unit (asset i of a portfolio, output i of a path step):
+    float64  one 32-bit word each: word i%4 of block i//4, U = 1 - x * 2^-32
+    float32  24-bit fields: field i = bits [24 i, 24 i + 23) of the concatenated blocks 0, 1, 2, ...
+             (word 0 of block 0 lowest), i.e. four 23-bit fractions per three words -- 16 uniforms cost
+             3 Philox calls instead of 4 (`philox_fields` in mcp_device.cuh); U = 1 - field * 2^-23
 """
 from __future__ import annotations
 
@@ -65,18 +70,31 @@ def _raw_outputs(index, sub, n_outputs, stream, seed):
     return out[:, :n_outputs]
 
 
+def _fields24(index, sub, n_fields, stream, seed):
+    """uint32 array (len(index), n_fields) of 23-bit fractions: the float32 kernels' uniform fields."""
+    n_trip = (n_fields + 3) // 4
+    w = _raw_outputs(index, sub, 3 * n_trip + ((-3 * n_trip) % 4), stream, seed).astype(np.uint64)
+    a, b, c = w[:, 0:3 * n_trip:3], w[:, 1:3 * n_trip:3], w[:, 2:3 * n_trip:3]
+    f = np.empty((w.shape[0], 4 * n_trip), dtype=np.uint64)
+    f[:, 0::4] = a
+    f[:, 1::4] = (a >> np.uint64(24)) | (b << np.uint64(8))
+    f[:, 2::4] = (b >> np.uint64(16)) | (c << np.uint64(16))
+    f[:, 3::4] = c >> np.uint64(8)
+    return (f[:, :n_fields] & np.uint64(0x7FFFFF)).astype(np.uint32)
+
+
 def exponentials(index, attempt, n_assets, seed, dtype="float32"):
     """Base-2 exponentials e = -log2(U), U in (0, 1].
 
-    float32: U = 1 - (x & 0x7FFFFF) * 2^-23 (23 mantissa bits, built on the GPU with
-    one LOP3 as a float in [1,2) and one subtraction); float64: U = 1 - x * 2^-32.
-    The ln 2 factor cancels in the normalisation w = e / sum(e).
+    float32: U = 1 - field * 2^-23 (23 mantissa bits, built on the GPU with one LOP3 as a
+    float in [1,2) and one subtraction; 24-bit fields, see the module docstring);
+    float64: U = 1 - x * 2^-32.  The ln 2 factor cancels in the normalisation w = e / sum(e).
     """
-    x = _raw_outputs(index, np.broadcast_to(np.asarray(attempt, dtype=np.uint64), np.shape(index)),
-                     n_assets, STREAM_WEIGHTS, seed)
+    sub = np.broadcast_to(np.asarray(attempt, dtype=np.uint64), np.shape(index))
     if dtype == "float32":
-        u = 1.0 - (x & np.uint32(0x7FFFFF)).astype(np.float64) * 2.0 ** -23
+        u = 1.0 - _fields24(index, sub, n_assets, STREAM_WEIGHTS, seed).astype(np.float64) * 2.0 ** -23
     else:
+        x = _raw_outputs(index, sub, n_assets, STREAM_WEIGHTS, seed)
         u = 1.0 - x.astype(np.float64) * 2.0 ** -32
     return -np.log2(u)
 
@@ -128,16 +146,16 @@ def normals(first_index, n_paths, n_steps, n_assets, seed, dtype="float32"):
     U1 in (0,1] from output 2k, angle fraction f in [0,1) from output 2k+1:
     z[2k] = r cos(theta), z[2k+1] = r sin(theta), r = sqrt(-2 ln U1), theta = pi (2f - 1)
     (the angle is centred on 0 so the MUFU sin/cos approximations stay in [-pi, pi)).
-    float32 uses 23-bit fractions, float64 32-bit ones (same convention as `exponentials`).
+    float32 uses the 23-bit fractions of the 24-bit fields, float64 32-bit words (same convention as `exponentials`).
     """
     idx = np.arange(first_index, first_index + n_paths, dtype=np.uint64)
     n_even = (n_assets + 1) // 2 * 2
     Z = np.empty((n_paths, n_steps, n_assets))
     for s in range(n_steps):
-        x = _raw_outputs(idx, np.full(n_paths, s, dtype=np.uint64), n_even, STREAM_NORMALS, seed)
         if dtype == "float32":
-            f = (x & np.uint32(0x7FFFFF)).astype(np.float64) * 2.0 ** -23
+            f = _fields24(idx, np.full(n_paths, s, dtype=np.uint64), n_even, STREAM_NORMALS, seed).astype(np.float64) * 2.0 ** -23
         else:
+            x = _raw_outputs(idx, np.full(n_paths, s, dtype=np.uint64), n_even, STREAM_NORMALS, seed)
             f = x.astype(np.float64) * 2.0 ** -32
         u1 = 1.0 - f[:, 0::2]
         th = np.pi * (2.0 * f[:, 1::2] - 1.0)
