@@ -10,7 +10,7 @@ import mcportfolio as mcp
 from bench import synthetic_inputs
 
 rng = np.random.default_rng(0)
-for n in (2, 16, 20, 33, 256):
+for n in (2, 16, 20, 33, 100, 256):      # 33 / 100 / 256 in RNG mode without bounds run the tcgen05 sweep
     mu, sigma = synthetic_inputs(n)
     P = 1337
     for dtype in ("float32", "float64"):
