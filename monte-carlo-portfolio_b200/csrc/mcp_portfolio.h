@@ -89,7 +89,7 @@ int pf_small_launch(mcp_context* h, PfJob& job);
 int pf_small_replay(mcp_context* h, const PfJob& job, const PfReplay& rp);
 int pf_large_launch(mcp_context* h, PfJob& job);
 int pf_large_replay(mcp_context* h, const PfJob& job, const PfReplay& rp);
-// tcgen05 path of the large sweep (mcp_portfolio_large_tc.cu): FP32, 32 < N <= 256, RNG mode without bounds
+// tcgen05 path of the large sweep (mcp_portfolio_large_tc.cu): FP32, 32 < N <= 256, no bounds (Philox or supplied weights)
 bool pf_large_tc_eligible(const PfJob& job);
 int pf_large_launch_tc(mcp_context* h, PfJob& job);
 

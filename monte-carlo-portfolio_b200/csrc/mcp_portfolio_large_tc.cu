@@ -1,4 +1,4 @@
-// Tensor-core portfolio sweep for 32 < N <= 256 assets in RNG mode (C5: N = 256, 1e9 portfolios).
+// Tensor-core portfolio sweep for 32 < N <= 256 assets, FP32, no bounds (C5: N = 256, 1e9 portfolios; Philox or supplied weights).
 //
 // The quadratic form of 128 portfolios at a time is a GEMM: Y' = E S' with E [128 x N] the tile's
 // un-normalised exponentials and S' the lower triangle of Sigma with doubled off-diagonals, then
@@ -55,6 +55,7 @@ constexpr uint32_t TC_STAGE_COLS = 80;       // hi 32 + lo 32 + bf16 16
 
 struct TcArgs {
     const unsigned char* table;              // global: Shi image, Slo image (canonical UMMA layout), mu[np]
+    const float* w_in;                       // supplied weights [P, n] (parity mode) or null (Philox)
     float* w_out;                            // raw exponentials (scaled by inv_out afterwards) or null
     float* inv_out;                          // 1 / sum(e) per portfolio (only with w_out)
     float* ret_out;
@@ -203,30 +204,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) large_sweep_tc(const TcArgs a) 
             const bool live = p0 + (uint64_t)row < a.P;
             for (int ci = (int)((g + 3u - first_mod) % 3u); ci < C; ci += TC_GROUPS, ++k) {
                 const int c = C - 1 - ci;
-                // ---- the row's 32 values of chunk c: 24-bit fields 32c .. 32c+31 = Philox blocks 6c .. 6c+5 ----
                 float l[TC_KC];
-                {
+                const int i0 = TC_KC * c;
+                if (a.w_in != nullptr) {
+                    // ---- supplied weights (parity mode): this row's 32 values of chunk c from global memory ----
+                    const float* src = a.w_in + (p0 + (uint64_t)row) * (uint64_t)a.n + (uint64_t)i0;
+                    if ((a.n & 3) == 0) {
+#pragma unroll
+                        for (int m = 0; m < 8; ++m) {
+                            const float4 v = (live && i0 + 4 * m < a.n) ? __ldg(reinterpret_cast<const float4*>(src) + m) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            l[4 * m] = v.x; l[4 * m + 1] = v.y; l[4 * m + 2] = v.z; l[4 * m + 3] = v.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < TC_KC; ++j) l[j] = (live && i0 + j < a.n) ? __ldg(src + j) : 0.f;
+                    }
+                } else {
+                    // ---- Philox: 24-bit fields 32c .. 32c+31 = blocks 6c .. 6c+5; l = lg2(U) = -e ----
                     uint32_t f[TC_KC];
                     philox_fields<TC_KC>(c0, c1, 0u, STREAM_WEIGHTS | (uint32_t)(6 * c), a.k0, a.k1, f);
 #pragma unroll
                     for (int j = 0; j < TC_KC; ++j) l[j] = Math<float>::lg2(Math<float>::unit_open0(f[j]));
-                }
-                const int i0 = TC_KC * c;
-                if (i0 + TC_KC > a.n) {                  // only the last chunk can reach past n (uniform branch)
+                    if (i0 + TC_KC > a.n) {              // only the last chunk can reach past n (uniform branch)
 #pragma unroll
-                    for (int j = 0; j < TC_KC; ++j)
-                        if (i0 + j >= a.n) l[j] = 0.f;
+                        for (int j = 0; j < TC_KC; ++j)
+                            if (i0 + j >= a.n) l[j] = 0.f;
+                    }
                 }
-                if (a.w_out != nullptr && live) {         // raw exponentials e = -l; tc_scale_rows normalises them
+                if (a.w_out != nullptr && live) {         // raw values (e = -l, or the supplied weight); tc_scale_rows normalises them
+                    const float sg = a.w_in != nullptr ? 1.f : -1.f;
                     float* dst = a.w_out + (p0 + (uint64_t)row) * (uint64_t)a.n + (uint64_t)i0;
                     if ((a.n & 3) == 0) {
 #pragma unroll
                         for (int m = 0; m < 8; ++m)
-                            if (i0 + 4 * m < a.n) reinterpret_cast<float4*>(dst)[m] = make_float4(-l[4 * m], -l[4 * m + 1], -l[4 * m + 2], -l[4 * m + 3]);
+                            if (i0 + 4 * m < a.n) reinterpret_cast<float4*>(dst)[m] = make_float4(sg * l[4 * m], sg * l[4 * m + 1], sg * l[4 * m + 2], sg * l[4 * m + 3]);
                     } else {
 #pragma unroll
                         for (int j = 0; j < TC_KC; ++j)
-                            if (i0 + j < a.n) dst[j] = -l[j];
+                            if (i0 + j < a.n) dst[j] = sg * l[j];
                     }
                 }
                 if (k > 0) {                             // the stage's previous contents must have been read back
@@ -346,9 +361,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) large_sweep_tc(const TcArgs a) 
             }
             const uint64_t local = tile * TC_ROWS + (uint64_t)row;
             if (local < a.P) {
-                const float q = q0 + q1, s = -(s0 + s1), r = -(r0 + r1);         // e = -l
+                const bool supplied = a.w_in != nullptr;
+                const float q = q0 + q1;
+                const float s = supplied ? 1.f : -(s0 + s1), r = supplied ? (r0 + r1) : -(r0 + r1);         // Philox rows hold l = -e
                 float ret, risk, sharpe;
-                metrics_from<float>(q, r, s, a.rf, false, ret, risk, sharpe);
+                metrics_from<float>(q, r, s, a.rf, supplied, ret, risk, sharpe);
                 ++n_acc;
                 const uint64_t gi = a.first + local;
                 if (sharpe > best_s) { best_s = sharpe; idx_s = gi; }          // tiles ascend per thread: first occurrence kept
@@ -360,7 +377,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) large_sweep_tc(const TcArgs a) 
                 if (a.risk_out) a.risk_out[local] = risk;
                 if (a.sharpe_out) a.sharpe_out[local] = sharpe;
                 if (a.acc_out) a.acc_out[local] = 1;
-                if (a.inv_out) a.inv_out[local] = Math<float>::rcp(s);
+                if (a.inv_out) a.inv_out[local] = supplied ? 1.f : Math<float>::rcp(s);
             }
         }
         warp_argmax<float>(best_s, idx_s);
@@ -420,7 +437,7 @@ static inline uint16_t bf16_round(float x) {
 bool pf_large_tc_eligible(const PfJob& job) {
     const char* v = getenv("MCP_LARGE_TC");               // "0" forces the SIMT kernel (A/B tests, benchmarks)
     if (v && v[0] == '0') return false;
-    return job.dtype == MCP_F32 && job.n > PF_SMALL_MAX_N && job.n <= TC_MAX_N && job.w_in == nullptr && !job.bounds;
+    return job.dtype == MCP_F32 && job.n > PF_SMALL_MAX_N && job.n <= TC_MAX_N && !job.bounds;
 }
 
 int pf_large_launch_tc(mcp_context* h, PfJob& job) {
@@ -451,6 +468,7 @@ int pf_large_launch_tc(mcp_context* h, PfJob& job) {
 
     TcArgs a;
     a.table = dev;
+    a.w_in = (const float*)job.w_in;
     a.w_out = (float*)job.w_out;
     a.inv_out = nullptr;
     if (a.w_out)      // two sweeps can be in flight in the HOST-space pipeline (one per side stream): one scratch each

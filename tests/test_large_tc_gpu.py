@@ -125,3 +125,29 @@ def test_tc_many_tiles_selection_matches_arrays(mcp):
     with simt_kernel():
         sm = mcp.simulate_portfolios(mu, sigma, P, risk_free=0.03, seed=1, dtype="float32", return_arrays=False)
     assert np.isclose(sm.max_sharpe["sharpe"], lean.max_sharpe["sharpe"], rtol=5e-6)
+
+
+@pytest.mark.parametrize("n", [33, 64, 100, 254, 256])
+def test_tc_supplied_weights_parity_mode(mcp, n):
+    """Supplied weights through the tensor-core kernel: identical inputs as the FP64 oracle, 1e-4, same picks."""
+    mu, sigma = wild_sigma(n, seed=100 + n) if n in (64, 256) else synthetic_inputs(n, seed=n)
+    P = 3000
+    W = np.random.RandomState(n).dirichlet(np.ones(n) * 0.5, size=P)          # sparse-ish weights: some near 1, many near 0
+    W[0] = 0; W[0, n - 1] = 1.0                                               # a one-asset portfolio (last column: the zero-padded chunk)
+    W[1] = 1.0 / n
+    tc = mcp.simulate_portfolios(mu, sigma, P, weights=W, risk_free=0.01, risk_target=0.2, dtype="float32")      # FP64 host weights: the FP32 sweep is a screen, near-ties are decided in FP64
+    want = ref.evaluate(W, mu, sigma, 0.01, 0.2)
+    assert tc.n_accepted == P
+    assert np.allclose(tc.risks, want["risks"], rtol=1e-4) and np.allclose(tc.returns, want["returns"], rtol=1e-4, atol=1e-7)
+    assert np.allclose(tc.sharpes, want["sharpes"], rtol=1e-4, atol=1e-4 * np.abs(want["sharpes"]).max())
+    assert np.array_equal(tc.weights, W.astype(np.float32))
+    assert np.isclose(tc.risks[0], np.sqrt(sigma[n - 1, n - 1]), rtol=2e-6)
+    for pick in ("max_sharpe", "target_risk"):
+        assert getattr(tc, pick)["index"] == want[pick]["index"], pick        # FP32 screen + FP64 decision
+    with simt_kernel():
+        sm = mcp.simulate_portfolios(mu, sigma, P, weights=W, risk_free=0.01, risk_target=0.2, dtype="float32")
+    # both kernels are FP32-class: neither may be further from the FP64 oracle than a few FP32 roundings of a
+    # cancelling sum (the ill-scaled covariances lose ~1e-5 in either), and they agree with each other likewise
+    e_tc, e_sm = np.abs(tc.risks / want["risks"] - 1).max(), np.abs(sm.risks / want["risks"] - 1).max()
+    assert e_tc < 2e-5 and e_tc < 3 * e_sm + 2e-6, (e_tc, e_sm)
+    assert np.abs(tc.risks / sm.risks - 1).max() < 2e-5
