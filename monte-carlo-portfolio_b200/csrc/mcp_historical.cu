@@ -15,6 +15,7 @@
 // warp reduction; the selections reuse the (key, first index) argmax machinery of the sweep.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -195,6 +196,182 @@ __global__ void __launch_bounds__(HV_BLOCK) hist_var_kernel(const HistArgs<T> a)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// FP32 fast path for lower-tail ranks (the reference's alpha = 0.95 on T <= 512 periods): a warp works on
+// FOUR consecutive portfolios at once.
+//   * series: every R element read from shared memory feeds four portfolios (two packed FFMA2), so the
+//     LDS count per portfolio drops 4x; the FMA order per (period, portfolio) is the plain kernel's.
+//   * selection: each lane sorts its VPL keys with a sorting network (39 compare-exchanges for 12), parks
+//     positions 1.. in shared memory and keeps only the head in a register; k+1 rounds of
+//     REDUX.UMIN (one instruction for the warp-wide minimum) + ballot pop the order statistics; the
+//     owning lane advances its head with one LDS.  The four portfolios' chains interleave (ILP 4).
+// Results are bit-identical to hist_var_kernel<float, VPL> (tests compare the two).
+// ---------------------------------------------------------------------------------------------
+constexpr int HF_PPW = 4;
+
+template <int VPL> __device__ __forceinline__ void lane_sort(uint32_t (&y)[VPL]) {
+#define MCP_CE(i, j) { const uint32_t lo_ = min(y[i], y[j]), hi_ = max(y[i], y[j]); y[i] = lo_; y[j] = hi_; }
+    if constexpr (VPL == 12) {          // 39-comparator network (verified with the 0/1 principle)
+        MCP_CE(0, 1) MCP_CE(2, 3) MCP_CE(4, 5) MCP_CE(6, 7) MCP_CE(8, 9) MCP_CE(10, 11)
+        MCP_CE(1, 3) MCP_CE(5, 7) MCP_CE(9, 11) MCP_CE(0, 2) MCP_CE(4, 6) MCP_CE(8, 10)
+        MCP_CE(1, 2) MCP_CE(5, 6) MCP_CE(9, 10) MCP_CE(0, 4) MCP_CE(7, 11)
+        MCP_CE(1, 5) MCP_CE(6, 10) MCP_CE(3, 7) MCP_CE(4, 8)
+        MCP_CE(5, 9) MCP_CE(2, 6) MCP_CE(0, 4) MCP_CE(7, 11) MCP_CE(3, 8)
+        MCP_CE(1, 5) MCP_CE(6, 10) MCP_CE(2, 3) MCP_CE(8, 9)
+        MCP_CE(1, 4) MCP_CE(7, 10) MCP_CE(3, 5) MCP_CE(6, 8)
+        MCP_CE(2, 4) MCP_CE(7, 9) MCP_CE(5, 6)
+        MCP_CE(3, 4) MCP_CE(7, 8)
+    } else {                            // odd-even transposition
+#pragma unroll
+        for (int round = 0; round < VPL; ++round) {
+#pragma unroll
+            for (int v = round & 1; v + 1 < VPL; v += 2) MCP_CE(v, v + 1)
+        }
+    }
+#undef MCP_CE
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(HV_BLOCK) hist_var_fast(const HistArgs<float> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sR = reinterpret_cast<float*>(smem_raw);                                 // [n][t_pad], t_pad = 32 VPL
+    float* sW = sR + (size_t)a.n * a.t_pad;                                         // [HV_WARPS][n][4]
+    uint32_t* sK = reinterpret_cast<uint32_t*>(sW + (size_t)HV_WARPS * a.n * HF_PPW);   // [HV_WARPS][4][VPL][32]
+    for (int i = threadIdx.x; i < a.n * a.t_pad; i += HV_BLOCK) sR[i] = a.r_t[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* myW = sW + (size_t)warp * a.n * HF_PPW;
+    uint32_t* myK = sK + (size_t)warp * HF_PPW * VPL * 32;
+
+    float best_v = -Math<float>::inf(), best_c = -Math<float>::inf();
+    uint64_t idx_v = MCP_NO_INDEX, idx_c = MCP_NO_INDEX;
+    const uint64_t groups = (a.P + HF_PPW - 1) / HF_PPW;
+    const uint64_t warps_total = (uint64_t)gridDim.x * HV_WARPS;
+    for (uint64_t gq = (uint64_t)blockIdx.x * HV_WARPS + warp; gq < groups; gq += warps_total) {
+        const uint64_t p0 = gq * HF_PPW;
+        __syncwarp();
+        for (int j = lane; j < HF_PPW * a.n; j += 32) {               // rows p0 .. p0+3 are contiguous: coalesced
+            const int pp = j / a.n, i = j - pp * a.n;
+            myW[i * HF_PPW + pp] = (p0 + (uint64_t)pp < a.P) ? a.w_in[p0 * (uint64_t)a.n + (uint64_t)j] : 0.f;
+        }
+        __syncwarp();
+        // ---- series[t] = sum_i R[t, i] w_i: this lane's periods, four portfolios (a: 0,1  b: 2,3) ----
+        float2 xa[VPL], xb[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) { xa[v] = make_float2(0.f, 0.f); xb[v] = make_float2(0.f, 0.f); }
+        for (int i = 0; i < a.n; ++i) {
+            const float4 w4 = *reinterpret_cast<const float4*>(myW + i * HF_PPW);
+            const float2 wa = make_float2(w4.x, w4.y), wb = make_float2(w4.z, w4.w);
+            const float* row = sR + (size_t)i * a.t_pad + lane;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const float2 r2 = bcast2(row[32 * v]);                  // padded columns are 0
+                xa[v] = fma2(r2, wa, xa[v]);
+                xb[v] = fma2(r2, wb, xb[v]);
+            }
+        }
+        // ---- per portfolio: sort the lane's keys, park positions 1.. in shared memory ----
+        uint32_t head[HF_PPW];
+        int hpos[HF_PPW];
+#pragma unroll
+        for (int pp = 0; pp < HF_PPW; ++pp) {
+            uint32_t y[VPL];
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const float xv = pp == 0 ? xa[v].x : pp == 1 ? xa[v].y : pp == 2 ? xb[v].x : xb[v].y;
+                y[v] = (lane + 32 * v < a.T_) ? HKey<float>::to_key(xv) : 0xffffffffu;      // padding sorts last
+            }
+            lane_sort<VPL>(y);
+            head[pp] = y[0];
+            hpos[pp] = 0;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) myK[(pp * VPL + v) * 32 + lane] = y[v];
+        }
+        // ---- pop the warp-wide minimum k_hi + 1 times (four interleaved chains) ----
+        uint32_t k_lo_key[HF_PPW], k_hi_key[HF_PPW];
+#pragma unroll
+        for (int pp = 0; pp < HF_PPW; ++pp) k_lo_key[pp] = k_hi_key[pp] = 0;
+#pragma unroll 1
+        for (int r = 0; r <= a.k_hi; ++r) {
+#pragma unroll
+            for (int pp = 0; pp < HF_PPW; ++pp) {
+                const uint32_t m = __reduce_min_sync(0xffffffffu, head[pp]);
+                if (r == a.k_lo) k_lo_key[pp] = m;
+                k_hi_key[pp] = m;
+                const unsigned owners = __ballot_sync(0xffffffffu, head[pp] == m);
+                // branch-free pop: every lane reloads its (possibly advanced) head
+                const bool own = lane == __ffs(owners) - 1;
+                hpos[pp] += own ? 1 : 0;
+                const uint32_t nxt = myK[(pp * VPL + (hpos[pp] < VPL ? hpos[pp] : VPL - 1)) * 32 + lane];
+                if (own) head[pp] = hpos[pp] < VPL ? nxt : 0xffffffffu;
+            }
+        }
+        // ---- numpy _lerp, then CVaR = mean(x[x <= VaR]) (VaR if empty), app.py:261-263 ----
+#pragma unroll
+        for (int pp = 0; pp < HF_PPW; ++pp) {
+            const float v_lo = HKey<float>::from_key(k_lo_key[pp]), v_hi = HKey<float>::from_key(k_hi_key[pp]);
+            const float diff = v_hi - v_lo;
+            float var = v_lo + diff * a.gamma;
+            if (a.gamma >= 0.5f) var = v_hi - diff * (1.f - a.gamma);
+            float s = 0.f;
+            int cnt = 0;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const float xv = pp == 0 ? xa[v].x : pp == 1 ? xa[v].y : pp == 2 ? xb[v].x : xb[v].y;
+                const bool in = (lane + 32 * v < a.T_) && xv <= var;
+                s += in ? xv : 0.f;
+                cnt += in ? 1 : 0;
+            }
+            s = warp_sum<float>(s);
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            const float cvar = cnt > 0 ? s / (float)cnt : var;
+            const uint64_t p = p0 + (uint64_t)pp;
+            if (p < a.P) {
+                if (lane == 0) {
+                    if (a.var_out) a.var_out[p] = var;
+                    if (a.cvar_out) a.cvar_out[p] = cvar;
+                }
+                const uint64_t g = a.first + p;
+                if (var > best_v) { best_v = var; idx_v = g; }          // p ascends per warp: first occurrence kept
+                if (cvar > best_c) { best_c = cvar; idx_c = g; }
+            }
+        }
+    }
+    __shared__ PfCand wc[HV_WARPS];
+    if (lane == 0) wc[warp] = PfCand{(double)best_v, idx_v, (double)best_c, idx_c, 0.0, 0.0};
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        PfCand b = wc[0];
+        for (int w = 1; w < HV_WARPS; ++w) {
+            const PfCand o = wc[w];
+            if (cand_better<double>(o.key_s, o.idx_s, b.key_s, b.idx_s)) { b.key_s = o.key_s; b.idx_s = o.idx_s; }
+            if (cand_better<double>(o.key_d, o.idx_d, b.key_d, b.idx_d)) { b.key_d = o.key_d; b.idx_d = o.idx_d; }
+        }
+        a.cands[blockIdx.x] = b;
+    }
+}
+
+template <int VPL>
+static int hist_launch_fast(mcp_context* h, const HistArgs<float>& a, int max_blocks, int* blocks, cudaStream_t st, bool* done) {
+    *done = false;
+    const size_t smem = ((size_t)a.n * a.t_pad + (size_t)HV_WARPS * a.n * HF_PPW) * sizeof(float) + (size_t)HV_WARPS * HF_PPW * VPL * 32 * sizeof(uint32_t);
+    if (a.t_pad != 32 * VPL || smem > h->prop.sharedMemPerBlockOptin) return MCP_OK;           // the plain kernel takes it
+    auto kern = hist_var_fast<VPL>;
+    if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    MCP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HV_BLOCK, smem));
+    if (per_sm < 1) return MCP_OK;
+    const uint64_t groups = (a.P + HF_PPW - 1) / HF_PPW;
+    uint64_t grid = std::min<uint64_t>((uint64_t)h->prop.multiProcessorCount * per_sm, (groups + HV_WARPS - 1) / HV_WARPS);
+    grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, max_blocks));
+    *blocks = (int)grid;
+    kern<<<(unsigned)grid, HV_BLOCK, smem, st>>>(a);
+    MCP_CUDA(h, cudaGetLastError());
+    h->launches++;
+    *done = true;
+    return MCP_OK;
+}
+
 template <typename T, int VPL>
 static int hist_launch_t(mcp_context* h, const HistArgs<T>& a, size_t smem, int max_blocks, int* blocks, cudaStream_t st) {
     auto kern = hist_var_kernel<T, VPL>;
@@ -214,6 +391,17 @@ static int hist_launch_t(mcp_context* h, const HistArgs<T>& a, size_t smem, int 
 template <typename T>
 static int hist_dispatch(mcp_context* h, const HistArgs<T>& a, size_t smem, int max_blocks, int* blocks, cudaStream_t st) {
     const int vpl = (a.T_ + 31) / 32;
+    if constexpr (sizeof(T) == 4) {
+        const char* env = getenv("MCP_HIST_FAST");                 // "0" forces the plain kernel (A/B tests)
+        if (a.k_hi < HV_EXTRACT_MAX && !(env && env[0] == '0')) {
+            bool done = false;
+            if (vpl <= 4 && a.t_pad == 128) MCP_CHECK(hist_launch_fast<4>(h, a, max_blocks, blocks, st, &done));
+            else if (vpl <= 8 && a.t_pad == 256) MCP_CHECK(hist_launch_fast<8>(h, a, max_blocks, blocks, st, &done));
+            else if (vpl <= 12 && a.t_pad == 384) MCP_CHECK(hist_launch_fast<12>(h, a, max_blocks, blocks, st, &done));
+            else if (vpl <= 16 && a.t_pad == 512) MCP_CHECK(hist_launch_fast<16>(h, a, max_blocks, blocks, st, &done));
+            if (done) return MCP_OK;
+        }
+    }
 #define MCP_HV(V) if (vpl <= V) return hist_launch_t<T, V>(h, a, smem, max_blocks, blocks, st);
     MCP_HV(1) MCP_HV(2) MCP_HV(4) MCP_HV(8) MCP_HV(12) MCP_HV(16) MCP_HV(24) MCP_HV(32) MCP_HV(64)
 #undef MCP_HV

@@ -116,3 +116,27 @@ def test_asset_stats_kernel(mcp, c1, c2):
             if T > 2:
                 assert got[j]["sharpe"] == pytest.approx(want["sharpe"], rel=1e-9)
                 assert got[j]["sortino"] == pytest.approx(want["sortino"], rel=1e-9)
+
+
+@pytest.mark.parametrize("T", [33, 100, 200, 365, 384, 500])
+@pytest.mark.parametrize("alpha", [0.95, 0.99])
+def test_fast_fp32_kernel_is_bit_identical_to_the_plain_one(mcp, T, alpha):
+    """hist_var_fast (4 portfolios per warp, sorting network, REDUX pop-min) against hist_var_kernel<float>
+    (MCP_HIST_FAST=0) on the same inputs, and both against the FP64 oracle; ties included."""
+    import os
+    rng = np.random.default_rng(T)
+    n, P = 16, 1003                                        # P % 4 != 0: the last group is partial
+    R = np.round(rng.standard_normal((T, n)) * 0.04, 3)    # rounded returns: repeated series values (ties at the rank)
+    W = rng.dirichlet(np.ones(n), size=P)
+    W[5] = 0; W[5, 2] = 1.0                                # a one-asset portfolio: the series IS a (tied) column of R
+    fast = mcp.historical_var_cvar(R, W, alpha, dtype="float32")
+    os.environ["MCP_HIST_FAST"] = "0"
+    try:
+        plain = mcp.historical_var_cvar(R, W, alpha, dtype="float32")
+    finally:
+        del os.environ["MCP_HIST_FAST"]
+    assert np.array_equal(fast["var"], plain["var"]) and np.array_equal(fast["cvar"], plain["cvar"])
+    assert fast["best_var"] == plain["best_var"] and fast["best_cvar"] == plain["best_cvar"]
+    v, c = ref.historical_var_cvar(R, W, alpha)
+    assert np.allclose(fast["var"], v, rtol=1e-4, atol=1e-7) and np.allclose(fast["cvar"], c, rtol=1e-4, atol=1e-7)
+    assert fast["best_var"]["index"] == int(np.argmax(fast["var"])) and fast["best_cvar"]["index"] == int(np.argmax(fast["cvar"]))
