@@ -62,3 +62,26 @@ def test_paths_any_shape(mcp, n, M, S, dtype, seed, first):
     x = out["terminal"].astype(np.float64)
     for a, (v, c) in out["stats"].items():
         assert v == ref.var(x, a) and np.isclose(c, ref.cvar(x, a), rtol=1e-12, atol=1e-300)
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(n=st.integers(33, 256), P=st.integers(1, 400), seed=st.integers(0, 2**40), first=st.integers(0, 2**45),
+       supplied=st.booleans())
+def test_tensor_core_sweep_any_shape(mcp, n, P, seed, first, supplied):
+    """FP32, 32 < N <= 256: the tcgen05 kernel (Philox rows or supplied rows) against the FP64 oracle."""
+    mu, sigma = synthetic_inputs(n, seed=n + 3)
+    if supplied:
+        W = np.random.RandomState(seed % 2**31).dirichlet(np.ones(n), size=P)
+        r = mcp.simulate_portfolios(mu, sigma, P, weights=W, risk_free=0.03, dtype="float32")
+        assert np.array_equal(r.weights, W.astype(np.float32))
+    else:
+        r = mcp.simulate_portfolios(mu, sigma, P, risk_free=0.03, seed=seed, first_index=first, dtype="float32")
+        W, _ = philox_np.dirichlet_weights(first, P, n, seed, "float32")
+        assert np.allclose(r.weights, W, atol=2e-6)
+    want = ref.evaluate(W, mu, sigma, 0.03, 0.30)
+    assert r.n_accepted == P
+    assert np.allclose(r.risks, want["risks"], rtol=1e-4) and np.allclose(r.returns, want["returns"], rtol=1e-4)
+    assert np.allclose(r.sharpes, want["sharpes"], rtol=1e-4, atol=1e-3)
+    i = r.max_sharpe["index"]
+    assert r.max_sharpe["sharpe"] == float(r.sharpes[i]) or supplied       # supplied FP64 rows: the pick is decided in FP64
+    assert np.isclose(r.sharpes[i], r.sharpes.max(), rtol=1e-5)
