@@ -227,6 +227,18 @@ int mcp_historical_var(mcp_handle h, const mcp_hist_params* params,
 int mcp_asset_stats(mcp_handle h, const double* returns_host, int n_periods, int n_assets, double risk_free,
                     double annual_factor, double alpha, double* stats_out);
 
+/* ---- frontier envelope of metrics that are already on the device ------------------------
+ * Bins n (risk, return) pairs (DEVICE arrays of `dtype`; NaN rows = skipped portfolios are ignored)
+ * exactly like mcp_portfolios does with n_bins > 0: K equal risk bins over [risk_lo, risk_hi], per bin
+ * the largest return and the first global index (first_index + row) attaining it.  Lets a caller sweep
+ * ONCE with the risk / return arrays kept in HBM (8 bytes per portfolio), read the attained risk range
+ * from that sweep (all-reduce it across ranks), and bin afterwards -- instead of sweeping twice
+ * (replaces the scatter of app.py:726-736).
+ * bin_best_return / bin_best_index: host, n_bins entries; empty bins get -inf / MCP_NO_INDEX.          */
+int mcp_envelope_arrays(mcp_handle h, int dtype, const void* risks_dev, const void* returns_dev, uint64_t n,
+                        uint64_t first_index, double risk_lo, double risk_hi, int n_bins,
+                        double* bin_best_return, uint64_t* bin_best_index);
+
 /* ---- microbenchmarks used as roofline denominators (bench.py) ------------------------- */
 int mcp_measure_fma_peak(mcp_handle h, int dtype /* MCP_F32 | MCP_F64 | 2 = packed FP32x2 (FFMA2) */, double* tflops);
 

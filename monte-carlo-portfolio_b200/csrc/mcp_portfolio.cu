@@ -391,3 +391,42 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
     fill_selection(out->target_risk, rec.data() + PF_REC_HEADER + N, N);
     return MCP_OK;
 }
+
+extern "C" int mcp_envelope_arrays(mcp_handle h, int dtype, const void* risks, const void* returns, uint64_t n, uint64_t first_index,
+                                   double risk_lo, double risk_hi, int K, double* bin_best_return, uint64_t* bin_best_index) {
+    if (!h) return MCP_ERR_INVALID;
+    MCP_REQUIRE(h, dtype == MCP_F32 || dtype == MCP_F64, "mcp_envelope_arrays: bad dtype %d", dtype);
+    MCP_REQUIRE(h, K >= 1 && K <= ENV_MAX_BINS, "mcp_envelope_arrays: n_bins=%d out of range [1, %d]", K, ENV_MAX_BINS);
+    MCP_REQUIRE(h, bin_best_return && bin_best_index, "mcp_envelope_arrays: bin outputs are NULL");
+    MCP_REQUIRE(h, std::isfinite(risk_lo) && std::isfinite(risk_hi) && risk_hi > risk_lo, "mcp_envelope_arrays: needs finite risk_lo < risk_hi");
+    MCP_REQUIRE(h, (risks && returns) || n == 0, "mcp_envelope_arrays: NULL arrays");
+    for (int b = 0; b < K; ++b) { bin_best_return[b] = -INFINITY; bin_best_index[b] = MCP_NO_INDEX; }
+    if (n == 0) return MCP_OK;
+    mcp_device_guard guard(h->device);
+    cudaStream_t st = h->stream;
+    const size_t es = dtype == MCP_F64 ? 8 : 4;
+    unsigned long long* env = nullptr;
+    MCP_CHECK(mcp_dev_reserve(h, 8, sizeof(unsigned long long) * 8 * (size_t)K, (void**)&env));
+    unsigned long long *fmax = env, *fidx = env + 2 * (size_t)K, *cmax = env + 4 * (size_t)K, *cidx = env + 6 * (size_t)K;
+    MCP_CHECK(env_reset(h, K, fmax, fidx, st));
+    MCP_CUDA(h, cudaEventRecord(h->ev[0], st));
+    (void)es;
+    MCP_CHECK(env_reset(h, K, cmax, cidx, st));
+    MCP_CHECK(env_chunk(h, dtype, risks, returns, n, first_index, risk_lo, risk_hi, K, cmax, cidx, st));   // grid-stride over all n
+    MCP_CHECK(env_fold(h, K, cmax, cidx, fmax, fidx, st));
+    MCP_CUDA(h, cudaEventRecord(h->ev[1], st));
+    std::vector<unsigned long long> hb(2 * (size_t)K);
+    MCP_CUDA(h, cudaMemcpyAsync(hb.data(), fmax, sizeof(unsigned long long) * K, cudaMemcpyDeviceToHost, st));
+    MCP_CUDA(h, cudaMemcpyAsync(hb.data() + K, fidx, sizeof(unsigned long long) * K, cudaMemcpyDeviceToHost, st));
+    MCP_CUDA(h, cudaStreamSynchronize(st));
+    float ms = 0;
+    MCP_CUDA(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    h->last_ms = ms;
+    for (int b = 0; b < K; ++b) {
+        if (hb[b] == 0ull) continue;                         // empty bin
+        bin_best_return[b] = mcp_key_to_value(hb[b], dtype);
+        bin_best_index[b] = hb[K + b];
+    }
+    return MCP_OK;
+}
+

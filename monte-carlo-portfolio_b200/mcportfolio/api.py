@@ -191,7 +191,10 @@ def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, risk_free=0.0
                       dtype='float32' and FP64 weights the FP32 sweep screens and the picks are
                       decided in FP64 among the near-ties (same index as the FP64 reference).
     risk_free         subtracted raw, as app.py:711 (pass 3.0 for the app's default widget value).
-    return_arrays     False: selections only, zero HBM write-back (C3 sizes).
+    return_arrays     False: selections only, zero HBM write-back (C3 sizes).  'device': arrays stay on
+                      the GPU as torch tensors.  'device-metrics': only risks and returns stay on the GPU
+                      (8 bytes per portfolio; skipped portfolios hold NaN) -- what the single-sweep
+                      frontier envelope keeps in HBM.
     out               optional dict of preallocated arrays ('weights', 'returns', 'risks',
                       'sharpes', 'accepted') to reuse pinned buffers across calls.
     n_bins, risk_range  frontier envelope: per risk bin over [lo, hi] the maximum return and the
@@ -235,7 +238,8 @@ def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, risk_free=0.0
     params.risk_free, params.risk_target = float(risk_free), float(risk_target)
     params.min_weights, params.max_weights = _ptr(lo), _ptr(hi)
     params.max_tries, params.keep_last = int(max_tries), int(bool(keep_last))
-    params.space = MCP_DEVICE if device_mode or return_arrays == "device" else MCP_HOST
+    metrics_only = return_arrays == "device-metrics"
+    params.space = MCP_DEVICE if device_mode or return_arrays == "device" or metrics_only else MCP_HOST
     params.weights_in = _ptr(w_in)
     params.weights_recheck = _ptr(recheck)
     n_bins = int(n_bins)
@@ -249,6 +253,8 @@ def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, risk_free=0.0
     if return_arrays:
         names = (("weights", (P, n), npdt), ("returns", (P,), npdt), ("risks", (P,), npdt),
                  ("sharpes", (P,), npdt), ("accepted", (P,), np.uint8))
+        if metrics_only:
+            names = names[1:3]
         if params.space == MCP_DEVICE:
             import torch
             tdt = torch.float32 if code == MCP_F32 else torch.float64
@@ -261,7 +267,7 @@ def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, risk_free=0.0
                 if a is not None and (a.shape != shape or a.dtype != dt or not a.flags.c_contiguous):
                     raise ValueError(f"out[{name!r}] must be C-contiguous {shape} {np.dtype(dt)}")
                 arrays[name] = a if a is not None else np.empty(shape, dtype=dt)
-        for name in ("weights", "returns", "risks", "sharpes", "accepted"):
+        for name in arrays:
             setattr(res, name, _ptr(arrays[name]))
     bin_ret = np.empty(n_bins)
     bin_idx = np.empty(n_bins, dtype=np.uint64)
@@ -279,7 +285,9 @@ def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, risk_free=0.0
 
     n_acc = int(res.n_accepted)
     positions = None
-    if return_arrays and n_acc < P:
+    if metrics_only:
+        positions = None                        # rows are not compacted: row i is portfolio first_index + i
+    elif return_arrays and n_acc < P:
         # skipped portfolios (app.py:706-707): the reference's arrays simply do not contain them
         acc = arrays["accepted"]
         if params.space == MCP_DEVICE:
@@ -334,22 +342,73 @@ def efficient_frontier(mean_returns, cov_matrix, points=200, min_weights=None, m
 def frontier_envelope(mean_returns, cov_matrix, n_portfolios, n_bins=512, *, risk_range=None, **kw):
     """Efficient-frontier envelope binned by risk (config C5), plus the two picks.
 
-    Replaces the reference's scatter of every portfolio (app.py:726-736).  With risk_range=None
-    a first sweep (no write-back) finds the attained [risk_min, risk_max]; the counter-based
-    generator then reproduces exactly the same portfolios for the binning sweep.
+    Replaces the reference's scatter of every portfolio (app.py:726-736).  With risk_range=None the
+    attained [risk_min, risk_max] defines the bins: when the per-portfolio (risk, return) pairs fit in
+    HBM (8 bytes each) ONE sweep keeps them there and a bandwidth-bound pass bins them; otherwise a first
+    sweep (no write-back) finds the range and the counter-based generator reproduces exactly the same
+    portfolios for a second, binning sweep.  Both routes give identical bins.
     Returns the PortfolioResult of the binning sweep; result.extra['envelope'] holds
     'edges' (n_bins + 1), 'best_return' (-inf for empty bins) and 'best_index' (global, -1 if empty).
     """
     kw.setdefault("return_arrays", False)
+    if risk_range is None and kw["return_arrays"] is False and kw.get("weights") is None and _metrics_fit(n_portfolios, kw):
+        # ONE sweep: risks / returns stay in HBM (8 B per portfolio), the attained range comes out of the same
+        # sweep, the binning pass then reads the arrays back at HBM speed (mcp_envelope_arrays)
+        r = simulate_portfolios(mean_returns, cov_matrix, n_portfolios, **{**kw, "return_arrays": "device-metrics"})
+        if r.n_accepted == 0:
+            raise ValueError("no portfolio satisfied the bounds; the envelope is empty")
+        r.extra["envelope"] = envelope_from_arrays(r.risks, r.returns, n_bins, _widen(r.risk_range),
+                                                   first_index=kw.get("first_index", 0), device=kw.get("device"))
+        r.risks = r.returns = None              # scratch of the envelope, not part of the result
+        return r
     if risk_range is None:
         probe = simulate_portfolios(mean_returns, cov_matrix, n_portfolios, **{**kw, "return_arrays": False})
         if probe.n_accepted == 0:
             raise ValueError("no portfolio satisfied the bounds; the envelope is empty")
-        lo, hi = probe.risk_range
-        if not hi > lo:
-            hi = lo + max(abs(lo), 1.0) * 1e-6
-        risk_range = (lo, hi)
+        risk_range = _widen(probe.risk_range)
     return simulate_portfolios(mean_returns, cov_matrix, n_portfolios, n_bins=n_bins, risk_range=risk_range, **kw)
+
+
+def _widen(rng):
+    lo, hi = rng
+    if not hi > lo:
+        hi = lo + max(abs(lo), 1.0) * 1e-6
+    return (lo, hi)
+
+
+def _metrics_fit(n_portfolios, kw) -> bool:
+    """Do the risk / return arrays of the single-sweep envelope fit comfortably in free HBM?"""
+    import torch
+    eng = get_engine(kw.get("device"))
+    es = 8 if _dtype(kw.get("dtype", "float32"))[0] == MCP_F64 else 4
+    free, _ = torch.cuda.mem_get_info(eng.device)
+    return 2 * es * int(n_portfolios) <= free // 2
+
+
+def envelope_from_arrays(risks, returns, n_bins, risk_range, *, first_index=0, device=None):
+    """Frontier envelope of (risk, return) arrays that are already on the GPU (CUDA torch tensors of one dtype):
+    per risk bin over [lo, hi] the maximum return and the first global index (first_index + row) attaining it;
+    NaN rows are ignored.  Same result as the n_bins / risk_range options of `simulate_portfolios`."""
+    import torch
+    if not (_is_device_tensor(risks) and _is_device_tensor(returns)):
+        raise TypeError("envelope_from_arrays takes CUDA torch tensors")
+    if risks.dtype != returns.dtype or risks.dtype not in (torch.float32, torch.float64) or risks.shape != returns.shape or risks.dim() != 1:
+        raise ValueError("risks and returns must be 1-D tensors of the same length and dtype (float32 / float64)")
+    n_bins = int(n_bins)
+    lo, hi = float(risk_range[0]), float(risk_range[1])
+    if not (np.isfinite(lo) and np.isfinite(hi) and hi > lo):
+        raise ValueError("the envelope needs risk_range=(lo, hi) with finite lo < hi")
+    risks, returns = risks.contiguous(), returns.contiguous()
+    eng = get_engine(device if device is not None else risks.device.index)
+    eng.set_stream(torch.cuda.current_stream(eng.device).cuda_stream)
+    bin_ret = np.empty(n_bins)
+    bin_idx = np.empty(n_bins, dtype=np.uint64)
+    check(eng.handle, lib().mcp_envelope_arrays(eng.handle, MCP_F32 if risks.dtype == torch.float32 else MCP_F64,
+                                                risks.data_ptr(), returns.data_ptr(), risks.numel(), int(first_index), lo, hi, n_bins,
+                                                bin_ret.ctypes.data, bin_idx.ctypes.data))
+    idx = bin_idx.astype(np.int64)
+    idx[bin_idx == np.uint64(MCP_NO_INDEX)] = -1
+    return {"edges": np.linspace(lo, hi, n_bins + 1), "best_return": bin_ret, "best_index": idx}
 
 
 # ------------------------------------------------------------------------------------------

@@ -110,8 +110,9 @@ def simulate_portfolios_sharded(mean_returns, cov_matrix, n_portfolios, *, group
 
 
 def frontier_envelope_sharded(mean_returns, cov_matrix, n_portfolios, n_bins=512, *, risk_range=None, group=None, **kw):
-    """`frontier_envelope` over the whole job (C5).  Two sweeps of this rank's block: the first
-    finds the attained risk range (all-reduced min / max), the second bins; the per-rank bins
+    """`frontier_envelope` over the whole job (C5).  One sweep of this rank's block with its (risk, return)
+    pairs kept in HBM, the attained risk range all-reduced (min / max), then a bandwidth-bound binning pass
+    (two sweeps -- range, then bins -- when the pairs do not fit or the backend is gloo); the per-rank bins
     (n_bins x (return, global index)) are all-gathered and merged (larger return, then lower
     index), so every rank ends with the envelope of the WHOLE job."""
     import torch
@@ -123,17 +124,30 @@ def frontier_envelope_sharded(mean_returns, cov_matrix, n_portfolios, n_bins=512
     nccl = dist.get_backend(group) == "nccl"
     dev = torch.device("cuda", eng.device) if nccl else torch.device("cpu")
     kw = dict(kw, return_arrays=False)
-    if risk_range is None:
-        probe = api.simulate_portfolios(mean_returns, cov_matrix, count, first_index=first, **kw)
-        lo, hi = probe.risk_range if probe.n_accepted else (float("inf"), float("-inf"))
+
+    def global_range(r):
+        lo, hi = r.risk_range if r.n_accepted else (float("inf"), float("-inf"))
         t = torch.tensor([-lo, hi], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-        lo, hi = -float(t[0]), float(t[1])
-        if not hi > lo:
-            hi = lo + max(abs(lo), 1.0) * 1e-6
-        risk_range = (lo, hi)
-    r = api.simulate_portfolios(mean_returns, cov_matrix, count, first_index=first, n_bins=n_bins,
-                                risk_range=risk_range, **kw)
+        return api._widen((-float(t[0]), float(t[1])))
+
+    single = risk_range is None and nccl and kw.get("weights") is None and api._metrics_fit(count, kw)
+    if risk_range is None:                      # every rank must take the same route: all or none keep their metrics
+        flag = torch.tensor([1 if single else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        single = bool(flag.item())
+    if single:
+        # ONE sweep per rank with (risk, return) kept in HBM; the range is all-reduced, then each rank bins its arrays
+        r = api.simulate_portfolios(mean_returns, cov_matrix, count, first_index=first, **dict(kw, return_arrays="device-metrics"))
+        risk_range = global_range(r)
+        r.extra["envelope"] = api.envelope_from_arrays(r.risks, r.returns, n_bins, risk_range, first_index=first, device=kw.get("device"))
+        r.risks = r.returns = None
+    else:
+        if risk_range is None:
+            probe = api.simulate_portfolios(mean_returns, cov_matrix, count, first_index=first, **kw)
+            risk_range = global_range(probe)
+        r = api.simulate_portfolios(mean_returns, cov_matrix, count, first_index=first, n_bins=n_bins,
+                                    risk_range=risk_range, **kw)
     env = r.extra["envelope"]
     ret = torch.from_numpy(np.ascontiguousarray(env["best_return"])).to(dev)
     idx = torch.from_numpy(np.ascontiguousarray(env["best_index"])).to(dev)

@@ -461,3 +461,33 @@ def test_rng_weight_histogram_chi_square(mcp):
         s = W[:, 0] + W[:, 1]                                                       # Beta(2, N-2): mean 2/N
         assert abs(s.mean() - 2 / N) < 5 * np.sqrt(2 * (N - 2) / (N * N * (N + 1)) / P)
         assert np.isclose(s.var(), 2 * (N - 2) / (N * N * (N + 1)), rtol=0.01)
+
+
+@pytest.mark.parametrize("n,dtype", [(16, "float32"), (100, "float32"), (40, "float64")])
+def test_single_sweep_envelope_equals_two_sweeps(mcp, n, dtype):
+    """frontier_envelope keeps (risk, return) in HBM and bins them afterwards (mcp_envelope_arrays); the bins,
+    picks and range must be those of the two-sweep route (range sweep, then a binning sweep with n_bins set)."""
+    mu, sigma = synthetic_inputs(n, seed=5)
+    P, K = 300_000, 97
+    one = mcp.frontier_envelope(mu, sigma, P, K, risk_free=0.03, seed=6, dtype=dtype, first_index=12345)
+    two = mcp.simulate_portfolios(mu, sigma, P, risk_free=0.03, seed=6, dtype=dtype, first_index=12345, return_arrays=False,
+                                  n_bins=K, risk_range=one.risk_range)
+    a, b = one.extra["envelope"], two.extra["envelope"]
+    assert np.array_equal(a["best_index"], b["best_index"]) and np.array_equal(a["best_return"], b["best_return"])
+    assert np.array_equal(a["edges"], b["edges"]) and (a["best_index"] >= 0).sum() > K // 2
+    assert one.risks is None and one.n_accepted == two.n_accepted == P
+    for pick in ("max_sharpe", "target_risk"):
+        x, y = getattr(one, pick), getattr(two, pick)
+        assert x["global_index"] == y["global_index"] and x["sharpe"] == y["sharpe"] and x["risk"] == y["risk"]
+        assert np.array_equal(x["weights"], y["weights"])
+    # the public binning entry on arrays the caller holds
+    import torch
+    full = mcp.simulate_portfolios(mu, sigma, 50_000, risk_free=0.03, seed=6, dtype=dtype, return_arrays="device")
+    lo, hi = full.risk_range
+    env = mcp.envelope_from_arrays(full.risks, full.returns, 32, (lo, hi), first_index=7)
+    best, idx = _envelope_oracle(full.risks.cpu().numpy(), full.returns.cpu().numpy(), 32, lo, hi, dtype)
+    assert np.array_equal(env["best_return"], best) and np.array_equal(env["best_index"], np.where(idx >= 0, idx + 7, -1))
+    with pytest.raises(TypeError):
+        mcp.envelope_from_arrays(np.zeros(4), np.zeros(4), 4, (0.0, 1.0))
+    with pytest.raises(ValueError):
+        mcp.envelope_from_arrays(full.risks, full.returns, 4, (1.0, 1.0))
