@@ -19,7 +19,8 @@
 //   warps 0-11   three generator groups of 128 threads, one A stage each.  Group g produces the CTA's K chunks
 //                n = g (mod 3): 8 Philox calls -> l = lg2(U) = -e -> split -> tcgen05.st into its stage -> a_full[g].
 //                It never waits for the tensor core, only for its stage to have been read back (a_free[g]).
-//   warp 16      TMEM allocation and the single-thread MMA issue loop (10 MMAs per chunk, tcgen05.commit -> d_done).
+//   warp 16      TMEM allocation and the MMA issue loop: warp-convergent, one elected thread, descriptors computed on
+//                uniform values before the barrier waits (10 tcgen05.mma per chunk back to back, tcgen05.commit -> d_done).
 //                Chunks run from the widest (c = C-1, all columns, overwrites the accumulator) to the narrowest,
 //                so column block c is final as soon as chunk c's MMAs complete and the epilogue of a tile
 //                overlaps its remaining MMAs.
@@ -99,16 +100,18 @@ __device__ __forceinline__ bool mbar_test(uint64_t* b, uint32_t parity) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* b) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
+// warp-convergent issue: every lane executes the block, one elected lane issues (no divergent-branch lane loop around UTCHMMA)
+__device__ __forceinline__ void mma_tf32_ts_elect(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+__device__ __forceinline__ void mma_bf16_ts_elect(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ void mma_bf16_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+__device__ __forceinline__ void tc_commit_elect(uint64_t* b) {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(b)) : "memory");
 }
 #define TC_R32(v) "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),   \
                   "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),     \
@@ -273,36 +276,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) large_sweep_tc(const TcArgs a) 
             first_mod = (first_mod + (uint32_t)C) % 3u;
         }
     } else if (warp == TC_MMA_WARP) {
-        // ================= MMA issue: one thread =================
-        const uint32_t id_tf32_base = tc_idesc(2u, 0u), id_bf16_base = tc_idesc(1u, 0u);
+        // ================= MMA issue: one elected thread, warp-convergent =================
+        // The ten tcgen05.mma of a chunk go out back to back once its A stage is full: the descriptors are plain
+        // functions of the chunk index, computed on warp-uniform values before the barrier waits, and the issue is
+        // predicated on elect.sync in convergent code (an `if (lane == 0)` makes ptxas wrap every UTCHMMA in a lane loop).
+        const uint32_t sbo = 128u, hi_base = smem_u32(sHi), lo_base = smem_u32(sLo);
+        const uint32_t id32_base = tc_idesc(2u, 0u), id16_base = tc_idesc(1u, 0u);
         uint32_t g = 0, cyc = 0;                         // chunk n = 3 * cyc + g uses stage g for the cyc-th time
         uint32_t tl = 0;
         for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
             for (int ci = 0; ci < C; ++ci) {
                 const int c = C - 1 - ci;
-                const uint32_t N = (uint32_t)(TC_KC * (c + 1));
+                const uint32_t N = (uint32_t)(TC_KC * (c + 1)), lbo = (N / 8u) * 128u;
+                const uint32_t bhi = hi_base + tc_hi_off(c), blo = lo_base + tc_lo_off(c);
+                const uint64_t bd0 = tc_sdesc(bhi, lbo, sbo), bd1 = tc_sdesc(bhi + 2u * lbo, lbo, sbo), bd2 = tc_sdesc(bhi + 4u * lbo, lbo, sbo),
+                               bd3 = tc_sdesc(bhi + 6u * lbo, lbo, sbo), bl0 = tc_sdesc(blo, lbo, sbo), bl1 = tc_sdesc(blo + 2u * lbo, lbo, sbo);
+                const uint32_t id32 = id32_base | ((N >> 3) << 17), id16 = id16_base | ((N >> 3) << 17);
+                const uint32_t a_hi = tmem + TC_COL_A + TC_STAGE_COLS * g, a_lo = a_hi + 32u, a_bf = a_hi + 64u;
                 mbar_wait(&a_full[g], cyc & 1u);
                 if (ci == 0 && tl > 0) mbar_wait(drained, (tl - 1u) & 1u);          // chunk C-1 overwrites the whole accumulator
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t lbo = (N / 8u) * 128u, sbo = 128u;
-                    const uint32_t a_hi = tmem + TC_COL_A + TC_STAGE_COLS * g, a_lo = a_hi + 32u, a_bf = a_hi + 64u;
-                    const uint32_t id32 = id_tf32_base | ((N >> 3) << 17), id16 = id_bf16_base | ((N >> 3) << 17);
-                    const uint32_t bhi = smem_u32(sHi) + tc_hi_off(c), blo = smem_u32(sLo) + tc_lo_off(c);
-#pragma unroll
-                    for (uint32_t ks = 0; ks < 4; ++ks) {
-                        const uint64_t bd = tc_sdesc(bhi + ks * 2u * lbo, lbo, sbo);
-                        mma_tf32_ts(tmem, a_hi + 8u * ks, bd, id32, (ci > 0 || ks > 0) ? 1u : 0u);
-                        mma_tf32_ts(tmem, a_lo + 8u * ks, bd, id32, 1u);
-                    }
-#pragma unroll
-                    for (uint32_t ks = 0; ks < 2; ++ks) {
-                        const uint64_t bd = tc_sdesc(blo + ks * 2u * lbo, lbo, sbo);
-                        mma_bf16_ts(tmem, a_bf + 8u * ks, bd, id16, 1u);
-                    }
-                    tc_commit(&d_done[g]);
-                }
-                __syncwarp();
+                mma_tf32_ts_elect(tmem, a_hi, bd0, id32, ci > 0 ? 1u : 0u);
+                mma_tf32_ts_elect(tmem, a_lo, bd0, id32, 1u);
+                mma_tf32_ts_elect(tmem, a_hi + 8u, bd1, id32, 1u);
+                mma_tf32_ts_elect(tmem, a_lo + 8u, bd1, id32, 1u);
+                mma_tf32_ts_elect(tmem, a_hi + 16u, bd2, id32, 1u);
+                mma_tf32_ts_elect(tmem, a_lo + 16u, bd2, id32, 1u);
+                mma_tf32_ts_elect(tmem, a_hi + 24u, bd3, id32, 1u);
+                mma_tf32_ts_elect(tmem, a_lo + 24u, bd3, id32, 1u);
+                mma_bf16_ts_elect(tmem, a_bf, bl0, id16, 1u);
+                mma_bf16_ts_elect(tmem, a_bf + 8u, bl1, id16, 1u);
+                tc_commit_elect(&d_done[g]);
                 if (++g == TC_GROUPS) { g = 0; ++cyc; }
             }
         }
