@@ -227,7 +227,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) large_sweep_tc(const TcArgs a) 
                     uint32_t f[TC_KC];
                     philox_fields<TC_KC>(c0, c1, 0u, STREAM_WEIGHTS | (uint32_t)(6 * c), a.k0, a.k1, f);
 #pragma unroll
-                    for (int j = 0; j < TC_KC; ++j) l[j] = Math<float>::lg2(Math<float>::unit_open0(f[j]));
+                    for (int j = 0; j < TC_KC; j += 2) {          // U = 2 - f in (0, 1], two per FFMA2 (same values as unit_open0)
+                        const float2 m2 = make_float2(__uint_as_float((f[j] & 0x007fffffu) | 0x3f800000u),
+                                                      __uint_as_float((f[j + 1] & 0x007fffffu) | 0x3f800000u));
+                        const float2 u2 = fma2(m2, bcast2(-1.0f), bcast2(2.0f));
+                        l[j] = Math<float>::lg2(u2.x);
+                        l[j + 1] = Math<float>::lg2(u2.y);
+                    }
                     if (i0 + TC_KC > a.n) {              // only the last chunk can reach past n (uniform branch)
 #pragma unroll
                         for (int j = 0; j < TC_KC; ++j)
@@ -256,9 +262,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) large_sweep_tc(const TcArgs a) 
                 for (int h = 0; h < 2; ++h) {
                     uint32_t hi[16], lo[16], bf[8];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
+                    for (int j = 0; j < 16; j += 2) {            // lo = l - hi exactly (one FFMA2 per pair)
                         hi[j] = __float_as_uint(l[16 * h + j]) & 0xffffe000u;
-                        lo[j] = __float_as_uint(l[16 * h + j] - __uint_as_float(hi[j]));
+                        hi[j + 1] = __float_as_uint(l[16 * h + j + 1]) & 0xffffe000u;
+                        const float2 lo2 = fma2(make_float2(__uint_as_float(hi[j]), __uint_as_float(hi[j + 1])), bcast2(-1.0f),
+                                                make_float2(l[16 * h + j], l[16 * h + j + 1]));
+                        lo[j] = __float_as_uint(lo2.x);
+                        lo[j + 1] = __float_as_uint(lo2.y);
                     }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -323,7 +333,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) large_sweep_tc(const TcArgs a) 
         unsigned int n_acc = 0;
         uint32_t g = 0, cyc = 0;
         for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            float q0 = 0.f, q1 = 0.f, s0 = 0.f, s1 = 0.f, r0 = 0.f, r1 = 0.f;
+            float2 q2 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f), r2 = make_float2(0.f, 0.f);     // .x: even assets, .y: odd assets
             for (int ci = 0; ci < C; ++ci) {
                 const int c = C - 1 - ci;
                 const uint32_t st = lane_base + TC_COL_A + TC_STAGE_COLS * g;
@@ -345,20 +355,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) large_sweep_tc(const TcArgs a) 
 #pragma unroll
                     for (int m = 0; m < 4; ++m) {
                         const float4 u = mu4[m];
-                        const float l0 = __uint_as_float(hi[4 * m]) + __uint_as_float(lo[4 * m]);
-                        const float l1 = __uint_as_float(hi[4 * m + 1]) + __uint_as_float(lo[4 * m + 1]);
-                        const float l2 = __uint_as_float(hi[4 * m + 2]) + __uint_as_float(lo[4 * m + 2]);
-                        const float l3 = __uint_as_float(hi[4 * m + 3]) + __uint_as_float(lo[4 * m + 3]);
-                        q0 = fmaf(__uint_as_float(y[4 * m]), l0, q0);
-                        q1 = fmaf(__uint_as_float(y[4 * m + 1]), l1, q1);
-                        q0 = fmaf(__uint_as_float(y[4 * m + 2]), l2, q0);
-                        q1 = fmaf(__uint_as_float(y[4 * m + 3]), l3, q1);
-                        s0 += l0 + l1;
-                        s1 += l2 + l3;
-                        r0 = fmaf(l0, u.x, r0);
-                        r1 = fmaf(l1, u.y, r1);
-                        r0 = fmaf(l2, u.z, r0);
-                        r1 = fmaf(l3, u.w, r1);
+                        // l = hi + lo exactly; packed FP32x2 throughout (one FFMA2 = two assets)
+                        const float2 la = fma2(make_float2(__uint_as_float(hi[4 * m]), __uint_as_float(hi[4 * m + 1])), bcast2(1.0f),
+                                               make_float2(__uint_as_float(lo[4 * m]), __uint_as_float(lo[4 * m + 1])));
+                        const float2 lb = fma2(make_float2(__uint_as_float(hi[4 * m + 2]), __uint_as_float(hi[4 * m + 3])), bcast2(1.0f),
+                                               make_float2(__uint_as_float(lo[4 * m + 2]), __uint_as_float(lo[4 * m + 3])));
+                        q2 = fma2(make_float2(__uint_as_float(y[4 * m]), __uint_as_float(y[4 * m + 1])), la, q2);
+                        q2 = fma2(make_float2(__uint_as_float(y[4 * m + 2]), __uint_as_float(y[4 * m + 3])), lb, q2);
+                        s2 = fma2(la, bcast2(1.0f), s2);
+                        s2 = fma2(lb, bcast2(1.0f), s2);
+                        r2 = fma2(la, make_float2(u.x, u.y), r2);
+                        r2 = fma2(lb, make_float2(u.z, u.w), r2);
                     }
                 }
                 if (++g == TC_GROUPS) { g = 0; ++cyc; }
@@ -366,8 +373,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) large_sweep_tc(const TcArgs a) 
             const uint64_t local = tile * TC_ROWS + (uint64_t)row;
             if (local < a.P) {
                 const bool supplied = a.w_in != nullptr;
-                const float q = q0 + q1;
-                const float s = supplied ? 1.f : -(s0 + s1), r = supplied ? (r0 + r1) : -(r0 + r1);         // Philox rows hold l = -e
+                const float q = q2.x + q2.y;
+                const float s = supplied ? 1.f : -(s2.x + s2.y), r = supplied ? (r2.x + r2.y) : -(r2.x + r2.y);         // Philox rows hold l = -e
                 float ret, risk, sharpe;
                 metrics_from<float>(q, r, s, a.rf, supplied, ret, risk, sharpe);
                 ++n_acc;
