@@ -20,6 +20,7 @@ the reference's path on all host cores plus the reference-verbatim loop on one c
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -112,7 +113,12 @@ class ClockSampler:
         if self.proc:
             time.sleep(0.12)
             self.proc.terminate()
+            try:                                   # nvidia-smi's NVML teardown holds driver locks for tens of ms: let it finish
+                self.proc.wait(timeout=5)          # HERE, not inside the next workload's timed steps
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
             self.t.join(timeout=2)
+            time.sleep(0.3)
 
     def summary(self):
         sm, smax, reasons = [], [], set()
@@ -222,10 +228,18 @@ def run_ours(args):
 
     def timed(fn, steps, warmup):
         """-> (device seconds max over ranks, host wall seconds max over ranks, kernel ms list, last result)"""
+        res = None
         for _ in range(warmup):
-            fn()
+            res = fn()          # keep the previous result alive across the next call, exactly as the timed loop does: the
+                                # caching allocator then sizes its pool (one cudaMalloc of tens of ms) during the warm-up
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        kms, res = [], None
+        kms = []
+        hosts = []
+        # a full (generation-2) collection over torch's import-time object graph costs tens of ms and used to land
+        # inside one timed step; collect now, park the survivors, and keep the collector off while timing
+        gc.collect()
+        gc.freeze()
+        gc.disable()
         barrier()
         host = 0.0
         for a, b in ev:
@@ -237,8 +251,12 @@ def run_ours(args):
             b.record(stream)
             b.synchronize()
             host += time.perf_counter() - t0
+            hosts.append(round((time.perf_counter() - t0) * 1e3, 2))
             kms.append(res.kernel_ms if hasattr(res, "kernel_ms") else res["kernel_ms"])
         barrier()
+        gc.enable()
+        if os.environ.get("BENCH_DEBUG") and rank == 0:
+            print("per-step ms:", [round(a.elapsed_time(b), 2) for a, b in ev], "kernel ms:", [round(k, 2) for k in kms], "host ms:", hosts, file=sys.stderr)
         dev_s = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
         t = torch.tensor([dev_s, host], dtype=torch.float64, device="cuda")
         if world > 1:
