@@ -338,7 +338,7 @@ def run_ours(args):
         return
 
     # ---- roofline (rank 0's kernel): SIMT FP32 pipe, measured live ----
-    fma_peak = eng.measure_fma_peak("float32")
+    fma_peak = max(eng.measure_fma_peak("float32") for _ in range(5))      # a peak is a maximum: best of 5 runs of the microbenchmark
     achieved = my_count * flops_per_portfolio(n) / kernel_s / 1e12
     peaks = measured_peaks()
     traffic = None
@@ -355,7 +355,7 @@ def run_ours(args):
         env_line["roofline"]["fp32_equivalent_vs_ffma_peak"] = env_line["roofline"]["fp32_equivalent_tflops"] / fma_peak
     roofline = {"bound": "fp32-simt", "kernel": "small_sweep_packed<16,4> (Philox, FFMA2, no write-back)", "achieved": achieved,
                 "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak, "traffic": traffic,
-                "peak_source": "FFMA-chain microbenchmark (mcp_measure_fma_peak) run in this process; "
+                "peak_source": "FFMA-chain microbenchmark (mcp_measure_fma_peak), best of 5 runs in this process; "
                                "MEASURED_PEAKS.json has no SIMT figure",
                 "algorithmic_flop_per_portfolio": flops_per_portfolio(n), "portfolios_per_launch": my_count,
                 "kernel_ms": kernel_s * 1e3,
