@@ -71,20 +71,36 @@ def merge_records(records, larger_is_better: bool) -> dict | None:
     return best
 
 
-def all_gather_records(rec: dict | None, n_assets: int, device=None, group=None):
-    """Every rank's record, on every rank (one all_gather of (6 + N) doubles per criterion)."""
+def _pack_flat(rec: dict | None, n_assets: int) -> np.ndarray:
+    """One record as float64[_REC_HEAD + N]: the int64 global index rides along bit for bit."""
+    idx, body = pack_record(rec, n_assets)
+    return np.concatenate([np.array([idx], dtype=np.int64).view(np.float64), body])
+
+
+def _unpack_flat(flat: np.ndarray) -> dict | None:
+    return unpack_record(int(flat[:1].view(np.int64)[0]), flat[1:])
+
+
+def all_gather_flat(flat: np.ndarray, device=None, group=None) -> np.ndarray:
+    """Every rank's float64 vector on every rank, shape (world, len): ONE all_gather and one copy back
+    (each collective and each tiny D2H costs tens of microseconds: they are what a 20 ms step can lose)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    idx, body = pack_record(rec, n_assets)
     dev = torch.device("cpu") if device is None else device
-    t_idx = torch.tensor([idx], dtype=torch.int64, device=dev)
-    t_body = torch.from_numpy(body).to(dev)
-    g_idx = [torch.empty_like(t_idx) for _ in range(world)]
-    g_body = [torch.empty_like(t_body) for _ in range(world)]
-    dist.all_gather(g_idx, t_idx, group=group)
-    dist.all_gather(g_body, t_body, group=group)
-    return [unpack_record(int(i.item()), b.cpu().numpy()) for i, b in zip(g_idx, g_body)]
+    t = torch.from_numpy(np.ascontiguousarray(flat, dtype=np.float64)).to(dev)
+    out = torch.empty((world, t.numel()), dtype=torch.float64, device=dev)
+    dist.all_gather(list(out.unbind(0)), t, group=group)
+    return out.cpu().numpy()
+
+
+def all_gather_records(rec: dict | None, n_assets: int, device=None, group=None):
+    """Every rank's record, on every rank (one all_gather of (7 + N) doubles)."""
+    return [_unpack_flat(row) for row in all_gather_flat(_pack_flat(rec, n_assets), device, group)]
+
+
+def _with_global(rec):
+    return None if rec is None else dict(rec, index=rec["global_index"])
 
 
 def simulate_portfolios_sharded(mean_returns, cov_matrix, n_portfolios, *, group=None, **kw):
@@ -97,14 +113,13 @@ def simulate_portfolios_sharded(mean_returns, cov_matrix, n_portfolios, *, group
     n = len(np.asarray(mean_returns))
     r = api.simulate_portfolios(mean_returns, cov_matrix, count, first_index=first, **kw)
     dev = torch.device("cuda", api.get_engine(kw.get("device")).device) if dist.get_backend(group) == "nccl" else None
-    for name, larger in (("max_sharpe", True), ("target_risk", False)):
-        rec = getattr(r, name)
-        if rec is not None:
-            rec = dict(rec, index=rec["global_index"])
-        setattr(r, name, merge_records(all_gather_records(rec, n, dev, group), larger))
-    acc = torch.tensor([r.n_accepted], dtype=torch.int64, device=dev or "cpu")
-    dist.all_reduce(acc, group=group)
-    r.extra["n_accepted_global"] = int(acc.item())
+    L = _REC_HEAD + n
+    flat = np.concatenate([_pack_flat(_with_global(r.max_sharpe), n), _pack_flat(_with_global(r.target_risk), n),
+                           np.array([r.n_accepted], dtype=np.int64).view(np.float64)])
+    G = all_gather_flat(flat, dev, group)
+    r.max_sharpe = merge_records([_unpack_flat(row[:L]) for row in G], True)
+    r.target_risk = merge_records([_unpack_flat(row[L:2 * L]) for row in G], False)
+    r.extra["n_accepted_global"] = int(np.ascontiguousarray(G[:, 2 * L]).view(np.int64).sum())
     r.extra["shard"] = (first, count)
     return r
 
@@ -149,18 +164,15 @@ def frontier_envelope_sharded(mean_returns, cov_matrix, n_portfolios, n_bins=512
         r = api.simulate_portfolios(mean_returns, cov_matrix, count, first_index=first, n_bins=n_bins,
                                     risk_range=risk_range, **kw)
     env = r.extra["envelope"]
-    ret = torch.from_numpy(np.ascontiguousarray(env["best_return"])).to(dev)
-    idx = torch.from_numpy(np.ascontiguousarray(env["best_index"])).to(dev)
-    g_ret = [torch.empty_like(ret) for _ in range(world)]
-    g_idx = [torch.empty_like(idx) for _ in range(world)]
-    dist.all_gather(g_ret, ret, group=group)
-    dist.all_gather(g_idx, idx, group=group)
-    env["best_return"], env["best_index"] = merge_envelopes([t.cpu().numpy() for t in g_ret], [t.cpu().numpy() for t in g_idx])
-    for name, larger in (("max_sharpe", True), ("target_risk", False)):
-        rec = getattr(r, name)
-        if rec is not None:
-            rec = dict(rec, index=rec["global_index"])
-        setattr(r, name, merge_records(all_gather_records(rec, n, dev if nccl else None, group), larger))
+    L = _REC_HEAD + n
+    flat = np.concatenate([np.asarray(env["best_return"], dtype=np.float64), np.asarray(env["best_index"], dtype=np.int64).view(np.float64),
+                           _pack_flat(_with_global(r.max_sharpe), n), _pack_flat(_with_global(r.target_risk), n)])
+    G = all_gather_flat(flat, dev if nccl else None, group)
+    K = int(n_bins)
+    env["best_return"], env["best_index"] = merge_envelopes([row[:K] for row in G],
+                                                            [np.ascontiguousarray(row[K:2 * K]).view(np.int64) for row in G])
+    r.max_sharpe = merge_records([_unpack_flat(row[2 * K:2 * K + L]) for row in G], True)
+    r.target_risk = merge_records([_unpack_flat(row[2 * K + L:2 * K + 2 * L]) for row in G], False)
     r.extra["risk_range_global"] = risk_range
     return r
 
