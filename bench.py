@@ -427,12 +427,14 @@ def run_ours(args):
                      "workload": "simulate_method('CVaR'): 1e6 Philox portfolios, all arrays to host, T=365 x N=16 returns matrix "
                                  "(e2e through the public API; pageable host arrays)",
                      "opt_idx": mo["opt_idx"],
-                     "kernel": {"name": "hist_var_kernel<float,12>", "portfolios_per_s": Ph / (hv["kernel_ms"] * 1e-3),
+                     "kernel": {"name": "hist_var_fast<12> (4 portfolios per warp, FFMA2 series, sorting network + REDUX pop-min)", "portfolios_per_s": Ph / (hv["kernel_ms"] * 1e-3),
                                 "kernel_ms": hv["kernel_ms"],
                                 "roofline": {"bound": "fp32-simt", "achieved": hflop, "unit": "TFLOP/s",
                                              "algorithmic_flop_per_portfolio": 2 * Th * n,
-                                             "note": "R.w is T*N FMA per portfolio; the exact order-statistic selection (warp "
-                                                     "shuffles / votes, no flops) is most of the instruction stream"}}}
+                                             "peak": fma_peak, "frac": hflop / fma_peak,
+                                             "note": "R.w is T*N FMA per portfolio; the exact order-statistic selection (per-lane "
+                                                     "sort, REDUX / vote pops: no flops) and shared-memory loads are most of the "
+                                                     "instruction stream"}}}
         del Wd
 
     # ---- the app's own size: one rerun of tab 3 = 5 methods x 2500 portfolios (app.py:681-682) ----

@@ -236,12 +236,16 @@ __global__ void __launch_bounds__(HV_BLOCK) hist_var_fast(const HistArgs<float> 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* sR = reinterpret_cast<float*>(smem_raw);                                 // [n][t_pad], t_pad = 32 VPL
     float* sW = sR + (size_t)a.n * a.t_pad;                                         // [HV_WARPS][n][4]
-    uint32_t* sK = reinterpret_cast<uint32_t*>(sW + (size_t)HV_WARPS * a.n * HF_PPW);   // [HV_WARPS][4][VPL][32]
+    uint32_t* sK = reinterpret_cast<uint32_t*>(sW + (size_t)HV_WARPS * a.n * HF_PPW);   // [HV_WARPS][4][VPL + 1][32], last = sentinel
     for (int i = threadIdx.x; i < a.n * a.t_pad; i += HV_BLOCK) sR[i] = a.r_t[i];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* myW = sW + (size_t)warp * a.n * HF_PPW;
-    uint32_t* myK = sK + (size_t)warp * HF_PPW * VPL * 32;
+    uint32_t* myK = sK + (size_t)warp * HF_PPW * (VPL + 1) * 32 + lane;
+    unsigned lt_mask;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+#pragma unroll
+    for (int pp = 0; pp < HF_PPW; ++pp) myK[(pp * (VPL + 1) + VPL) * 32] = 0xffffffffu;      // a lane that ran out of values never wins again
 
     float best_v = -Math<float>::inf(), best_c = -Math<float>::inf();
     uint64_t idx_v = MCP_NO_INDEX, idx_c = MCP_NO_INDEX;
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(HV_BLOCK) hist_var_fast(const HistArgs<float> 
         }
         // ---- per portfolio: sort the lane's keys, park positions 1.. in shared memory ----
         uint32_t head[HF_PPW];
-        int hpos[HF_PPW];
+        const uint32_t* next[HF_PPW];                     // this lane's next parked key of each portfolio
 #pragma unroll
         for (int pp = 0; pp < HF_PPW; ++pp) {
             uint32_t y[VPL];
@@ -283,29 +287,29 @@ __global__ void __launch_bounds__(HV_BLOCK) hist_var_fast(const HistArgs<float> 
             }
             lane_sort<VPL>(y);
             head[pp] = y[0];
-            hpos[pp] = 0;
+            next[pp] = myK + (pp * (VPL + 1) + 1) * 32;
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) myK[(pp * VPL + v) * 32 + lane] = y[v];
+            for (int v = 1; v < VPL; ++v) myK[(pp * (VPL + 1) + v) * 32] = y[v];
         }
-        // ---- pop the warp-wide minimum k_hi + 1 times (four interleaved chains) ----
+        // ---- pop the warp-wide minimum k_hi + 1 times (four interleaved chains): REDUX.UMIN, ballot, and the lowest
+        // owning lane (no lower lane holds the minimum) advances to its next parked key with one LDS ----
         uint32_t k_lo_key[HF_PPW], k_hi_key[HF_PPW];
-#pragma unroll
-        for (int pp = 0; pp < HF_PPW; ++pp) k_lo_key[pp] = k_hi_key[pp] = 0;
-#pragma unroll 1
-        for (int r = 0; r <= a.k_hi; ++r) {
+        auto pop = [&](uint32_t (&out)[HF_PPW]) {
 #pragma unroll
             for (int pp = 0; pp < HF_PPW; ++pp) {
                 const uint32_t m = __reduce_min_sync(0xffffffffu, head[pp]);
-                if (r == a.k_lo) k_lo_key[pp] = m;
-                k_hi_key[pp] = m;
+                out[pp] = m;
                 const unsigned owners = __ballot_sync(0xffffffffu, head[pp] == m);
-                // branch-free pop: every lane reloads its (possibly advanced) head
-                const bool own = lane == __ffs(owners) - 1;
-                hpos[pp] += own ? 1 : 0;
-                const uint32_t nxt = myK[(pp * VPL + (hpos[pp] < VPL ? hpos[pp] : VPL - 1)) * 32 + lane];
-                if (own) head[pp] = hpos[pp] < VPL ? nxt : 0xffffffffu;
+                const bool own = head[pp] == m && (owners & lt_mask) == 0u;
+                const uint32_t nxt = *next[pp];             // every lane reloads (branch-free); only the owner takes it
+                if (own) { head[pp] = nxt; next[pp] += 32; }
             }
-        }
+        };
+#pragma unroll 1
+        for (int r = 0; r <= a.k_lo; ++r) pop(k_lo_key);
+#pragma unroll
+        for (int pp = 0; pp < HF_PPW; ++pp) k_hi_key[pp] = k_lo_key[pp];
+        if (a.k_hi > a.k_lo) pop(k_hi_key);
         // ---- numpy _lerp, then CVaR = mean(x[x <= VaR]) (VaR if empty), app.py:261-263 ----
 #pragma unroll
         for (int pp = 0; pp < HF_PPW; ++pp) {
@@ -354,7 +358,7 @@ __global__ void __launch_bounds__(HV_BLOCK) hist_var_fast(const HistArgs<float> 
 template <int VPL>
 static int hist_launch_fast(mcp_context* h, const HistArgs<float>& a, int max_blocks, int* blocks, cudaStream_t st, bool* done) {
     *done = false;
-    const size_t smem = ((size_t)a.n * a.t_pad + (size_t)HV_WARPS * a.n * HF_PPW) * sizeof(float) + (size_t)HV_WARPS * HF_PPW * VPL * 32 * sizeof(uint32_t);
+    const size_t smem = ((size_t)a.n * a.t_pad + (size_t)HV_WARPS * a.n * HF_PPW) * sizeof(float) + (size_t)HV_WARPS * HF_PPW * (VPL + 1) * 32 * sizeof(uint32_t);
     if (a.t_pad != 32 * VPL || smem > h->prop.sharedMemPerBlockOptin) return MCP_OK;           // the plain kernel takes it
     auto kern = hist_var_fast<VPL>;
     if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
