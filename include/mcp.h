@@ -163,6 +163,11 @@ int mcp_paths(mcp_handle h, const mcp_path_params* params,
  * `count` uint64 (kind 0) or double (kind 1) values that must be summed in place across
  * ranks; `n_total` is the global element count (= n when allreduce is NULL).             */
 typedef int (*mcp_allreduce_fn)(void* device_buffer, size_t count, int kind, void* user);
+/* By default the callback is SYNCHRONOUS: libmcp drains its stream before calling it and expects the sums to be
+ * in place when it returns.  With mcp_set_allreduce_stream_ordered(h, 1) the caller promises that the callback only
+ * ENQUEUES the reduction on the handle's stream (mcp_set_stream; e.g. an NCCL all-reduce on that stream): the radix
+ * passes, their all-reduces and the device-side digit selection then run back to back without host round trips.     */
+int mcp_set_allreduce_stream_ordered(mcp_handle h, int on);
 
 int mcp_quantiles(mcp_handle h, const void* values, int space, int dtype, uint64_t n,
                   uint64_t n_total, const double* alphas, int n_alphas,

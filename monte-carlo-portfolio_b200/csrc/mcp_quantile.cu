@@ -42,9 +42,12 @@ template <> struct KeyOf<double> {
 template <typename T>
 __global__ void __launch_bounds__(SEL_BLOCK) select_hist_kernel(const T* __restrict__ v, uint64_t n, int n_slots,
                                                                 const __grid_constant__ SelSlots slots, int shift, int bits,
-                                                                unsigned long long* __restrict__ hist) {
+                                                                unsigned long long* __restrict__ hist,
+                                                                const unsigned long long* __restrict__ dev_prefix) {
     using K = typename KeyOf<T>::K;
     extern __shared__ unsigned int sh[];
+    __shared__ K s_prefix[MCP_MAX_TARGETS];           // per-slot prefix: kernel parameter, or the device-side select state
+    if (threadIdx.x < MCP_MAX_TARGETS) s_prefix[threadIdx.x] = (K)(dev_prefix ? dev_prefix[threadIdx.x] : slots.prefix[threadIdx.x]);
     const int nb = 1 << bits;
     for (int i = threadIdx.x; i < n_slots * nb; i += SEL_BLOCK) sh[i] = 0;
     __syncthreads();
@@ -57,7 +60,7 @@ __global__ void __launch_bounds__(SEL_BLOCK) select_hist_kernel(const T* __restr
         const unsigned digit = (unsigned)((k >> shift) & mask);
         const K hi = all_match ? (K)0 : (K)(k >> (all_match ? 0 : hi_shift));
         for (int s = 0; s < n_slots; ++s) {
-            if (all_match || hi == (K)slots.prefix[s]) {
+            if (all_match || hi == s_prefix[s]) {
                 const unsigned act = __activemask();
                 const unsigned peers = __match_any_sync(act, digit);
                 if (lane == __ffs(peers) - 1) atomicAdd(&sh[s * nb + digit], (unsigned)__popc(peers));
@@ -107,6 +110,57 @@ __global__ void __launch_bounds__(SEL_BLOCK) tail_sum_kernel(const T* __restrict
         for (int w = 0; w < SEL_BLOCK / 32; ++w) acc += ws[w][threadIdx.x];
         if (acc != 0.0) atomicAdd((threadIdx.x & 1) ? &counts[threadIdx.x >> 1] : &sums[threadIdx.x >> 1], acc);
     }
+}
+
+// Device-side twin of mcp_select_advance: one CTA per target (slot t = target t, no prefix sharing).  Finds the
+// digit d with cum(d) <= rank < cum(d) + hist[d], then rank -= cum(d), prefix = prefix << bits | d.
+struct SelDevState {
+    unsigned long long prefix[MCP_MAX_TARGETS];
+    unsigned long long rank[MCP_MAX_TARGETS];
+    int error;                                         // a rank fell outside its prefix's population
+};
+
+__global__ void __launch_bounds__(256) select_advance_kernel(const unsigned long long* __restrict__ hist, int bits, SelDevState* st) {
+    const int t = blockIdx.x, nb = 1 << bits, per = (nb + 255) / 256;        // bins per thread (<= 8)
+    const unsigned long long* row = hist + (size_t)t * nb;
+    unsigned long long mine = 0;
+    for (int j = 0; j < per; ++j) {
+        const int d = threadIdx.x * per + j;
+        if (d < nb) mine += row[d];
+    }
+    // exclusive scan of the per-thread sums over the CTA
+    __shared__ unsigned long long wsum[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = mine;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xffffffffu, inc, m);
+        if (lane >= m) inc += o;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    unsigned long long base = 0;
+    for (int w = 0; w < warp; ++w) base += wsum[w];
+    const unsigned long long excl = base + inc - mine, rank = st->rank[t];
+    __shared__ int found;
+    if (threadIdx.x == 0) found = 0;
+    __syncthreads();
+    if (rank >= excl && rank < excl + mine) {          // exactly one thread owns the rank
+        unsigned long long cum = excl;
+        for (int j = 0; j < per; ++j) {
+            const int d = threadIdx.x * per + j;
+            const unsigned long long c = d < nb ? row[d] : 0ull;
+            if (rank < cum + c) {
+                st->rank[t] = rank - cum;
+                st->prefix[t] = (st->prefix[t] << bits) | (unsigned long long)d;
+                found = 1;
+                break;
+            }
+            cum += c;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && !found) st->error = 1;
 }
 
 static void assign_slots(mcp_select_state* s) {
@@ -207,11 +261,11 @@ int mcp_select_hist(mcp_handle h, const void* values_dev, int dtype, uint64_t n,
     if (dtype == MCP_F64) {
         if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(select_hist_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         select_hist_kernel<double><<<grid_for(h, n, 4), SEL_BLOCK, smem, st>>>((const double*)values_dev, n, s->n_slots, slots, shift, bits,
-                                                                                (unsigned long long*)hist_dev);
+                                                                                (unsigned long long*)hist_dev, nullptr);
     } else {
         if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(select_hist_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         select_hist_kernel<float><<<grid_for(h, n, 4), SEL_BLOCK, smem, st>>>((const float*)values_dev, n, s->n_slots, slots, shift, bits,
-                                                                               (unsigned long long*)hist_dev);
+                                                                               (unsigned long long*)hist_dev, nullptr);
     }
     MCP_CUDA(h, cudaGetLastError());
     h->launches++;
@@ -262,35 +316,77 @@ int mcp_quantiles(mcp_handle h, const void* values, int space, int dtype, uint64
         lo_t[a] = add_rank(lo);
         hi_t[a] = add_rank(hi);
     }
-    mcp_select_state sel;
-    MCP_CHECK(mcp_select_init(&sel, dtype == MCP_F64 ? 64 : 32, ranks, nt) == MCP_OK ? MCP_OK
-              : mcp_fail(h, MCP_ERR_INVALID, "mcp_quantiles: select init failed"));
     const size_t hist_elems = (size_t)MCP_MAX_TARGETS << SEL_BITS;
     unsigned long long* d_hist = nullptr;
-    MCP_CHECK(mcp_dev_reserve(h, 5, hist_elems * 8 + 64 * 8, (void**)&d_hist));
-    std::vector<uint64_t> h_hist(hist_elems);
+    MCP_CHECK(mcp_dev_reserve(h, 5, hist_elems * 8 + 64 * 8 + sizeof(SelDevState), (void**)&d_hist));
+    SelDevState* d_state = (SelDevState*)(d_hist + hist_elems + 64);
     double ms_total = 0;
+    uint64_t final_prefix[MCP_MAX_TARGETS];
     MCP_CUDA(h, cudaEventRecord(h->ev[0], st));
-    while (mcp_select_pass_bits(&sel) > 0) {
-        const int bits = mcp_select_pass_bits(&sel);
-        const size_t cnt = (size_t)sel.n_slots << bits;
-        MCP_CHECK(mcp_select_hist(h, v, dtype, n, &sel, (uint64_t*)d_hist));
-        if (allreduce) {
-            MCP_CUDA(h, cudaStreamSynchronize(st));
-            if (allreduce(d_hist, cnt, 0, user) != 0) return mcp_fail(h, MCP_ERR_INVALID, "mcp_quantiles: allreduce callback failed");
+    if (!allreduce || h->allreduce_stream_ordered) {
+        // ---- device-resident refinement: histogram -> (all-reduce on this stream) -> digit selection, pass after pass,
+        // one host round trip at the end.  One slot per target (no prefix sharing: <= 16 histograms of 2048 bins).
+        const int key_bits = dtype == MCP_F64 ? 64 : 32;
+        SelDevState hs;
+        memset(&hs, 0, sizeof hs);
+        for (int t = 0; t < nt; ++t) hs.rank[t] = ranks[t];
+        MCP_CUDA(h, cudaMemcpyAsync(d_state, &hs, sizeof hs, cudaMemcpyHostToDevice, st));
+        SelSlots unused;
+        memset(&unused, 0, sizeof unused);
+        for (int done = 0; done < key_bits;) {
+            const int bits = std::min(SEL_BITS, key_bits - done), shift = key_bits - done - bits;
+            const size_t cnt = (size_t)nt << bits;
+            MCP_CUDA(h, cudaMemsetAsync(d_hist, 0, cnt * 8, st));
+            if (n) {
+                const size_t smem = sizeof(unsigned int) * cnt;
+                if (dtype == MCP_F64) {
+                    if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(select_hist_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    select_hist_kernel<double><<<grid_for(h, n, 4), SEL_BLOCK, smem, st>>>((const double*)v, n, nt, unused, shift, bits, d_hist, d_state->prefix);
+                } else {
+                    if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(select_hist_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    select_hist_kernel<float><<<grid_for(h, n, 4), SEL_BLOCK, smem, st>>>((const float*)v, n, nt, unused, shift, bits, d_hist, d_state->prefix);
+                }
+                MCP_CUDA(h, cudaGetLastError());
+                h->launches++;
+            }
+            if (allreduce && allreduce(d_hist, cnt, 0, user) != 0) return mcp_fail(h, MCP_ERR_INVALID, "mcp_quantiles: allreduce callback failed");
+            select_advance_kernel<<<nt, 256, 0, st>>>(d_hist, bits, d_state);
+            MCP_CUDA(h, cudaGetLastError());
+            h->launches++;
+            done += bits;
         }
-        MCP_CUDA(h, cudaMemcpyAsync(h_hist.data(), d_hist, cnt * 8, cudaMemcpyDeviceToHost, st));
+        MCP_CUDA(h, cudaMemcpyAsync(&hs, d_state, sizeof hs, cudaMemcpyDeviceToHost, st));
         MCP_CUDA(h, cudaStreamSynchronize(st));
-        if (mcp_select_advance(&sel, h_hist.data()) != MCP_OK)
+        if (hs.error)
             return mcp_fail(h, MCP_ERR_INVALID, "mcp_quantiles: rank outside the population (n_total=%llu inconsistent with the data?)",
                             (unsigned long long)n_total);
+        for (int t = 0; t < nt; ++t) final_prefix[t] = hs.prefix[t];
+    } else {
+        // ---- synchronous callback: the host state machine (mcp_select_*) scans the all-reduced histograms ----
+        mcp_select_state sel;
+        MCP_CHECK(mcp_select_init(&sel, dtype == MCP_F64 ? 64 : 32, ranks, nt) == MCP_OK ? MCP_OK
+                  : mcp_fail(h, MCP_ERR_INVALID, "mcp_quantiles: select init failed"));
+        std::vector<uint64_t> h_hist(hist_elems);
+        while (mcp_select_pass_bits(&sel) > 0) {
+            const int bits = mcp_select_pass_bits(&sel);
+            const size_t cnt = (size_t)sel.n_slots << bits;
+            MCP_CHECK(mcp_select_hist(h, v, dtype, n, &sel, (uint64_t*)d_hist));
+            MCP_CUDA(h, cudaStreamSynchronize(st));
+            if (allreduce(d_hist, cnt, 0, user) != 0) return mcp_fail(h, MCP_ERR_INVALID, "mcp_quantiles: allreduce callback failed");
+            MCP_CUDA(h, cudaMemcpyAsync(h_hist.data(), d_hist, cnt * 8, cudaMemcpyDeviceToHost, st));
+            MCP_CUDA(h, cudaStreamSynchronize(st));
+            if (mcp_select_advance(&sel, h_hist.data()) != MCP_OK)
+                return mcp_fail(h, MCP_ERR_INVALID, "mcp_quantiles: rank outside the population (n_total=%llu inconsistent with the data?)",
+                                (unsigned long long)n_total);
+        }
+        for (int t = 0; t < nt; ++t) final_prefix[t] = sel.prefix[t];
     }
     // ---- VaR: numpy's _lerp on the two exact order statistics ----
     TailArgs ta;
     memset(&ta, 0, sizeof ta);
     for (int a = 0; a < n_alphas; ++a) {
-        const double lo = mcp_key_to_value(sel.prefix[lo_t[a]], dtype);
-        const double hi = mcp_key_to_value(sel.prefix[hi_t[a]], dtype);
+        const double lo = mcp_key_to_value(final_prefix[lo_t[a]], dtype);
+        const double hi = mcp_key_to_value(final_prefix[hi_t[a]], dtype);
         const double t = gamma[a], diff = hi - lo;
         double r = lo + diff * t;
         if (t >= 0.5) r = hi - diff * (1 - t);
@@ -309,7 +405,7 @@ int mcp_quantiles(mcp_handle h, const void* values, int space, int dtype, uint64
     }
     MCP_CUDA(h, cudaEventRecord(h->ev[1], st));
     if (allreduce) {
-        MCP_CUDA(h, cudaStreamSynchronize(st));
+        if (!h->allreduce_stream_ordered) MCP_CUDA(h, cudaStreamSynchronize(st));
         if (allreduce(d_sums, 2 * MCP_MAX_ALPHAS, 1, user) != 0) return mcp_fail(h, MCP_ERR_INVALID, "mcp_quantiles: allreduce callback failed");
     }
     double sums[2 * MCP_MAX_ALPHAS];
@@ -325,6 +421,12 @@ int mcp_quantiles(mcp_handle h, const void* values, int space, int dtype, uint64
         ms_total = ms;
     }
     h->last_ms = ms_total;
+    return MCP_OK;
+}
+
+int mcp_set_allreduce_stream_ordered(mcp_handle h, int on) {
+    if (!h) return MCP_ERR_INVALID;
+    h->allreduce_stream_ordered = on != 0;
     return MCP_OK;
 }
 

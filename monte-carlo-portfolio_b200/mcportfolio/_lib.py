@@ -112,6 +112,7 @@ SYMBOLS = {
     "mcp_historical_var": (C.c_int, [C.c_void_p, C.POINTER(HistParams), C.c_void_p, C.POINTER(HistOut)]),
     "mcp_asset_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p]),
     "mcp_measure_fma_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
+    "mcp_set_allreduce_stream_ordered": (C.c_int, [C.c_void_p, C.c_int]),
     "mcp_envelope_arrays": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_double, C.c_double,
                                       C.c_int, C.c_void_p, C.c_void_p]),
 }

@@ -72,6 +72,10 @@ class Engine:
     def synchronize(self):
         check(self._h, lib().mcp_synchronize(self._h))
 
+    def set_allreduce_stream_ordered(self, on: bool) -> None:
+        """Promise that all-reduce callbacks only enqueue on the handle's stream (see include/mcp.h)."""
+        check(self._h, lib().mcp_set_allreduce_stream_ordered(self._h, 1 if on else 0))
+
     def measure_fma_peak(self, dtype="float32") -> float:
         code = 2 if dtype == "float32x2" else _dtype(dtype)[0]
         out = C.c_double()

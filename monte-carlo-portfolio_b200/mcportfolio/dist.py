@@ -205,28 +205,62 @@ def wrap_device_buffer(ptr: int, count: int, kind: int, device_index: int):
                            device=torch.device("cuda", device_index))
 
 
-def make_allreduce(device_index: int, group=None):
-    """The callback libmcp's mcp_quantiles calls between radix passes: NCCL sum, in place."""
+def make_allreduce(device_index: int, group=None, stream_ordered: bool = False):
+    """The callback libmcp's mcp_quantiles calls between radix passes: NCCL sum, in place.
+
+    stream_ordered=True: the all-reduce is only ENQUEUED (torch's NCCL work is ordered after, and the current
+    stream then waits on, everything on the current stream -- which is the handle's stream), no host wait: use
+    with Engine.set_allreduce_stream_ordered(True)."""
     import torch
     import torch.distributed as dist
 
     def allreduce(ptr, count, kind):
         t = wrap_device_buffer(ptr, count, kind, device_index)
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-        torch.cuda.current_stream(device_index).synchronize()
+        if not stream_ordered:
+            torch.cuda.current_stream(device_index).synchronize()
 
     return allreduce
 
 
 def simulate_paths_sharded(mean_returns, cov_matrix, weights, n_paths, n_steps=252, *, group=None, **kw):
-    """`simulate_paths` over the whole job: local paths, globally exact VaR / CVaR."""
+    """`simulate_paths` over the whole job: local paths, globally exact VaR / CVaR.  Over NCCL the radix passes,
+    their histogram all-reduces and the digit selection are all stream-ordered (no host round trip per pass)."""
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     first, count = shard_range(n_paths, rank, world)
     eng = api.get_engine(kw.get("device"))
-    return api.simulate_paths(mean_returns, cov_matrix, weights, count, n_steps, first_index=first,
-                              allreduce=make_allreduce(eng.device, group) if world > 1 else None,
-                              n_total=n_paths, **kw)
+    if not (world > 1 and dist.get_backend(group) == "nccl"):
+        return api.simulate_paths(mean_returns, cov_matrix, weights, count, n_steps, first_index=first,
+                                  allreduce=make_allreduce(eng.device, group) if world > 1 else None,
+                                  n_total=n_paths, **kw)
+    # stream-ordered route: libmcp and NCCL must share ONE real stream.  torch's default stream has handle 0, which
+    # mcp_set_stream reads as "use the handle's own stream", so run the whole call on a side stream of ours.
+    import torch
+    side = _side_stream(eng.device)
+    cur = torch.cuda.current_stream(eng.device)
+    side.wait_stream(cur)
+    eng.set_allreduce_stream_ordered(True)
+    try:
+        with torch.cuda.stream(side):
+            out = api.simulate_paths(mean_returns, cov_matrix, weights, count, n_steps, first_index=first,
+                                     allreduce=make_allreduce(eng.device, group, True), n_total=n_paths, **kw)
+    finally:
+        eng.set_allreduce_stream_ordered(False)
+    cur.wait_stream(side)
+    if out.get("terminal_device") is not None:
+        out["terminal_device"].record_stream(cur)
+    return out
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device_index: int):
+    import torch
+    if device_index not in _SIDE_STREAMS:
+        _SIDE_STREAMS[device_index] = torch.cuda.Stream(device_index)
+    return _SIDE_STREAMS[device_index]
 
 
 def emulate_sharded_quantiles(shards, alphas, device_index: int = 0):
