@@ -7,7 +7,8 @@
 // histograms 11 key bits of the values whose higher bits match the target's prefix
 // (warp-aggregated shared-memory atomics via __match_any_sync), the per-rank histograms are
 // summed (NCCL all-reduce supplied by the host as a callback when the vector is sharded), and a
-// host-side scan picks the digit.  3 passes for FP32, 6 for FP64; the vector (40 MB at C4) is
+// scan picks the digit -- on the device (select_advance_kernel: the passes, their all-reduces and the digit selection run
+// back to back on one stream) or, with a synchronous all-reduce callback, on the host.  3 passes for FP32, 6 for FP64; the vector (40 MB at C4) is
 // L2-resident after the first pass.  A last pass accumulates the tail sums in FP64.
 #include <algorithm>
 #include <cmath>
@@ -120,9 +121,9 @@ struct SelDevState {
     int error;                                         // a rank fell outside its prefix's population
 };
 
-__global__ void __launch_bounds__(256) select_advance_kernel(const unsigned long long* __restrict__ hist, int bits, SelDevState* st) {
+__global__ void __launch_bounds__(256) select_advance_kernel(const unsigned long long* __restrict__ hist, int bits, SelDevState* st, int shared_row) {
     const int t = blockIdx.x, nb = 1 << bits, per = (nb + 255) / 256;        // bins per thread (<= 8)
-    const unsigned long long* row = hist + (size_t)t * nb;
+    const unsigned long long* row = hist + (shared_row ? 0 : (size_t)t * nb);   // first pass: every target has the empty prefix
     unsigned long long mine = 0;
     for (int j = 0; j < per; ++j) {
         const int d = threadIdx.x * per + j;
@@ -335,22 +336,23 @@ int mcp_quantiles(mcp_handle h, const void* values, int space, int dtype, uint64
         memset(&unused, 0, sizeof unused);
         for (int done = 0; done < key_bits;) {
             const int bits = std::min(SEL_BITS, key_bits - done), shift = key_bits - done - bits;
-            const size_t cnt = (size_t)nt << bits;
+            const int slots_now = done == 0 ? 1 : nt;                 // pass 0: one histogram serves all targets
+            const size_t cnt = (size_t)slots_now << bits;
             MCP_CUDA(h, cudaMemsetAsync(d_hist, 0, cnt * 8, st));
             if (n) {
                 const size_t smem = sizeof(unsigned int) * cnt;
                 if (dtype == MCP_F64) {
                     if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(select_hist_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    select_hist_kernel<double><<<grid_for(h, n, 4), SEL_BLOCK, smem, st>>>((const double*)v, n, nt, unused, shift, bits, d_hist, d_state->prefix);
+                    select_hist_kernel<double><<<grid_for(h, n, 4), SEL_BLOCK, smem, st>>>((const double*)v, n, slots_now, unused, shift, bits, d_hist, d_state->prefix);
                 } else {
                     if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(select_hist_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    select_hist_kernel<float><<<grid_for(h, n, 4), SEL_BLOCK, smem, st>>>((const float*)v, n, nt, unused, shift, bits, d_hist, d_state->prefix);
+                    select_hist_kernel<float><<<grid_for(h, n, 4), SEL_BLOCK, smem, st>>>((const float*)v, n, slots_now, unused, shift, bits, d_hist, d_state->prefix);
                 }
                 MCP_CUDA(h, cudaGetLastError());
                 h->launches++;
             }
             if (allreduce && allreduce(d_hist, cnt, 0, user) != 0) return mcp_fail(h, MCP_ERR_INVALID, "mcp_quantiles: allreduce callback failed");
-            select_advance_kernel<<<nt, 256, 0, st>>>(d_hist, bits, d_state);
+            select_advance_kernel<<<nt, 256, 0, st>>>(d_hist, bits, d_state, done == 0 ? 1 : 0);
             MCP_CUDA(h, cudaGetLastError());
             h->launches++;
             done += bits;
