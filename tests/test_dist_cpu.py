@@ -39,6 +39,23 @@ def test_merge_records_first_occurrence():
     assert unpack_record(*pack_record(big, 2))["global_index"] == 2**40 + 12345
 
 
+def test_flat_records_carry_int64_indices_bit_for_bit():
+    """The per-step all_gather ships records as ONE float64 vector; the int64 global index is a bit pattern inside it
+    (patterns that read as NaN / denormal / -0.0 as a double must come back unchanged)."""
+    import torch
+    from mcportfolio.dist import _pack_flat, _unpack_flat
+    mk = lambda i: {"key": 1.5, "global_index": i, "index": i, "ret": 0.1, "risk": 0.2, "sharpe": 1.5, "weights": np.array([0.25, 0.75])}
+    for idx in (0, 1, 2**40 + 12345, 2**53 + 1, 2**63 - 1, 0x7FF8000000000001, 0x7FF0000000000000, 0x0000000000000001):
+        flat = _pack_flat(mk(idx), 2)
+        assert flat.dtype == np.float64 and flat.shape == (8,)
+        trip = torch.from_numpy(flat.copy()).clone().numpy()          # what a gather + copy back does: no arithmetic
+        back = _unpack_flat(trip)
+        assert back["global_index"] == idx and back["key"] == 1.5 and np.array_equal(back["weights"], [0.25, 0.75])
+    assert _unpack_flat(_pack_flat(None, 2)) is None
+    acc = np.array([123456789012], dtype=np.int64).view(np.float64)
+    assert int(np.ascontiguousarray(acc).view(np.int64)[0]) == 123456789012
+
+
 def test_merge_envelopes():
     from mcportfolio.dist import merge_envelopes
     a_r, a_i = np.array([1.0, -np.inf, 3.0, 2.0]), np.array([5, -1, 7, 9])
