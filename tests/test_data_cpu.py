@@ -89,3 +89,29 @@ def test_returns_with_overlays_feeds_the_frame():
     assert np.allclose(r["B"].to_numpy(), prices["B"].pct_change().fillna(0).to_numpy())
     r2 = returns_with_overlays(prices, {"B": [("short_asset", 0, 0, 1.0)]})
     assert np.allclose(r2["B"].to_numpy(), -prices["B"].pct_change().fillna(0).to_numpy())
+
+
+@pytest.mark.needs_reference
+def test_option_overlay_against_the_reference_function_randomised():
+    """f4, dev container only: calc_options_series (app.py:182-193) exec'd from the reference on random legs / prices
+    (including zero prices, unknown tags, negative quantities) against the vectorised host mirror."""
+    import pandas as pd
+    import textwrap
+    from oracle import ref_loader
+    from mcportfolio.overlay import KINDS, option_overlay_returns
+    with open(ref_loader.REFERENCE_APP, encoding="utf-8") as fh:
+        lines = fh.readlines()
+    ns = {"np": np, "pd": pd}
+    exec(compile(textwrap.dedent("".join(lines[163:193])), ref_loader.REFERENCE_APP, "exec"), ns)
+    tags = list(KINDS) + ["something else"]
+    rng = np.random.default_rng(42)
+    for trial in range(40):
+        T = int(rng.integers(1, 60))
+        prices = np.round(50 * np.cumprod(1 + 0.05 * rng.standard_normal(T)), 2)
+        if T > 3 and trial % 3 == 0:
+            prices[rng.integers(0, T)] = 0.0
+        legs = [(tags[rng.integers(len(tags))], float(np.round(rng.uniform(20, 90), 1)), float(np.round(rng.uniform(0, 5), 2)),
+                 float(np.round(rng.uniform(-2, 2), 2))) for _ in range(int(rng.integers(0, 5)))]
+        want = ns["calc_options_series"](legs, pd.Series(prices)).to_numpy()
+        got = option_overlay_returns(legs, prices)
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-15), (trial, legs)
