@@ -194,3 +194,27 @@ def test_asset_stats_against_reference_functions(c1, c2):
             got = ref.asset_stats(R[1:, j], spec["risk_free"], spec["ann_factor"])
             for k, v in want.items():
                 assert got[k] == pytest.approx(v, rel=1e-12, abs=1e-15), (tag, j, k)
+
+
+def test_fp32_uniform_fields_are_24_bit_slices_of_the_stream():
+    """float32 streams: field i = bits [24 i, 24 i + 23) of the concatenated Philox blocks (word 0 of block 0 lowest),
+    the spec `philox_fields` in mcp_device.cuh implements with funnel shifts; float64 keeps one word per uniform."""
+    idx = np.array([5, 2**40 + 7, 2**63 + 11], dtype=np.uint64)
+    sub = np.array([0, 3, 99], dtype=np.uint64)
+    for nf in (1, 3, 4, 5, 16, 24, 33, 256):
+        f = philox_np._fields24(idx, sub, nf, philox_np.STREAM_WEIGHTS, 99)
+        n_words = 4 * ((3 * ((nf + 3) // 4) + 3) // 4)
+        w = philox_np._raw_outputs(idx, sub, n_words, philox_np.STREAM_WEIGHTS, 99)
+        assert f.shape == (3, nf) and f.dtype == np.uint32 and f.max() < 2**23
+        for r in range(3):
+            big = 0
+            for j, x in enumerate(w[r]):
+                big |= int(x) << (32 * j)
+            assert [int(v) for v in f[r]] == [(big >> (24 * i)) & 0x7FFFFF for i in range(nf)]
+    # 16 uniforms take 3 blocks, not 4; the exponentials are -log2(1 - field 2^-23)
+    e32 = philox_np.exponentials(idx, 0, 16, 7, "float32")
+    f = philox_np._fields24(idx, np.zeros(3, dtype=np.uint64), 16, philox_np.STREAM_WEIGHTS, 7)
+    assert np.array_equal(e32, -np.log2(1.0 - f.astype(np.float64) * 2.0 ** -23))
+    e64 = philox_np.exponentials(idx, 0, 16, 7, "float64")
+    x = philox_np._raw_outputs(idx, np.zeros(3, dtype=np.uint64), 16, philox_np.STREAM_WEIGHTS, 7)
+    assert np.array_equal(e64, -np.log2(1.0 - x.astype(np.float64) * 2.0 ** -32))
