@@ -5,8 +5,8 @@
 // q_p = sum_j Y'_pj E_pj (app.py:709 restated on the triangle).  E never exists in shared or global
 // memory: it is produced by Philox in the registers of the thread that owns the row, written to
 // TENSOR MEMORY as the MMA's A operand (tcgen05.st), multiplied on the 5th-generation tensor cores
-// (tcgen05.mma, A from TMEM, B = S' from shared memory, FP32 accumulators in TMEM), and the same
-// thread reads its accumulator row back (tcgen05.ld) for the row-dot while E is still in registers.
+// (tcgen05.mma, A from TMEM, B = S' from shared memory, FP32 accumulators in TMEM); an epilogue thread of
+// the same TMEM lane reads the accumulator row AND the staged E back (tcgen05.ld) for the row-dot.
 //
 // FP32 accuracy on TF32/BF16 tensor cores (split operands, all accumulation in FP32):
 //     E  = Ehi + Elo           Ehi = E with the low 13 mantissa bits cleared (a TF32 number), Elo = E - Ehi exact
@@ -17,7 +17,8 @@
 //
 // Roles (544 threads, one CTA per SM, persistent over tiles of 128 portfolios; thread = portfolio row = TMEM lane):
 //   warps 0-11   three generator groups of 128 threads, one A stage each.  Group g produces the CTA's K chunks
-//                n = g (mod 3): 8 Philox calls -> l = lg2(U) = -e -> split -> tcgen05.st into its stage -> a_full[g].
+//                n = g (mod 3): 6 Philox calls (32 uniforms as 24-bit fields) -> l = lg2(U) = -e -> split -> tcgen05.st
+//                into its stage -> a_full[g].
 //                It never waits for the tensor core, only for its stage to have been read back (a_free[g]).
 //   warp 16      TMEM allocation and the MMA issue loop: warp-convergent, one elected thread, descriptors computed on
 //                uniform values before the barrier waits (10 tcgen05.mma per chunk back to back, tcgen05.commit -> d_done).
@@ -27,9 +28,9 @@
 //   warps 12-15  epilogue + finaliser: per chunk, tcgen05.ld the 32 finished accumulator columns and the chunk's
 //                stage (l = hi + lo exactly), release the stage, accumulate q, sum l, l.mu; per tile compute
 //                return / risk / Sharpe (app.py:708-711), track the selections, write the arrays.
-// Measured on B200 (N = 256): 2.5-2.7e9 portfolios/s vs 5.9e8 for the SIMT kernel.  Ablation of the same launch:
-// without the MMAs 3.0e9, without Philox 3.0e9, without both 5.1e9 -- the generator's instruction stream and the
-// stage hand-off latency (3 stages fit beside the 256 accumulator columns) share the rest; the tensor pipe is ~46 % busy.
+// Measured on B200 (N = 256): 3.1e9 portfolios/s vs 5.9e8 for the SIMT kernel; tensor pipe 60 % busy, issue 56 %,
+// generators waiting for a free stage 20 % of the time (3 stages fit beside the 256 accumulator columns).  DESIGN.md
+// section 4 has the measured history (ablation, clock64 trace, what the elect.sync issue path and FFMA2 bought).
 // The Philox counter layout and the 24-bit uniform fields are those of every other FP32 sweep kernel (global index /
 // attempt 0 / block; mcp_device.cuh), so the weights are the same portfolios the SIMT kernels and oracle/philox_np.py produce.
 #include <algorithm>
