@@ -195,6 +195,7 @@ static int run_fma2_peak(mcp_context* h, double* tflops) {
     void* out = nullptr;
     const int blocks = h->prop.multiProcessorCount * 8, threads = 256, iters = 2048;
     MCP_CHECK(mcp_dev_reserve(h, 6, (size_t)blocks * threads * sizeof(float), &out));
+    ++h->const_epoch;
     double best = 0;
     for (int rep = 0; rep < 5; ++rep) {
         MCP_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
@@ -217,6 +218,7 @@ static int run_fma_peak(mcp_context* h, double* tflops) {
     void* out = nullptr;
     const int blocks = h->prop.multiProcessorCount * 8, threads = 256, iters = 2048;
     MCP_CHECK(mcp_dev_reserve(h, 6, (size_t)blocks * threads * sizeof(T), &out));
+    ++h->const_epoch;
     double best = 0;
     for (int rep = 0; rep < 5; ++rep) {
         MCP_CUDA(h, cudaEventRecord(h->ev[0], h->stream));

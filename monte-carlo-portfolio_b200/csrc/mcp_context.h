@@ -25,6 +25,8 @@ struct mcp_context {
     uint64_t launches = 0;
     double last_ms = 0.0;
     bool allreduce_stream_ordered = false;   // mcp_set_allreduce_stream_ordered
+    uint64_t const_epoch = 0;                // bumped by every writer of dev[6] (kernel constants): a cached table is valid only
+                                             // while the epoch it was written under is still current
     // device scratch (grow-only): [0] candidates/records, [1..2] pipeline slot inputs,
     // [3..4] pipeline slot outputs, [5] quantile histograms, [6] kernel constants, [7] replay,
     // [8] envelope bins, [9..10] envelope risk/return scratch per slot, [11] recheck rows,

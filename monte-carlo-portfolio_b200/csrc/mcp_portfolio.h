@@ -49,6 +49,7 @@ struct PfJob {
     unsigned long long* env_bins = nullptr;
     cudaStream_t stream = nullptr;
     int blocks_used = 0;               // out: grid size of the launch
+    uint64_t tc_table_epoch = 0;       // != 0: the tcgen05 sweep's S' / mu table of THIS call sits in slot 6 under that epoch
 };
 
 // Replay of selected portfolios: regenerates (RNG mode) or re-reads (supplied mode, `rows`

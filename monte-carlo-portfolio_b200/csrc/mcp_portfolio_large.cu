@@ -504,6 +504,7 @@ static int large_launch_tiled(mcp_context* h, PfJob& job) {
     }
     float* dev = nullptr;
     MCP_CHECK(mcp_dev_reserve(h, 6, host.size() * sizeof(float), (void**)&dev));
+    ++h->const_epoch;
     MCP_CUDA(h, cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, job.stream));
     MCP_CUDA(h, cudaStreamSynchronize(job.stream));        // `host` is pageable and dies at scope exit
 
@@ -549,6 +550,7 @@ static int large_launch_generic(mcp_context* h, PfJob& job) {
     }
     T* dev = nullptr;
     MCP_CHECK(mcp_dev_reserve(h, 6, host.size() * sizeof(T), (void**)&dev));
+    ++h->const_epoch;
     MCP_CUDA(h, cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, job.stream));
     MCP_CUDA(h, cudaStreamSynchronize(job.stream));
     GenArgs<T> a;

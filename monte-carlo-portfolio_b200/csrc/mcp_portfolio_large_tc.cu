@@ -456,27 +456,30 @@ int pf_large_launch_tc(mcp_context* h, PfJob& job) {
     const int n = job.n, np = std::max(64, (n + TC_KC - 1) / TC_KC * TC_KC), C = np / TC_KC;
     const uint32_t hi_bytes = tc_hi_off(C), lo_bytes = tc_lo_off(C);
     const size_t table_bytes = (size_t)hi_bytes + lo_bytes + (size_t)np * 4;
-    std::vector<unsigned char> host(table_bytes, 0);
-    // S'[k][j], j <= k: Sigma_kk on the diagonal, Sigma_kj + Sigma_jk below it (w' Sigma w = sum_k sum_{j<=k} w_k S'_kj w_j).
-    // Canonical K-major no-swizzle layout per chunk: [K core (4 tf32 / 8 bf16)][N group of 8][8 rows x 16 bytes].
-    for (int k = 0; k < n; ++k) {
-        const int c = k / TC_KC, kk = k % TC_KC, Nc = TC_KC * (c + 1);
-        for (int j = 0; j <= k; ++j) {
-            const double v = j == k ? job.sigma[(size_t)k * n + k] : job.sigma[(size_t)k * n + j] + job.sigma[(size_t)j * n + k];
-            const float shi = tf32_round((float)v);
-            const uint16_t slo = bf16_round((float)(v - (double)shi));
-            const size_t oh = (size_t)tc_hi_off(c) + ((size_t)(kk / 4) * (Nc / 8) + j / 8) * 128 + (j % 8) * 16 + (kk % 4) * 4;
-            const size_t ol = (size_t)hi_bytes + tc_lo_off(c) + ((size_t)(kk / 8) * (Nc / 8) + j / 8) * 128 + (j % 8) * 16 + (kk % 8) * 2;
-            memcpy(&host[oh], &shi, 4);
-            memcpy(&host[ol], &slo, 2);
-        }
-    }
-    float* hmu = reinterpret_cast<float*>(host.data() + hi_bytes + lo_bytes);
-    for (int i = 0; i < n; ++i) hmu[i] = (float)job.mu[i];
     unsigned char* dev = nullptr;
     MCP_CHECK(mcp_dev_reserve(h, 6, table_bytes, (void**)&dev));
-    MCP_CUDA(h, cudaMemcpyAsync(dev, host.data(), table_bytes, cudaMemcpyHostToDevice, job.stream));
-    MCP_CUDA(h, cudaStreamSynchronize(job.stream));        // `host` is pageable and dies at scope exit
+    if (job.tc_table_epoch == 0 || job.tc_table_epoch != h->const_epoch) {          // once per mcp_portfolios call: later chunks and the replays reuse it
+        std::vector<unsigned char> host(table_bytes, 0);
+        // S'[k][j], j <= k: Sigma_kk on the diagonal, Sigma_kj + Sigma_jk below it (w' Sigma w = sum_k sum_{j<=k} w_k S'_kj w_j).
+        // Canonical K-major no-swizzle layout per chunk: [K core (4 tf32 / 8 bf16)][N group of 8][8 rows x 16 bytes].
+        for (int k = 0; k < n; ++k) {
+            const int c = k / TC_KC, kk = k % TC_KC, Nc = TC_KC * (c + 1);
+            for (int j = 0; j <= k; ++j) {
+                const double v = j == k ? job.sigma[(size_t)k * n + k] : job.sigma[(size_t)k * n + j] + job.sigma[(size_t)j * n + k];
+                const float shi = tf32_round((float)v);
+                const uint16_t slo = bf16_round((float)(v - (double)shi));
+                const size_t oh = (size_t)tc_hi_off(c) + ((size_t)(kk / 4) * (Nc / 8) + j / 8) * 128 + (j % 8) * 16 + (kk % 4) * 4;
+                const size_t ol = (size_t)hi_bytes + tc_lo_off(c) + ((size_t)(kk / 8) * (Nc / 8) + j / 8) * 128 + (j % 8) * 16 + (kk % 8) * 2;
+                memcpy(&host[oh], &shi, 4);
+                memcpy(&host[ol], &slo, 2);
+            }
+        }
+        float* hmu = reinterpret_cast<float*>(host.data() + hi_bytes + lo_bytes);
+        for (int i = 0; i < n; ++i) hmu[i] = (float)job.mu[i];
+        MCP_CUDA(h, cudaMemcpyAsync(dev, host.data(), table_bytes, cudaMemcpyHostToDevice, job.stream));
+        MCP_CUDA(h, cudaStreamSynchronize(job.stream));        // `host` is pageable and dies at scope exit; other streams may read next
+        job.tc_table_epoch = ++h->const_epoch;
+    }
 
     TcArgs a;
     a.table = dev;
