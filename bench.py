@@ -390,6 +390,22 @@ def run_ours(args):
         del r
         torch.cuda.empty_cache()
 
+    # ---- the FP64 arithmetic of the same sweep (the parity dtype), against the measured FP64 FMA peak ----
+    fp64 = None
+    if world == 1:
+        P64 = 2_000_000_000
+        for _ in range(2):
+            r64 = mcp.simulate_portfolios(mu, sigma, P64, risk_free=RISK_FREE, seed=SEED, return_arrays=False, dtype="float64", device=local)
+        peak64 = max(eng.measure_fma_peak("float64") for _ in range(3))
+        a64 = P64 * flops_per_portfolio(n) / (r64.kernel_ms * 1e-3) / 1e12
+        fp64 = {"metric": "portfolios/sec (16 assets, FP64)", "value": P64 / (r64.kernel_ms * 1e-3), "unit": "portfolios/s", "dtype": "f64",
+                "roofline": {"bound": "fp64-simt", "kernel": "small_sweep<double,16,K=2> (Philox, 32-bit uniforms, libdevice log2)",
+                             "achieved": a64, "peak": peak64, "unit": "TFLOP/s", "frac": a64 / peak64,
+                             "peak_source": "DFMA-chain microbenchmark (mcp_measure_fma_peak), best of 3",
+                             "algorithmic_flop_per_portfolio": flops_per_portfolio(n), "kernel_ms": r64.kernel_ms,
+                             "note": "the FP64 log2 of the 16 uniforms (software, ~30 DFMA-class instructions each) is most of the "
+                                     "FP64 pipe time; FP64 is the parity dtype, not the throughput path"}}
+
     # ---- e2e with full arrays back to host (C2-shaped: 1e6 portfolios, 76 MB D2H per step) ----
     e2e_arrays = None
     if world == 1:
@@ -488,7 +504,7 @@ def run_ours(args):
         "e2e_arrays": e2e_arrays,
         "gpu_launches": launches_timed,
         "clocks": clk.summary(),
-        "roofline": roofline, "roofline_writeback": wb,
+        "roofline": roofline, "roofline_writeback": wb, "fp64": fp64,
         "cpu_baseline": cpu,
         "paths": {"metric": "path-steps/sec (16 assets, 252 steps)", "value": paths_value, "unit": "path-steps/s",
                   "ms_per_step": p_dev_s / args.steps * 1e3,
