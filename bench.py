@@ -399,12 +399,13 @@ def run_ours(args):
         peak64 = max(eng.measure_fma_peak("float64") for _ in range(3))
         a64 = P64 * flops_per_portfolio(n) / (r64.kernel_ms * 1e-3) / 1e12
         fp64 = {"metric": "portfolios/sec (16 assets, FP64)", "value": P64 / (r64.kernel_ms * 1e-3), "unit": "portfolios/s", "dtype": "f64",
-                "roofline": {"bound": "fp64-simt", "kernel": "small_sweep<double,16,K=2> (Philox, 32-bit uniforms, libdevice log2)",
+                "roofline": {"bound": "fp64-simt", "kernel": "small_sweep<double,16,K=2> (Philox, 32-bit uniforms, table + degree-9 polynomial log2)",
                              "achieved": a64, "peak": peak64, "unit": "TFLOP/s", "frac": a64 / peak64,
                              "peak_source": "DFMA-chain microbenchmark (mcp_measure_fma_peak), best of 3",
                              "algorithmic_flop_per_portfolio": flops_per_portfolio(n), "kernel_ms": r64.kernel_ms,
-                             "note": "the FP64 log2 of the 16 uniforms (software, ~30 DFMA-class instructions each) is most of the "
-                                     "FP64 pipe time; FP64 is the parity dtype, not the throughput path"}}
+                             "note": "the FP64 log2 of the 16 uniforms (software: ~10 DFMA each after the table lookup; libdevice's "
+                                     "log2 made this kernel 2.1x slower) shares the FP64 pipe with the 184 DFMA of the forms; FP64 "
+                                     "is the parity dtype, not the throughput path"}}
 
     # ---- e2e with full arrays back to host (C2-shaped: 1e6 portfolios, 76 MB D2H per step) ----
     e2e_arrays = None
