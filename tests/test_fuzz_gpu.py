@@ -85,3 +85,27 @@ def test_tensor_core_sweep_any_shape(mcp, n, P, seed, first, supplied):
     i = r.max_sharpe["index"]
     assert r.max_sharpe["sharpe"] == float(r.sharpes[i]) or supplied       # supplied FP64 rows: the pick is decided in FP64
     assert np.isclose(r.sharpes[i], r.sharpes.max(), rtol=1e-5)
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(T=st.integers(2, 520), n=st.integers(1, 24), P=st.integers(1, 300), alpha=st.sampled_from([0.9, 0.95, 0.99, 0.5]),
+       decimals=st.sampled_from([2, 3, 8]), dtype=st.sampled_from(["float32", "float64"]), seed=st.integers(0, 10**6))
+def test_historical_var_cvar_any_shape(mcp, T, n, P, alpha, decimals, dtype, seed):
+    """Per-portfolio historical VaR / CVaR (app.py:710-713): fast FP32 kernel, plain kernel (FP64, deep ranks, short series)
+    and ties (rounded returns) against the oracle's np.percentile restatement."""
+    rng = np.random.default_rng(seed)
+    R = np.round(rng.standard_normal((T, n)) * 0.03, decimals)
+    W = rng.dirichlet(np.ones(n), size=P)
+    out = mcp.historical_var_cvar(R, W, alpha, dtype=dtype)
+    v, c = ref.historical_var_cvar(R, W, alpha)
+    if dtype == "float64":
+        assert np.allclose(out["var"], v, rtol=1e-10, atol=1e-15) and np.allclose(out["cvar"], c, rtol=1e-10, atol=1e-15)
+    else:
+        # FP32 series: an order statistic can swap with a neighbour that differs by FP32 rounding only -> compare values
+        scale = np.abs(R).max() + 1e-12
+        assert np.allclose(out["var"], v, rtol=1e-4, atol=2e-6 * scale + 1e-9)
+        # CVaR = mean of the tail INCLUDING the VaR element(s): with tied values an FP32 rounding can move a whole tie group
+        # in or out of the tail, so the FP32 check needs room for one element of the tail mean
+        k = max(1, int((T - 1) * (1 - alpha)) + 1)
+        assert np.all(np.abs(out["cvar"] - c) <= 1e-4 * np.abs(c) + (np.abs(v - c) + 4e-6 * scale) * (T if decimals < 8 else 1) / k + 1e-9)
+    assert out["best_var"]["index"] == int(np.argmax(out["var"])) and out["best_cvar"]["index"] == int(np.argmax(out["cvar"]))
