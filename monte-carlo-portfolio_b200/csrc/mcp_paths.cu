@@ -68,9 +68,11 @@ __device__ __forceinline__ void draw_normals(const PathArgs<T, NP>& a, uint32_t 
             for (int k = 0; k < 2; ++k) {
                 const T u1 = Math<T>::unit_open0(x[2 * k]);
                 const T r = Math<T>::sqrt(Math<T>::lg2(u1) * PathConst<T>::neg2ln2());
-                const T th = PathConst<T>::centred(x[2 * k + 1]) * PathConst<T>::pi();
-                z[4 * b + 2 * k] = r * Math<T>::cosf_(th);
-                z[4 * b + 2 * k + 1] = r * Math<T>::sinf_(th);
+                // FP64: sincospi on the angle in units of pi (no Payne-Hanek reduction, one call for both values)
+                double sn, cs;
+                ::sincospi((double)PathConst<T>::centred(x[2 * k + 1]), &sn, &cs);
+                z[4 * b + 2 * k] = r * (T)cs;
+                z[4 * b + 2 * k + 1] = r * (T)sn;
             }
         }
     }
