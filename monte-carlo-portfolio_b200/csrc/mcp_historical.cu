@@ -251,12 +251,30 @@ __global__ void __launch_bounds__(HV_BLOCK) hist_var_fast(const HistArgs<float> 
     uint64_t idx_v = MCP_NO_INDEX, idx_c = MCP_NO_INDEX;
     const uint64_t groups = (a.P + HF_PPW - 1) / HF_PPW;
     const uint64_t warps_total = (uint64_t)gridDim.x * HV_WARPS;
-    for (uint64_t gq = (uint64_t)blockIdx.x * HV_WARPS + warp; gq < groups; gq += warps_total) {
+    // the four weight rows of a group are 4 n contiguous floats; with 4 n <= 64 (n <= 16) a lane holds the NEXT group's
+    // values in two registers while the current group is being processed (the global-load latency sat in front of the STS)
+    const bool prefetch = HF_PPW * a.n <= 64;
+    float nxt0 = 0.f, nxt1 = 0.f;
+    auto fetch = [&](uint64_t g, int j) -> float {
+        const uint64_t q0 = g * HF_PPW;
+        return (g < groups && j < HF_PPW * a.n && q0 + (uint64_t)(j / a.n) < a.P) ? __ldg(a.w_in + q0 * (uint64_t)a.n + (uint64_t)j) : 0.f;
+    };
+    const uint64_t g_first = (uint64_t)blockIdx.x * HV_WARPS + warp;
+    if (prefetch) { nxt0 = fetch(g_first, lane); nxt1 = fetch(g_first, lane + 32); }
+    for (uint64_t gq = g_first; gq < groups; gq += warps_total) {
         const uint64_t p0 = gq * HF_PPW;
         __syncwarp();
-        for (int j = lane; j < HF_PPW * a.n; j += 32) {               // rows p0 .. p0+3 are contiguous: coalesced
-            const int pp = j / a.n, i = j - pp * a.n;
-            myW[i * HF_PPW + pp] = (p0 + (uint64_t)pp < a.P) ? a.w_in[p0 * (uint64_t)a.n + (uint64_t)j] : 0.f;
+        if (prefetch) {
+            const int j0 = lane, j1 = lane + 32;
+            if (j0 < HF_PPW * a.n) myW[(j0 % a.n) * HF_PPW + j0 / a.n] = nxt0;
+            if (j1 < HF_PPW * a.n) myW[(j1 % a.n) * HF_PPW + j1 / a.n] = nxt1;
+            nxt0 = fetch(gq + warps_total, j0);
+            nxt1 = fetch(gq + warps_total, j1);
+        } else {
+            for (int j = lane; j < HF_PPW * a.n; j += 32) {               // rows p0 .. p0+3 are contiguous: coalesced
+                const int pp = j / a.n, i = j - pp * a.n;
+                myW[i * HF_PPW + pp] = (p0 + (uint64_t)pp < a.P) ? a.w_in[p0 * (uint64_t)a.n + (uint64_t)j] : 0.f;
+            }
         }
         __syncwarp();
         // ---- series[t] = sum_i R[t, i] w_i: this lane's periods, four portfolios (a: 0,1  b: 2,3) ----
