@@ -170,25 +170,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) large_sweep_tc(const TcArgs a) 
     unsigned int* sAcc = reinterpret_cast<unsigned int*>(sCand + 4);    // [4]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    {   // S' images + mu: one 16-byte copy loop (the table is laid out exactly like this shared-memory block)
-        const uint32_t bytes = hi_bytes + lo_bytes + (uint32_t)a.np * 4u;
-        const uint4* src = reinterpret_cast<const uint4*>(a.table);
-        uint4* dst = reinterpret_cast<uint4*>(smem);
-        for (uint32_t i = tid; i < bytes / 16; i += TC_THREADS) dst[i] = src[i];
-    }
+    // S' images + mu arrive by TMA bulk copies (cp.async.bulk: global -> shared through the async proxy, completion counted
+    // in bytes on an mbarrier) issued by one thread while the other warps set up barriers and tensor memory; the table in
+    // global memory is laid out exactly like this shared-memory block.
+    uint64_t* table_bar = bars + 11;
     if (tid == 0) {
         for (int g = 0; g < TC_GROUPS; ++g) { mbar_init(&a_full[g], TC_ROWS); mbar_init(&d_done[g], 1); mbar_init(&a_free[g], TC_ROWS); }
         mbar_init(drained, TC_ROWS);
+        mbar_init(table_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t bytes = hi_bytes + lo_bytes + (uint32_t)a.np * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(table_bar)), "r"(bytes) : "memory");
+        for (uint32_t off = 0; off < bytes; off += 32768u) {
+            const uint32_t part = bytes - off < 32768u ? bytes - off : 32768u;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(smem + off)), "l"(a.table + off), "r"(part), "r"(smem_u32(table_bar)) : "memory");
+        }
     }
     if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes of S' -> visible to the MMA (async proxy)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    mbar_wait(table_bar, 0u);                                          // every consumer of S' / mu waits for the bytes to land
     const uint32_t tmem = *tmem_slot;
 
     const uint64_t n_tiles = (a.P + TC_ROWS - 1) / TC_ROWS;
