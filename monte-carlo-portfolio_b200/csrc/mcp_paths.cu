@@ -152,13 +152,11 @@ __global__ void __launch_bounds__(PATH_BLOCK) path_kernel_packed(const __grid_co
                 const float2 f1 = make_float2(__uint_as_float((fa[2 * k] & 0x007fffffu) | 0x3f800000u),
                                               __uint_as_float((fb[2 * k] & 0x007fffffu) | 0x3f800000u));
                 const float2 u1 = fma2(f1, bcast2(-1.0f), bcast2(2.0f));                      // (0, 1]
-                const float2 t = fma2(make_float2(Math<float>::lg2(u1.x), Math<float>::lg2(u1.y)),
-                                      bcast2(PathConst<float>::neg2ln2()), bcast2(0.0f));     // -2 ln U1
-                const float2 r = make_float2(Math<float>::sqrt(t.x), Math<float>::sqrt(t.y));
+                // r / sqrt(2 ln 2) = sqrt(-lg2 U1): the constant rides in lp (host), the negation in the MUFU operand
+                const float2 r = make_float2(Math<float>::sqrt(-Math<float>::lg2(u1.x)), Math<float>::sqrt(-Math<float>::lg2(u1.y)));
                 const float2 f2 = make_float2(__uint_as_float((fa[2 * k + 1] & 0x007fffffu) | 0x40000000u),
                                               __uint_as_float((fb[2 * k + 1] & 0x007fffffu) | 0x40000000u));
-                const float2 c = fma2(f2, bcast2(1.0f), bcast2(-3.0f));                       // 2f - 1 in [-1, 1)
-                const float2 th = fma2(c, bcast2(kPi), bcast2(0.0f));
+                const float2 th = fma2(f2, bcast2(kPi), bcast2(-3.0f * kPi));                 // pi (2f - 1) in [-pi, pi), one rounding
                 const float2 cs = make_float2(Math<float>::cosf_(th.x), Math<float>::cosf_(th.y));
                 const float2 sn = make_float2(Math<float>::sinf_(th.x), Math<float>::sinf_(th.y));
                 z[2 * k] = fma2(r, cs, bcast2(0.0f));
@@ -220,7 +218,14 @@ static int path_launch_t(mcp_context* h, const mcp_path_params* p, const double*
     void (*kern)(PathArgs<T, NP>) = z_dev ? path_kernel<T, NP, 1> : path_kernel<T, NP, 0>;
     int per_thread = 1;
     if constexpr (sizeof(T) == 4 && NP <= 16) {
-        if (!z_dev) { kern = path_kernel_packed<NP>; per_thread = 2; }
+        if (!z_dev) {
+            // the packed kernel's normals come out divided by sqrt(2 ln 2) (its Box-Muller radius is sqrt(-lg2 U1))
+            kern = path_kernel_packed<NP>;
+            per_thread = 2;
+            const double c = std::sqrt(2.0 * std::log(2.0));
+            for (int i = 0; i < NP; ++i)
+                for (int j = 0; j <= i; ++j) a.lp[i * (i + 1) / 2 + j] = (i < n && j < n) ? (T)(L[(size_t)i * n + j] * sdt * c) : (T)0;
+        }
     }
     int per_sm = 0;
     MCP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PATH_BLOCK, 0));
