@@ -379,16 +379,19 @@ __global__ void __launch_bounds__(PF_BLOCK) small_sweep(const __grid_constant__ 
 // of portfolio B).  It works on l = lg2(U) = -e so that no negation is ever materialised:
 // q = l' S l (= e' S e), s = sum(-mask_i l_i), r = sum(-mu_i l_i).  Every value is bit-identical
 // to the scalar path (IEEE fma per lane, same operation order), so small_replay reproduces it.
-template <int NP, int K>
+// OUT = false is the instance the 10^10-portfolio sweep runs: nothing is written per portfolio, so the
+// per-portfolio pointer tests, staging addresses and stores are not even compiled in (the kernel is
+// issue-bound: they were about 1/8 of its instruction stream).
+template <int NP, int K, bool OUT>
 __global__ void __launch_bounds__(PF_BLOCK) small_sweep_packed(const __grid_constant__ SmallArgs<float, NP> a) {
     static_assert(K % 2 == 0, "packed sweep pairs portfolios");
     constexpr int KP = K / 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool vec = (a.n & 3) == 0 && (reinterpret_cast<uintptr_t>(a.w_out) & 15) == 0;
+    const bool vec = OUT && (a.n & 3) == 0 && (reinterpret_cast<uintptr_t>(a.w_out) & 15) == 0;
     const int stride = vec ? a.n + 4 : (a.n | 1);
     float* stage = reinterpret_cast<float*>(smem_raw) + (size_t)warp * 32 * stride;
-    const int q32 = 32 / a.n, m32 = 32 % a.n;
+    const int q32 = OUT ? 32 / a.n : 0, m32 = OUT ? 32 % a.n : 0;
     const uint64_t n_sub = (a.P + PF_BLOCK - 1) / PF_BLOCK;
     const uint64_t n_tiles = (n_sub + K - 1) / K;
     constexpr uint32_t NONE = 0xffffffffu;
@@ -455,12 +458,14 @@ __global__ void __launch_bounds__(PF_BLOCK) small_sweep_packed(const __grid_cons
                 if (d > best_d) { best_d = d; sub_d = sub; }
                 rmin = fminf(rmin, risk);
                 rmax = fmaxf(rmax, risk);
-                if (a.ret_out != nullptr) a.ret_out[local] = ret;
-                if (a.risk_out != nullptr) a.risk_out[local] = risk;
-                if (a.sharpe_out != nullptr) a.sharpe_out[local] = sharpe;
-                if (a.acc_out != nullptr) a.acc_out[local] = 1;
+                if constexpr (OUT) {
+                    if (a.ret_out != nullptr) a.ret_out[local] = ret;
+                    if (a.risk_out != nullptr) a.risk_out[local] = risk;
+                    if (a.sharpe_out != nullptr) a.sharpe_out[local] = sharpe;
+                    if (a.acc_out != nullptr) a.acc_out[local] = 1;
+                }
             }
-            if (a.w_out != nullptr) {
+            if (OUT && a.w_out != nullptr) {
                 // w_i = e_i / s = l_i * (-1 / s): stage this thread's row, then the warp streams the tile out
                 const float ninv = -Math<float>::rcp(s);
                 const uint64_t warp_row0 = local - lane;
@@ -631,7 +636,8 @@ static int small_launch_k(mcp_context* h, PfJob& job, const SmallArgs<T, NP>& a)
 
 template <int NP, int K>
 static int small_launch_packed(mcp_context* h, PfJob& job, const SmallArgs<float, NP>& a) {
-    auto kern = small_sweep_packed<NP, K>;
+    const bool any_out = job.w_out || job.ret_out || job.risk_out || job.sharpe_out || job.acc_out;
+    auto kern = any_out ? small_sweep_packed<NP, K, true> : small_sweep_packed<NP, K, false>;
     const size_t smem = job.w_out ? (size_t)(PF_BLOCK / 32) * 32 * (job.n + 4) * sizeof(float) : 0;
     if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
