@@ -441,6 +441,33 @@ __global__ void __launch_bounds__(PF_BLOCK) small_sweep_packed(const __grid_cons
                 r2[kp] = fma2(nmu, l2[kp][i], r2[kp]);
             }
         }
+        if constexpr (!OUT) {
+            // selection only; whole tiles (all but the last of the range) skip the per-portfolio range test
+            auto pick = [&](int k, bool active) {
+                const float q = (k & 1) ? q2[k / 2].y : q2[k / 2].x;
+                const float r = (k & 1) ? r2[k / 2].y : r2[k / 2].x;
+                const float s = (k & 1) ? s2[k / 2].y : s2[k / 2].x;
+                float ret, risk, sharpe;
+                metrics_from<float>(q, r, s, a.rf, false, ret, risk, sharpe);
+                if (active) {
+                    const uint32_t sub = (uint32_t)(tile * K + k);
+                    ++n_acc;
+                    if (sharpe > best_s) { best_s = sharpe; sub_s = sub; }
+                    const float d = -fabsf(risk - a.target);
+                    if (d > best_d) { best_d = d; sub_d = sub; }
+                    rmin = fminf(rmin, risk);
+                    rmax = fmaxf(rmax, risk);
+                }
+            };
+            if ((tile + 1) * (uint64_t)(K * PF_BLOCK) <= a.P) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) pick(k, true);
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; ++k) pick(k, local0 + (uint64_t)k * PF_BLOCK < a.P);
+            }
+            continue;
+        }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const uint64_t local = local0 + (uint64_t)k * PF_BLOCK;
