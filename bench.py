@@ -61,14 +61,17 @@ def flops_per_portfolio(n):       # symmetric-minimal algorithmi
 
 def tc_tensor_flops(n):
     """Executed tensor-core flop per portfolio of large_sweep_tc: K chunks of 32 assets, chunk c multiplies
-    against the 32(c+1) triangle columns, three MMA sets per chunk (TF32 hi, TF32 lo, BF16 correction)."""
+    against the 32(c+1) triangle columns, three MMA sets per chunk (FP16 split, Philox rows: h1 S1, h2 S1, h1 S2;
+    TF32 split, supplied weights: TF32 hi, TF32 lo, BF16 correction)."""
     C = max(2, -(-n // 32))
     return sum(2 * 32 * 32 * (c + 1) * 3 for c in range(C))
 
 
-def tc_bf16_equiv_flops(n):       # TF32 MMAs run at half the BF16 rate: count them twice
+def tc_bf16_equiv_flops(n, split="fp16"):
+    """The same in BF16-rate flop: FP16 MMAs run at the BF16 rate; TF32 MMAs at half of it (counted twice)."""
     C = max(2, -(-n // 32))
-    return sum(2 * 32 * 32 * (c + 1) * (2 + 2 + 1) for c in range(C))
+    per = 3 if split == "fp16" else (2 + 2 + 1)
+    return sum(2 * 32 * 32 * (c + 1) * per for c in range(C))
 
 
 def flops_per_path_step(n):
@@ -318,7 +321,7 @@ def run_ours(args):
                             "d2h_bytes_per_step": (2 * (5 + N_LARGE) * 8 + 56) + 16 * N_BINS},
                     "filled_bins": int((env["best_index"] >= 0).sum()),
                     "target_risk": {"index": e_res.target_risk["global_index"], "risk": e_res.target_risk["risk"]},
-                    "roofline": {"bound": "tensor", "kernel": "large_sweep_tc (tcgen05: TF32 hi/lo + BF16 correction, A from TMEM)",
+                    "roofline": {"bound": "tensor", "kernel": "large_sweep_tc<F16> (tcgen05: FP16 split h1 S1 + h2 S1 + h1 S2, FP32 accumulate, A from TMEM)",
                                  "unit": "TFLOP/s",
                                  "achieved": my_pl * tc_bf16_equiv_flops(N_LARGE) / (e_dev_s / e_steps) / 1e12,
                                  "executed_tensor_flop_per_portfolio": tc_tensor_flops(N_LARGE),
@@ -327,10 +330,11 @@ def run_ours(args):
                                  "fp32_equivalent_tflops": my_pl * flops_per_portfolio(N_LARGE) / (e_dev_s / e_steps) / 1e12,
                                  "sweeps_per_step": 1, "step_ms": e_dev_s / e_steps * 1e3,
                                  "metric_bytes_kept_in_hbm": 8 * my_pl,
-                                 "note": "achieved = portfolios x executed tensor flop (TF32 MMAs counted twice: half the "
-                                         "BF16 rate) / step time, against the measured dense BF16 burst peak; the binning pass over the kept "
-                                         "(risk, return) arrays is inside the step.  fp32_equivalent_tflops = the same rate in algorithmic "
-                                         "FP32 flop (N^2+5N+6 per portfolio), comparable with the SIMT kernels' rooflines"}}
+                                 "note": "achieved = portfolios x executed tensor flop (three FP16 MMA sets per chunk, BF16 rate) / step time, "
+                                         "against the measured dense BF16 burst peak; the binning pass over the kept (risk, return) arrays is "
+                                         "inside the step.  The kernel is bound by the SIMT issue of its generator warps (Philox + lg2 + FP16 "
+                                         "split: ncu issue 59 %, ALU pipe 49 %), not by the tensor pipe; fp32_equivalent_tflops = the same rate in "
+                                         "algorithmic FP32 flop (N^2+5N+6 per portfolio), comparable with the SIMT kernels' rooflines"}}
 
     if rank != 0:
         if world > 1:

@@ -50,6 +50,7 @@ struct PfJob {
     cudaStream_t stream = nullptr;
     int blocks_used = 0;               // out: grid size of the launch
     uint64_t tc_table_epoch = 0;       // != 0: the tcgen05 sweep's S' / mu table of THIS call sits in slot 6 under that epoch
+    int tc_table_f16 = -1;             // operand split the table in slot 6 was built for (1: FP16 images, 0: TF32 + BF16)
 };
 
 // Replay of selected portfolios: regenerates (RNG mode) or re-reads (supplied mode, `rows`

@@ -8,29 +8,36 @@
 // (tcgen05.mma, A from TMEM, B = S' from shared memory, FP32 accumulators in TMEM); an epilogue thread of
 // the same TMEM lane reads the accumulator row AND the staged E back (tcgen05.ld) for the row-dot.
 //
-// FP32 accuracy on TF32/BF16 tensor cores (split operands, all accumulation in FP32):
+// FP32-class accuracy from narrow tensor-core operands (split operands, all accumulation in FP32).  Two splits share the kernel:
+//
+//   FP16 split (template F16 = true; Philox rows, where |l| = |lg2 U| <= 24 is inside FP16's range):
+//     E  = h1 + h2             h1 = FP16(E), h2 = FP16(E - h1): 22 significant bits
+//     S' = (S1 + S2) 2^-e      S1 = FP16(S' 2^e), S2 = FP16(S' 2^e - S1), 2^e puts the largest entry in [2^13, 2^14)
+//     Y' = h1 S1 + h2 S1 + h1 S2      three FP16 MMA sets at the full 16-bit rate; q is scaled back by 2^-e
+//     stage = h1 (16 columns) + h2 (16) + E itself in FP32 (32, for the epilogue's row-dot) = 64 columns -> 4 stages, 4 generator groups
+//     S1 + S2 = 2 x 72 KB of shared memory
+//   TF32 split (F16 = false; supplied weights, which may be any FP32 number):
 //     E  = Ehi + Elo           Ehi = E with the low 13 mantissa bits cleared (a TF32 number), Elo = E - Ehi exact
 //     S' = Shi + Slo           Shi = TF32 round-to-nearest of S', Slo = BF16(S' - Shi)
 //     Y' = Ehi Shi (tf32) + Elo Shi (tf32) + bf16(E) Slo (bf16)       relative error per product ~ 2^-19
-// S' does not fit shared memory as two FP32 copies; Shi (144 KB) + Slo in BF16 (72 KB) does, because the
-// triangle is stored in 32-row K chunks: chunk c holds rows k in [32c, 32c+32) and only columns j < 32(c+1).
+//     stage = 80 columns -> 3 stages / groups; Shi (144 KB) + Slo in BF16 (72 KB)
+// In both, S' is stored as a triangle in 32-row K chunks: chunk c holds rows k in [32c, 32c+32) and only columns j < 32(c+1).
 //
-// Roles (544 threads, one CTA per SM, persistent over tiles of 128 portfolios; thread = portfolio row = TMEM lane):
-//   warps 0-11   three generator groups of 128 threads, one A stage each.  Group g produces the CTA's K chunks
-//                n = g (mod 3): 6 Philox calls (32 uniforms as 24-bit fields) -> l = lg2(U) = -e -> split -> tcgen05.st
-//                into its stage -> a_full[g].
-//                It never waits for the tensor core, only for its stage to have been read back (a_free[g]).
-//   warp 16      TMEM allocation and the MMA issue loop: warp-convergent, one elected thread, descriptors computed on
-//                uniform values before the barrier waits (10 tcgen05.mma per chunk back to back, tcgen05.commit -> d_done).
-//                Chunks run from the widest (c = C-1, all columns, overwrites the accumulator) to the narrowest,
-//                so column block c is final as soon as chunk c's MMAs complete and the epilogue of a tile
-//                overlaps its remaining MMAs.
-//   warps 12-15  epilogue + finaliser: per chunk, tcgen05.ld the 32 finished accumulator columns and the chunk's
-//                stage (l = hi + lo exactly), release the stage, accumulate q, sum l, l.mu; per tile compute
-//                return / risk / Sharpe (app.py:708-711), track the selections, write the arrays.
-// Measured on B200 (N = 256): 3.1e9 portfolios/s vs 5.9e8 for the SIMT kernel; tensor pipe 60 % busy, issue 56 %,
-// generators waiting for a free stage 20 % of the time (3 stages fit beside the 256 accumulator columns).  DESIGN.md
-// section 4 has the measured history (ablation, clock64 trace, what the elect.sync issue path and FFMA2 bought).
+// Roles (one CTA per SM, persistent over tiles of 128 portfolios; thread = portfolio row = TMEM lane; G = 4 (FP16) or 3 (TF32) groups):
+//   warps 0..4G-1   generator groups of 128 threads, one A stage each.  Group g produces the CTA's K chunks n = g (mod G):
+//                   6 Philox calls (32 uniforms as 24-bit fields) -> l = lg2(U) = -e -> split -> tcgen05.st into its stage -> a_full[g].
+//                   It never waits for the tensor core, only for its stage to have been read back (a_free[g]).
+//   warp 4G+4       TMEM allocation and the MMA issue loop: warp-convergent, one elected thread; FP16: the chunk's descriptor words
+//                   come from a table in shared memory and the six tcgen05.mma + tcgen05.commit are ONE asm block under one elect.
+//                   Chunks run from the widest (c = C-1, all columns, overwrites the accumulator) to the narrowest,
+//                   so column block c is final as soon as chunk c's MMAs complete and the epilogue of a tile
+//                   overlaps its remaining MMAs.
+//   warps 4G..4G+3  epilogue + finaliser: per chunk, tcgen05.ld the 32 finished accumulator columns and the chunk's
+//                   stage (FP16: E itself; TF32: l = hi + lo exactly), release the stage, accumulate q, sum l, l.mu; per tile compute
+//                   return / risk / Sharpe (app.py:708-711), track the selections, write the arrays.
+// Measured on B200 (N = 256, FP16 split): 4.2e9 portfolios/s in a 50 ms launch, 3.7e9 in the 10^9-portfolio envelope step (TF32 split:
+// 3.6 / 3.1e9; SIMT kernel 5.9e8).  The kernel is bound by the SIMT issue of the generator warps (ncu: issue 59 %, ALU pipe 49 %,
+// tensor pipe 39 %): what moved it were instruction counts (DESIGN.md section 4 has the history and the ablations).
 // The Philox counter layout and the 24-bit uniform fields are those of every other FP32 sweep kernel (global index /
 // attempt 0 / block; mcp_device.cuh), so the weights are the same portfolios the SIMT kernels and oracle/philox_np.py produce.
 #include <algorithm>
@@ -39,6 +46,7 @@
 #include <cstring>
 #include <vector>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "mcp_device.cuh"
 #include "mcp_portfolio.h"
@@ -47,13 +55,19 @@ namespace mcp {
 
 constexpr int TC_ROWS = 128;                 // portfolios per tile = TMEM lanes
 constexpr int TC_KC = 32;                    // K (assets) per chunk
-constexpr int TC_GROUPS = 3;                 // row groups = A stages
-constexpr int TC_EPI_WARP0 = 4 * TC_GROUPS;   // four epilogue warps (one per TMEM lane quadrant)
-constexpr int TC_MMA_WARP = 4 * TC_GROUPS + 4;
-constexpr int TC_THREADS = (4 * TC_GROUPS + 5) * 32;
 constexpr int TC_MAX_N = 256;
 constexpr uint32_t TC_COL_A = 256;           // first TMEM column of the A stages (accumulator = columns 0..255)
-constexpr uint32_t TC_STAGE_COLS = 80;       // hi 32 + lo 32 + bf16 16
+constexpr int TC_MAX_GROUPS = 4;
+// Two operand splits share the kernel (template parameter F16):
+//   TF32 split (any FP32 input, so supplied weights use it): stage = hi 32 + lo 32 + bf16 16 = 80 columns, 3 stages / generator groups
+//   FP16 split (Philox rows: |lg2 U| <= 24 fits FP16):        stage = h1 16 + h2 16 + l 32 = 64 columns, 4 stages / generator groups
+template <bool F16> struct TcCfg {
+    static constexpr int GROUPS = F16 ? 4 : 3;                      // row groups = A stages
+    static constexpr uint32_t STAGE_COLS = F16 ? 64 : 80;
+    static constexpr int EPI_WARP0 = 4 * GROUPS;                    // four epilogue warps (one per TMEM lane quadrant)
+    static constexpr int MMA_WARP = 4 * GROUPS + 4;
+    static constexpr int THREADS = (4 * GROUPS + 5) * 32;
+};
 
 struct TcArgs {
     const unsigned char* table;              // global: Shi image, Slo image (canonical UMMA layout), mu[np]
@@ -70,6 +84,7 @@ struct TcArgs {
     int n, np;
     uint32_t k0, k1;
     float rf, target;
+    float qscale;                            // FP16 split: S' is stored times a power of two, q comes back times that; this undoes it
 };
 
 __host__ __device__ inline uint32_t tc_hi_off(int c) { return 2048u * (uint32_t)(c * (c + 1)); }     // bytes before chunk c
@@ -109,6 +124,30 @@ __device__ __forceinline__ void mma_tf32_ts_elect(uint32_t d, uint32_t a, uint64
 __device__ __forceinline__ void mma_bf16_ts_elect(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// One chunk of the FP16 split under a single elect: h1 S1 + h2 S1 + h1 S2 for both K = 16 halves, then the commit.  dlo* are the low
+// words of the four shared-memory descriptors (start address and LBO), dhi their common high word (SBO, version).
+__device__ __forceinline__ void mma6_f16_commit_elect(uint32_t d, uint32_t a_h1, uint32_t a_h2, uint32_t dlo10, uint32_t dlo11, uint32_t dlo20,
+                                                      uint32_t dlo21, uint32_t dhi, uint32_t idesc, uint32_t acc, uint32_t bar) {
+    asm volatile("{\n\t.reg .pred p, q, t;\n\t.reg .b64 e10, e11, e20, e21;\n\t.reg .b32 b1, b2;\n\t"
+                 "elect.sync _|q, 0xffffffff;\n\t"
+                 "setp.ne.b32 p, %9, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"
+                 "mov.b64 e10, {%3, %7};\n\tmov.b64 e11, {%4, %7};\n\tmov.b64 e20, {%5, %7};\n\tmov.b64 e21, {%6, %7};\n\t"
+                 "add.u32 b1, %1, 8;\n\tadd.u32 b2, %2, 8;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], e10, %8, p;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], e10, %8, t;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], e20, %8, t;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [b1], e11, %8, t;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [b2], e11, %8, t;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [b1], e21, %8, t;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n\t}"
+                 ::"r"(d), "r"(a_h1), "r"(a_h2), "r"(dlo10), "r"(dlo11), "r"(dlo20), "r"(dlo21), "r"(dhi), "r"(idesc), "r"(acc), "r"(bar) : "memory");
+}
+// (x & 0x007fffff) | expo as one LOP3 (immediate mask, exponent bits from a register)
+__device__ __forceinline__ uint32_t tc_mant_or(uint32_t x, uint32_t expo) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, 0x007fffff, %2, 0xEA;" : "=r"(d) : "r"(x), "r"(expo));
+    return d;
 }
 __device__ __forceinline__ void tc_commit_elect(uint64_t* b) {
     asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
@@ -153,27 +192,32 @@ __device__ __forceinline__ uint64_t tc_sdesc(uint32_t saddr, uint32_t lbo, uint3
     return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) | ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) large_sweep_tc(const TcArgs a) {
+template <bool F16>
+__global__ void __launch_bounds__(TcCfg<F16>::THREADS, 1) large_sweep_tc(const TcArgs a) {
+    constexpr int TC_GROUPS = TcCfg<F16>::GROUPS, TC_EPI_WARP0 = TcCfg<F16>::EPI_WARP0, TC_MMA_WARP = TcCfg<F16>::MMA_WARP;
+    constexpr uint32_t TC_STAGE_COLS = TcCfg<F16>::STAGE_COLS;
     extern __shared__ __align__(128) unsigned char smem[];
     const int C = a.np / TC_KC;                                         // K chunks per tile (2..8)
-    const uint32_t hi_bytes = tc_hi_off(C), lo_bytes = tc_lo_off(C);
+    // TF32 split: Shi image (32-bit) | Slo image (16-bit);  FP16 split: S1 image | S2 image (both 16-bit)
+    const uint32_t hi_bytes = F16 ? tc_lo_off(C) : tc_hi_off(C), lo_bytes = tc_lo_off(C);
     unsigned char* sHi = smem;
     unsigned char* sLo = smem + hi_bytes;
     float* sMu = reinterpret_cast<float*>(sLo + lo_bytes);                                       // [np]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sMu + a.np);
-    uint64_t* a_full = bars;                       // [3]  128 arrivals: the stage's A operand is in TMEM
-    uint64_t* d_done = bars + 3;                   // [3]  tcgen05.commit: the stage's MMAs are complete
-    uint64_t* a_free = bars + 6;                   // [3]  128 arrivals: the epilogue has read the stage back
-    uint64_t* drained = bars + 9;                  // [1]  128 arrivals: the tile's last accumulator columns were read
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-    PfCand* sCand = reinterpret_cast<PfCand*>(bars + 12);               // [4] per epilogue warp
+    uint64_t* a_full = bars;                           // [G]  128 arrivals: the stage's A operand is in TMEM
+    uint64_t* d_done = bars + TC_MAX_GROUPS;           // [G]  tcgen05.commit: the stage's MMAs are complete
+    uint64_t* a_free = bars + 2 * TC_MAX_GROUPS;       // [G]  128 arrivals: the epilogue has read the stage back
+    uint64_t* drained = bars + 3 * TC_MAX_GROUPS;      // [1]  128 arrivals: the tile's last accumulator columns were read
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_MAX_GROUPS + 1);
+    PfCand* sCand = reinterpret_cast<PfCand*>(bars + 3 * TC_MAX_GROUPS + 3);               // [4] per epilogue warp
     unsigned int* sAcc = reinterpret_cast<unsigned int*>(sCand + 4);    // [4]
+    uint4* sDesc = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(sAcc + 4) + 15) & ~(uintptr_t)15);   // [8] per-chunk descriptor words (FP16 split)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // S' images + mu arrive by TMA bulk copies (cp.async.bulk: global -> shared through the async proxy, completion counted
     // in bytes on an mbarrier) issued by one thread while the other warps set up barriers and tensor memory; the table in
     // global memory is laid out exactly like this shared-memory block.
-    uint64_t* table_bar = bars + 11;
+    uint64_t* table_bar = bars + 3 * TC_MAX_GROUPS + 2;
     if (tid == 0) {
         for (int g = 0; g < TC_GROUPS; ++g) { mbar_init(&a_full[g], TC_ROWS); mbar_init(&d_done[g], 1); mbar_init(&a_free[g], TC_ROWS); }
         mbar_init(drained, TC_ROWS);
@@ -205,14 +249,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) large_sweep_tc(const TcArgs a) 
         // linear sums).  It never waits for the tensor core, only for its stage to be read back (a_free).
         const int g = warp >> 2, row = tid & (TC_ROWS - 1);
         const uint32_t stage = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + TC_COL_A + TC_STAGE_COLS * (uint32_t)g;
+        uint32_t one_bits;                               // 1.0f in a register the optimiser cannot see through: (x & 0x7fffff) | 1.0f stays ONE LOP3
+        asm("mov.u32 %0, 0x3f800000;" : "=r"(one_bits));
         uint32_t k = 0;                                  // chunks this group has produced (barrier parity)
-        uint32_t first_mod = 0;                          // (tl * C) mod 3
+        uint32_t first_mod = 0;                          // (tl * C) mod G
         for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const uint64_t p0 = tile * TC_ROWS;
             const uint64_t gidx = a.first + p0 + (uint64_t)row;
             const uint32_t c0 = (uint32_t)gidx, c1 = (uint32_t)(gidx >> 32);
             const bool live = p0 + (uint64_t)row < a.P;
-            for (int ci = (int)((g + 3u - first_mod) % 3u); ci < C; ci += TC_GROUPS, ++k) {
+            for (int ci = (int)((g + (uint32_t)TC_GROUPS - first_mod) % (uint32_t)TC_GROUPS); ci < C; ci += TC_GROUPS, ++k) {
                 const int c = C - 1 - ci;
                 float l[TC_KC];
                 const int i0 = TC_KC * c;
@@ -235,8 +281,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) large_sweep_tc(const TcArgs a) 
                     philox_fields<TC_KC>(c0, c1, 0u, STREAM_WEIGHTS | (uint32_t)(6 * c), a.k0, a.k1, f);
 #pragma unroll
                     for (int j = 0; j < TC_KC; j += 2) {          // U = 2 - f in (0, 1], two per FFMA2 (same values as unit_open0)
-                        const float2 m2 = make_float2(__uint_as_float((f[j] & 0x007fffffu) | 0x3f800000u),
-                                                      __uint_as_float((f[j + 1] & 0x007fffffu) | 0x3f800000u));
+                        const float2 m2 = make_float2(__uint_as_float(tc_mant_or(f[j], one_bits)), __uint_as_float(tc_mant_or(f[j + 1], one_bits)));
                         const float2 u2 = fma2(m2, bcast2(-1.0f), bcast2(2.0f));
                         l[j] = Math<float>::lg2(u2.x);
                         l[j + 1] = Math<float>::lg2(u2.y);
@@ -260,37 +305,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) large_sweep_tc(const TcArgs a) 
                             if (i0 + j < a.n) dst[j] = sg * l[j];
                     }
                 }
-                if (k > 0) {                             // the stage's previous contents must have been read back
-                    mbar_wait(&a_free[g], (k - 1u) & 1u);
-                    tc_fence_after();
-                }
-                // ---- split: hi = TF32 truncation, lo = exact remainder, bf = BF16 copy for the Slo term ----
+                if constexpr (F16) {
+                    // ---- split: h1 = FP16(l), h2 = FP16(l - h1): 22 significant bits in two FP16 operands; l itself rides along in
+                    //      the stage for the epilogue's row-dot.  The split is done BEFORE waiting for the stage: the wait -> tcgen05.st
+                    //      -> a_full segment is on the ring every stage travels (generator -> MMA -> epilogue -> generator), and
+                    //      only the four stores have to be on it ----
+                    uint32_t h1[16], h2[16];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t hi[16], lo[16], bf[8];
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2) {            // lo = l - hi exactly (one FFMA2 per pair)
-                        hi[j] = __float_as_uint(l[16 * h + j]) & 0xffffe000u;
-                        hi[j + 1] = __float_as_uint(l[16 * h + j + 1]) & 0xffffe000u;
-                        const float2 lo2 = fma2(make_float2(__uint_as_float(hi[j]), __uint_as_float(hi[j + 1])), bcast2(-1.0f),
-                                                make_float2(l[16 * h + j], l[16 * h + j + 1]));
-                        lo[j] = __float_as_uint(lo2.x);
-                        lo[j + 1] = __float_as_uint(lo2.y);
+                    for (int j = 0; j < 16; ++j) {
+                        const float2 l2 = make_float2(l[2 * j], l[2 * j + 1]);
+                        const __half2 p1 = __floats2half2_rn(l2.x, l2.y);                                  // low half = even k
+                        const float2 b = __half22float2(p1);
+                        const float2 rem = fma2(b, bcast2(-1.0f), l2);                                     // exact
+                        const __half2 p2 = __floats2half2_rn(rem.x, rem.y);
+                        h1[j] = *reinterpret_cast<const uint32_t*>(&p1);
+                        h2[j] = *reinterpret_cast<const uint32_t*>(&p2);
                     }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const __nv_bfloat162 p2 = __floats2bfloat162_rn(l[16 * h + 2 * j], l[16 * h + 2 * j + 1]);        // low half = even k
-                        bf[j] = *reinterpret_cast<const uint32_t*>(&p2);
+                    if (k > 0) {                         // the stage's previous contents must have been read back
+                        mbar_wait(&a_free[g], (k - 1u) & 1u);
+                        tc_fence_after();
                     }
-                    tmem_st16(stage + 16u * h, hi);
-                    tmem_st16(stage + 32u + 16u * h, lo);
-                    tmem_st8(stage + 64u + 8u * h, bf);
+                    tmem_st16(stage, h1);
+                    tmem_st16(stage + 16u, h2);
+                    tmem_st16(stage + 32u, *reinterpret_cast<const uint32_t(*)[16]>(&l[0]));
+                    tmem_st16(stage + 48u, *reinterpret_cast<const uint32_t(*)[16]>(&l[16]));
+                } else {
+                    if (k > 0) {                         // the stage's previous contents must have been read back
+                        mbar_wait(&a_free[g], (k - 1u) & 1u);
+                        tc_fence_after();
+                    }
+                    // ---- split: hi = TF32 truncation, lo = exact remainder, bf = BF16 copy for the Slo term ----
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t hi[16], lo[16], bf[8];
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {            // lo = l - hi exactly (one FFMA2 per pair)
+                            hi[j] = __float_as_uint(l[16 * h + j]) & 0xffffe000u;
+                            hi[j + 1] = __float_as_uint(l[16 * h + j + 1]) & 0xffffe000u;
+                            const float2 lo2 = fma2(make_float2(__uint_as_float(hi[j]), __uint_as_float(hi[j + 1])), bcast2(-1.0f),
+                                                    make_float2(l[16 * h + j], l[16 * h + j + 1]));
+                            lo[j] = __float_as_uint(lo2.x);
+                            lo[j + 1] = __float_as_uint(lo2.y);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const __nv_bfloat162 p2 = __floats2bfloat162_rn(l[16 * h + 2 * j], l[16 * h + 2 * j + 1]);        // low half = even k
+                            bf[j] = *reinterpret_cast<const uint32_t*>(&p2);
+                        }
+                        tmem_st16(stage + 16u * h, hi);
+                        tmem_st16(stage + 32u + 16u * h, lo);
+                        tmem_st8(stage + 64u + 8u * h, bf);
+                    }
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 mbar_arrive(&a_full[g]);
             }
-            first_mod = (first_mod + (uint32_t)C) % 3u;
+            first_mod = (first_mod + (uint32_t)C) % (uint32_t)TC_GROUPS;
         }
     } else if (warp == TC_MMA_WARP) {
         // ================= MMA issue: one elected thread, warp-convergent =================
@@ -298,32 +369,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) large_sweep_tc(const TcArgs a) 
         // functions of the chunk index, computed on warp-uniform values before the barrier waits, and the issue is
         // predicated on elect.sync in convergent code (an `if (lane == 0)` makes ptxas wrap every UTCHMMA in a lane loop).
         const uint32_t sbo = 128u, hi_base = smem_u32(sHi), lo_base = smem_u32(sLo);
-        const uint32_t id32_base = tc_idesc(2u, 0u), id16_base = tc_idesc(1u, 0u);
+        const uint32_t id32_base = tc_idesc(2u, 0u), id16_base = tc_idesc(1u, 0u), idf16_base = tc_idesc(0u, 0u);   // TF32 / BF16 / FP16 operands
+        if constexpr (F16) {
+            if (lane < C) {                              // low descriptor words of chunk `lane`: start address >> 4 | (LBO >> 4) << 16
+                const uint32_t Nl = (uint32_t)(TC_KC * (lane + 1)), lbol = (Nl / 8u) * 128u;
+                const uint32_t b1 = hi_base + tc_lo_off(lane), b2 = lo_base + tc_lo_off(lane);
+                sDesc[lane] = make_uint4((uint32_t)tc_sdesc(b1, lbol, sbo), (uint32_t)tc_sdesc(b1 + 2u * lbol, lbol, sbo),
+                                         (uint32_t)tc_sdesc(b2, lbol, sbo), (uint32_t)tc_sdesc(b2 + 2u * lbol, lbol, sbo));
+            }
+            __syncwarp();
+        }
         uint32_t g = 0, cyc = 0;                         // chunk n = 3 * cyc + g uses stage g for the cyc-th time
         uint32_t tl = 0;
         for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
             for (int ci = 0; ci < C; ++ci) {
                 const int c = C - 1 - ci;
                 const uint32_t N = (uint32_t)(TC_KC * (c + 1)), lbo = (N / 8u) * 128u;
-                const uint32_t bhi = hi_base + tc_hi_off(c), blo = lo_base + tc_lo_off(c);
-                const uint64_t bd0 = tc_sdesc(bhi, lbo, sbo), bd1 = tc_sdesc(bhi + 2u * lbo, lbo, sbo), bd2 = tc_sdesc(bhi + 4u * lbo, lbo, sbo),
-                               bd3 = tc_sdesc(bhi + 6u * lbo, lbo, sbo), bl0 = tc_sdesc(blo, lbo, sbo), bl1 = tc_sdesc(blo + 2u * lbo, lbo, sbo);
-                const uint32_t id32 = id32_base | ((N >> 3) << 17), id16 = id16_base | ((N >> 3) << 17);
-                const uint32_t a_hi = tmem + TC_COL_A + TC_STAGE_COLS * g, a_lo = a_hi + 32u, a_bf = a_hi + 64u;
-                mbar_wait(&a_full[g], cyc & 1u);
-                if (ci == 0 && tl > 0) mbar_wait(drained, (tl - 1u) & 1u);          // chunk C-1 overwrites the whole accumulator
-                tc_fence_after();
-                mma_tf32_ts_elect(tmem, a_hi, bd0, id32, ci > 0 ? 1u : 0u);
-                mma_tf32_ts_elect(tmem, a_lo, bd0, id32, 1u);
-                mma_tf32_ts_elect(tmem, a_hi + 8u, bd1, id32, 1u);
-                mma_tf32_ts_elect(tmem, a_lo + 8u, bd1, id32, 1u);
-                mma_tf32_ts_elect(tmem, a_hi + 16u, bd2, id32, 1u);
-                mma_tf32_ts_elect(tmem, a_lo + 16u, bd2, id32, 1u);
-                mma_tf32_ts_elect(tmem, a_hi + 24u, bd3, id32, 1u);
-                mma_tf32_ts_elect(tmem, a_lo + 24u, bd3, id32, 1u);
-                mma_bf16_ts_elect(tmem, a_bf, bl0, id16, 1u);
-                mma_bf16_ts_elect(tmem, a_bf + 8u, bl1, id16, 1u);
-                tc_commit_elect(&d_done[g]);
+                const uint32_t a_st = tmem + TC_COL_A + TC_STAGE_COLS * g;
+                if constexpr (F16) {
+                    // six FP16 MMAs (K = 16 each): h1 S1 + h2 S1 + h1 S2 for the two halves of the chunk, one elect, one asm block;
+                    // the chunk's descriptor words come from the table this warp built in shared memory before the loop (this warp
+                    // shares its scheduler with five busy ones: every instruction between a_full and the first MMA is ring latency)
+                    const uint4 dw = sDesc[c];
+                    const uint32_t idh = idf16_base | ((N >> 3) << 17);
+                    mbar_wait(&a_full[g], cyc & 1u);
+                    if (ci == 0 && tl > 0) mbar_wait(drained, (tl - 1u) & 1u);          // chunk C-1 overwrites the whole accumulator
+                    tc_fence_after();
+                    mma6_f16_commit_elect(tmem, a_st, a_st + 16u, dw.x, dw.y, dw.z, dw.w, 0x4008u, idh, ci > 0 ? 1u : 0u, smem_u32(&d_done[g]));
+                } else {
+                    const uint32_t bhi = hi_base + tc_hi_off(c), blo = lo_base + tc_lo_off(c);
+                    const uint64_t bd0 = tc_sdesc(bhi, lbo, sbo), bd1 = tc_sdesc(bhi + 2u * lbo, lbo, sbo), bd2 = tc_sdesc(bhi + 4u * lbo, lbo, sbo),
+                                   bd3 = tc_sdesc(bhi + 6u * lbo, lbo, sbo), bl0 = tc_sdesc(blo, lbo, sbo), bl1 = tc_sdesc(blo + 2u * lbo, lbo, sbo);
+                    const uint32_t id32 = id32_base | ((N >> 3) << 17), id16 = id16_base | ((N >> 3) << 17);
+                    const uint32_t a_hi = a_st, a_lo = a_hi + 32u, a_bf = a_hi + 64u;
+                    mbar_wait(&a_full[g], cyc & 1u);
+                    if (ci == 0 && tl > 0) mbar_wait(drained, (tl - 1u) & 1u);          // chunk C-1 overwrites the whole accumulator
+                    tc_fence_after();
+                    mma_tf32_ts_elect(tmem, a_hi, bd0, id32, ci > 0 ? 1u : 0u);
+                    mma_tf32_ts_elect(tmem, a_lo, bd0, id32, 1u);
+                    mma_tf32_ts_elect(tmem, a_hi + 8u, bd1, id32, 1u);
+                    mma_tf32_ts_elect(tmem, a_lo + 8u, bd1, id32, 1u);
+                    mma_tf32_ts_elect(tmem, a_hi + 16u, bd2, id32, 1u);
+                    mma_tf32_ts_elect(tmem, a_lo + 16u, bd2, id32, 1u);
+                    mma_tf32_ts_elect(tmem, a_hi + 24u, bd3, id32, 1u);
+                    mma_tf32_ts_elect(tmem, a_lo + 24u, bd3, id32, 1u);
+                    mma_bf16_ts_elect(tmem, a_bf, bl0, id16, 1u);
+                    mma_bf16_ts_elect(tmem, a_bf + 8u, bl1, id16, 1u);
+                    tc_commit_elect(&d_done[g]);
+                }
                 if (++g == TC_GROUPS) { g = 0; ++cyc; }
             }
         }
@@ -350,8 +443,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) large_sweep_tc(const TcArgs a) 
                 for (int h = 0; h < 2; ++h) {
                     uint32_t y[16], hi[16], lo[16];
                     tmem_ld16(lane_base + (uint32_t)(TC_KC * c + 16 * h), y);
-                    tmem_ld16(st + 16u * h, hi);
-                    tmem_ld16(st + 32u + 16u * h, lo);
+                    if constexpr (F16) {
+                        tmem_ld16(st + 32u + 16u * h, hi);                  // the FP16 stage carries l itself
+                    } else {
+                        tmem_ld16(st + 16u * h, hi);
+                        tmem_ld16(st + 32u + 16u * h, lo);
+                    }
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (h == 1) {                         // everything of this chunk is in registers: release stage and columns
                         tc_fence_before();
@@ -362,11 +459,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) large_sweep_tc(const TcArgs a) 
 #pragma unroll
                     for (int m = 0; m < 4; ++m) {
                         const float4 u = mu4[m];
-                        // l = hi + lo exactly; packed FP32x2 throughout (one FFMA2 = two assets)
-                        const float2 la = fma2(make_float2(__uint_as_float(hi[4 * m]), __uint_as_float(hi[4 * m + 1])), bcast2(1.0f),
-                                               make_float2(__uint_as_float(lo[4 * m]), __uint_as_float(lo[4 * m + 1])));
-                        const float2 lb = fma2(make_float2(__uint_as_float(hi[4 * m + 2]), __uint_as_float(hi[4 * m + 3])), bcast2(1.0f),
-                                               make_float2(__uint_as_float(lo[4 * m + 2]), __uint_as_float(lo[4 * m + 3])));
+                        float2 la, lb;
+                        if constexpr (F16) {
+                            la = make_float2(__uint_as_float(hi[4 * m]), __uint_as_float(hi[4 * m + 1]));
+                            lb = make_float2(__uint_as_float(hi[4 * m + 2]), __uint_as_float(hi[4 * m + 3]));
+                        } else {
+                            // l = hi + lo exactly; packed FP32x2 throughout (one FFMA2 = two assets)
+                            la = fma2(make_float2(__uint_as_float(hi[4 * m]), __uint_as_float(hi[4 * m + 1])), bcast2(1.0f),
+                                      make_float2(__uint_as_float(lo[4 * m]), __uint_as_float(lo[4 * m + 1])));
+                            lb = fma2(make_float2(__uint_as_float(hi[4 * m + 2]), __uint_as_float(hi[4 * m + 3])), bcast2(1.0f),
+                                      make_float2(__uint_as_float(lo[4 * m + 2]), __uint_as_float(lo[4 * m + 3])));
+                        }
                         q2 = fma2(make_float2(__uint_as_float(y[4 * m]), __uint_as_float(y[4 * m + 1])), la, q2);
                         q2 = fma2(make_float2(__uint_as_float(y[4 * m + 2]), __uint_as_float(y[4 * m + 3])), lb, q2);
                         s2 = fma2(la, bcast2(1.0f), s2);
@@ -380,7 +483,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) large_sweep_tc(const TcArgs a) 
             const uint64_t local = tile * TC_ROWS + (uint64_t)row;
             if (local < a.P) {
                 const bool supplied = a.w_in != nullptr;
-                const float q = q2.x + q2.y;
+                const float q = F16 ? (q2.x + q2.y) * a.qscale : q2.x + q2.y;
                 const float s = supplied ? 1.f : -(s2.x + s2.y), r = supplied ? (r2.x + r2.y) : -(r2.x + r2.y);         // Philox rows hold l = -e
                 float ret, risk, sharpe;
                 metrics_from<float>(q, r, s, a.rf, supplied, ret, risk, sharpe);
@@ -458,26 +561,76 @@ bool pf_large_tc_eligible(const PfJob& job) {
     return job.dtype == MCP_F32 && job.n > PF_SMALL_MAX_N && job.n <= TC_MAX_N && !job.bounds;
 }
 
+// FP16 split: Philox rows only (|lg2 U| <= 24 is inside FP16's range; supplied weights may be any FP32 value), MCP_LARGE_TC_F16=0 disables
+static bool tc_use_f16(const PfJob& job) {
+    const char* v = getenv("MCP_LARGE_TC_F16");
+    if (v && v[0] == '0') return false;
+    return job.w_in == nullptr;
+}
+
+template <bool F16>
+static int tc_launch(mcp_context* h, PfJob& job, const TcArgs& a, size_t table_bytes) {
+    auto kern = large_sweep_tc<F16>;
+    const size_t smem = table_bytes + (3 * TC_MAX_GROUPS + 3) * sizeof(uint64_t) + 4 * sizeof(PfCand) + 4 * sizeof(unsigned int) + 8 * sizeof(uint4) + 32;
+    if (smem > h->prop.sharedMemPerBlockOptin)
+        return mcp_fail(h, MCP_ERR_INVALID, "large_sweep_tc: N=%d needs %zu B of shared memory (max %zu)", job.n, smem, (size_t)h->prop.sharedMemPerBlockOptin);
+    MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t n_tiles = (job.P + TC_ROWS - 1) / TC_ROWS;
+    uint64_t grid = std::min<uint64_t>((uint64_t)h->prop.multiProcessorCount, n_tiles);
+    grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, job.max_blocks));
+    job.blocks_used = (int)grid;
+    kern<<<(unsigned)grid, TcCfg<F16>::THREADS, smem, job.stream>>>(a);
+    MCP_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return MCP_OK;
+}
+
 int pf_large_launch_tc(mcp_context* h, PfJob& job) {
     const int n = job.n, np = std::max(64, (n + TC_KC - 1) / TC_KC * TC_KC), C = np / TC_KC;
-    const uint32_t hi_bytes = tc_hi_off(C), lo_bytes = tc_lo_off(C);
+    const bool f16 = tc_use_f16(job);
+    const uint32_t lo_bytes = tc_lo_off(C), hi_bytes = f16 ? lo_bytes : tc_hi_off(C);
     const size_t table_bytes = (size_t)hi_bytes + lo_bytes + (size_t)np * 4;
+    // S'[k][j], j <= k: Sigma_kk on the diagonal, Sigma_kj + Sigma_jk below it (w' Sigma w = sum_k sum_{j<=k} w_k S'_kj w_j)
+    auto s_prime = [&](int k, int j) { return j == k ? job.sigma[(size_t)k * n + k] : job.sigma[(size_t)k * n + j] + job.sigma[(size_t)j * n + k]; };
+    // FP16 split: S' is stored times 2^e with the largest entry in [2^13, 2^14) (FP16 keeps 11 significant bits down to
+    // 2^-14, i.e. over 28 binades below the largest entry; the second image holds the next 11 bits); q is multiplied by 2^-e
+    double qscale = 1.0, sscale = 1.0;
+    if (f16) {
+        double smax = 0;
+        for (int k = 0; k < n; ++k)
+            for (int j = 0; j <= k; ++j) smax = std::max(smax, std::fabs(s_prime(k, j)));
+        if (smax > 0 && std::isfinite(smax)) {
+            int e = 0;
+            std::frexp(smax, &e);                       // smax = m 2^e, m in [0.5, 1)
+            e = std::min(120, std::max(-120, 14 - e));        // 2^e and 2^-e both normal FP32 numbers
+            sscale = std::ldexp(1.0, e);
+            qscale = std::ldexp(1.0, -e);
+        }
+    }
     unsigned char* dev = nullptr;
     MCP_CHECK(mcp_dev_reserve(h, 6, table_bytes, (void**)&dev));
-    if (job.tc_table_epoch == 0 || job.tc_table_epoch != h->const_epoch) {          // once per mcp_portfolios call: later chunks and the replays reuse it
+    // once per mcp_portfolios call and operand split: later chunks and the replays reuse it
+    if (job.tc_table_epoch == 0 || job.tc_table_epoch != h->const_epoch || job.tc_table_f16 != (f16 ? 1 : 0)) {
         std::vector<unsigned char> host(table_bytes, 0);
-        // S'[k][j], j <= k: Sigma_kk on the diagonal, Sigma_kj + Sigma_jk below it (w' Sigma w = sum_k sum_{j<=k} w_k S'_kj w_j).
-        // Canonical K-major no-swizzle layout per chunk: [K core (4 tf32 / 8 bf16)][N group of 8][8 rows x 16 bytes].
+        // Canonical K-major no-swizzle layout per chunk: [K core (4 tf32 / 8 16-bit)][N group of 8][8 rows x 16 bytes].
         for (int k = 0; k < n; ++k) {
             const int c = k / TC_KC, kk = k % TC_KC, Nc = TC_KC * (c + 1);
             for (int j = 0; j <= k; ++j) {
-                const double v = j == k ? job.sigma[(size_t)k * n + k] : job.sigma[(size_t)k * n + j] + job.sigma[(size_t)j * n + k];
-                const float shi = tf32_round((float)v);
-                const uint16_t slo = bf16_round((float)(v - (double)shi));
-                const size_t oh = (size_t)tc_hi_off(c) + ((size_t)(kk / 4) * (Nc / 8) + j / 8) * 128 + (j % 8) * 16 + (kk % 4) * 4;
-                const size_t ol = (size_t)hi_bytes + tc_lo_off(c) + ((size_t)(kk / 8) * (Nc / 8) + j / 8) * 128 + (j % 8) * 16 + (kk % 8) * 2;
-                memcpy(&host[oh], &shi, 4);
-                memcpy(&host[ol], &slo, 2);
+                const double v = s_prime(k, j);
+                const size_t o16 = (size_t)tc_lo_off(c) + ((size_t)(kk / 8) * (Nc / 8) + j / 8) * 128 + (j % 8) * 16 + (kk % 8) * 2;
+                if (f16) {
+                    const double vs = v * sscale;
+                    const __half s1 = __float2half_rn((float)vs);
+                    const __half s2 = __float2half_rn((float)(vs - (double)__half2float(s1)));
+                    memcpy(&host[o16], &s1, 2);
+                    memcpy(&host[(size_t)hi_bytes + o16], &s2, 2);
+                } else {
+                    const float shi = tf32_round((float)v);
+                    const uint16_t slo = bf16_round((float)(v - (double)shi));
+                    const size_t oh = (size_t)tc_hi_off(c) + ((size_t)(kk / 4) * (Nc / 8) + j / 8) * 128 + (j % 8) * 16 + (kk % 4) * 4;
+                    memcpy(&host[oh], &shi, 4);
+                    memcpy(&host[(size_t)hi_bytes + o16], &slo, 2);
+                }
             }
         }
         float* hmu = reinterpret_cast<float*>(host.data() + hi_bytes + lo_bytes);
@@ -485,6 +638,7 @@ int pf_large_launch_tc(mcp_context* h, PfJob& job) {
         MCP_CUDA(h, cudaMemcpyAsync(dev, host.data(), table_bytes, cudaMemcpyHostToDevice, job.stream));
         MCP_CUDA(h, cudaStreamSynchronize(job.stream));        // `host` is pageable and dies at scope exit; other streams may read next
         job.tc_table_epoch = ++h->const_epoch;
+        job.tc_table_f16 = f16 ? 1 : 0;
     }
 
     TcArgs a;
@@ -499,17 +653,8 @@ int pf_large_launch_tc(mcp_context* h, PfJob& job) {
     a.first = job.first; a.P = job.P; a.n = n; a.np = np;
     a.k0 = (uint32_t)job.seed; a.k1 = (uint32_t)(job.seed >> 32);
     a.rf = (float)job.rf; a.target = (float)job.target;
-    const size_t smem = table_bytes + 12 * sizeof(uint64_t) + 4 * sizeof(PfCand) + 4 * sizeof(unsigned int) + 16;
-    if (smem > h->prop.sharedMemPerBlockOptin)
-        return mcp_fail(h, MCP_ERR_INVALID, "large_sweep_tc: N=%d needs %zu B of shared memory (max %zu)", n, smem, (size_t)h->prop.sharedMemPerBlockOptin);
-    MCP_CUDA(h, cudaFuncSetAttribute(large_sweep_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint64_t n_tiles = (job.P + TC_ROWS - 1) / TC_ROWS;
-    uint64_t grid = std::min<uint64_t>((uint64_t)h->prop.multiProcessorCount, n_tiles);
-    grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, job.max_blocks));
-    job.blocks_used = (int)grid;
-    large_sweep_tc<<<(unsigned)grid, TC_THREADS, smem, job.stream>>>(a);
-    MCP_CUDA(h, cudaGetLastError());
-    h->launches++;
+    a.qscale = (float)qscale;
+    MCP_CHECK(f16 ? tc_launch<true>(h, job, a, table_bytes) : tc_launch<false>(h, job, a, table_bytes));
     if (a.w_out) {
         const uint64_t total = job.P * (uint64_t)n;
         const unsigned blocks = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)h->prop.multiProcessorCount * 8);

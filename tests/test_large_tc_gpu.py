@@ -38,6 +38,20 @@ class simt_kernel:
             os.environ["MCP_LARGE_TC"] = self.old
 
 
+class tf32_split:
+    """MCP_LARGE_TC_F16=0 makes Philox rows use the TF32 + BF16 operand split that supplied weights always use."""
+
+    def __enter__(self):
+        self.old = os.environ.get("MCP_LARGE_TC_F16")
+        os.environ["MCP_LARGE_TC_F16"] = "0"
+
+    def __exit__(self, *exc):
+        if self.old is None:
+            del os.environ["MCP_LARGE_TC_F16"]
+        else:
+            os.environ["MCP_LARGE_TC_F16"] = self.old
+
+
 def wild_sigma(n, seed):
     """Covariance with variances over six decades and strong common factors: cancellation in w'Sw and
     entries whose TF32 rounding error alone would exceed the FP32 tolerance."""
@@ -151,3 +165,38 @@ def test_tc_supplied_weights_parity_mode(mcp, n):
     e_tc, e_sm = np.abs(tc.risks / want["risks"] - 1).max(), np.abs(sm.risks / want["risks"] - 1).max()
     assert e_tc < 2e-5 and e_tc < 3 * e_sm + 2e-6, (e_tc, e_sm)
     assert np.abs(tc.risks / sm.risks - 1).max() < 2e-5
+
+
+@pytest.mark.parametrize("n,scale", [(40, 1.0), (256, 1.0), (96, 1e-12), (200, 1e9), (64, 3e-30)])
+def test_fp16_split_agrees_with_tf32_split_and_oracle_at_any_covariance_scale(mcp, n, scale):
+    """Philox rows run the FP16 operand split (S' stored times a power of two so that FP16's range is never the issue):
+    same weights, FP32-class agreement with the TF32 split and with the FP64 oracle, whatever the units of Sigma."""
+    mu, sigma = wild_sigma(n, seed=7 * n)
+    sigma = sigma * scale
+    P, seed = 3000, 21
+    f16 = mcp.simulate_portfolios(mu, sigma, P, risk_free=0.0, seed=seed, dtype="float32")
+    with tf32_split():
+        t32 = mcp.simulate_portfolios(mu, sigma, P, risk_free=0.0, seed=seed, dtype="float32")
+    assert np.array_equal(f16.weights, t32.weights)                       # the generator is the same code
+    W, _ = philox_np.dirichlet_weights(0, P, n, seed, "float32")
+    want = ref.evaluate(W, mu, sigma, 0.0, 0.30)
+    e16, e32 = np.abs(f16.risks / want["risks"] - 1).max(), np.abs(t32.risks / want["risks"] - 1).max()
+    assert e16 < 2e-5 and e32 < 2e-5, (e16, e32)                          # 1e-4 is the bar
+    assert np.abs(f16.risks / t32.risks - 1).max() < 1e-5
+    assert np.allclose(f16.returns, t32.returns, rtol=2e-6, atol=1e-9)
+    assert np.isfinite(f16.sharpes).all()
+    i = f16.max_sharpe["index"]
+    assert f16.max_sharpe["risk"] == float(f16.risks[i]) and f16.max_sharpe["sharpe"] == float(f16.sharpes[i])
+
+
+def test_fp16_split_zero_and_tiny_covariance(mcp):
+    """Sigma = 0 (every risk exactly 0, Sharpe 0 by the reference's guard, app.py:711) and a covariance of denormal size."""
+    n = 48
+    mu = np.linspace(0.01, 0.2, n)
+    z = mcp.simulate_portfolios(mu, np.zeros((n, n)), 500, risk_free=0.0, seed=1, dtype="float32")
+    assert np.all(z.risks == 0) and np.all(z.sharpes == 0) and np.isfinite(z.returns).all()
+    _, sigma = wild_sigma(n, seed=3)
+    t = mcp.simulate_portfolios(mu, sigma * 1e-36, 500, risk_free=0.0, seed=1, dtype="float32")
+    W, _ = philox_np.dirichlet_weights(0, 500, n, 1, "float32")
+    want = ref.evaluate(W, mu, sigma * 1e-36, 0.0, 0.30)
+    assert np.allclose(t.risks, want["risks"], rtol=1e-4)
