@@ -129,8 +129,9 @@ typedef struct {
 } mcp_portfolio_out;
 
 /* Kernel selection (internal, by shape): N <= 32 register kernels (FP32 packed FFMA2 / FP64);
- * 32 < N <= 256 FP32 without bounds: tcgen05 tensor-core sweep (environment MCP_LARGE_TC=0 forces the
- * SIMT kernel, for A/B measurements); bounds rejection at N > 32: tiled SIMT kernel; FP64 N > 32 and
+ * 32 < N <= 256 FP32 without bounds: tcgen05 tensor-core sweep -- FP16 operand split for in-kernel RNG rows,
+ * TF32 + BF16 split for supplied weights (environment MCP_LARGE_TC=0 forces the SIMT kernel, MCP_LARGE_TC_F16=0
+ * the TF32 split, for A/B measurements); bounds rejection at N > 32: tiled SIMT kernel; FP64 N > 32 and
  * FP32 N > 256: warp-per-portfolio kernel.  All produce the same portfolios for a given (seed, index).   */
 int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* params,
                    const double* mu_host, const double* sigma_host,
