@@ -120,6 +120,20 @@ template <> struct Math<double> {
     static __device__ __forceinline__ double unit_frac(uint32_t x) { return (double)x * 0x1p-32; }
 };
 
+// (x & 0x007fffff) | expo as ONE LOP3: written as `(x & m) | c` with two literals, ptxas often emits an AND and an OR (one
+// 32-bit immediate per instruction).  `expo` comes from opaque_u32(), a register the optimiser cannot fold back into a literal.
+// The sweeps are issue-bound: this is 4-5 % of their instruction stream.
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {
+    uint32_t r;
+    asm("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ uint32_t mant_or(uint32_t x, uint32_t expo) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, 0x007fffff, %2, 0xEA;" : "=r"(d) : "r"(x), "r"(expo));
+    return d;
+}
+
 // ---- packed FP32x2 (Blackwell FFMA2): one instruction = two FMAs, operands may be register
 // pairs, uniform-register pairs (constant bank) or a broadcast scalar.  The fused sweep is
 // issue-bound, so halving the FFMA count is worth more than any pipe-level trick.

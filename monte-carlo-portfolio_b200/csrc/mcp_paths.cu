@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(PATH_BLOCK) path_kernel_packed(const __grid_co
     const uint64_t n_sub = (a.M + PATH_BLOCK - 1) / PATH_BLOCK;
     const uint64_t n_tiles = (n_sub + 1) / 2;
     const float kPi = 3.14159265358979323846f;
+    const uint32_t one_bits = opaque_u32(0x3f800000u), two_bits = opaque_u32(0x40000000u);
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t mA = tile * (2 * PATH_BLOCK) + threadIdx.x, mB = mA + PATH_BLOCK;
         const uint64_t gA = a.first + mA, gB = a.first + mB;
@@ -149,13 +150,11 @@ __global__ void __launch_bounds__(PATH_BLOCK) path_kernel_packed(const __grid_co
             philox_fields<NP>((uint32_t)gB, (uint32_t)(gB >> 32), (uint32_t)s, STREAM_NORMALS, a.k0, a.k1, fb);
 #pragma unroll
             for (int k = 0; k < NP / 2; ++k) {
-                const float2 f1 = make_float2(__uint_as_float((fa[2 * k] & 0x007fffffu) | 0x3f800000u),
-                                              __uint_as_float((fb[2 * k] & 0x007fffffu) | 0x3f800000u));
+                const float2 f1 = make_float2(__uint_as_float(mant_or(fa[2 * k], one_bits)), __uint_as_float(mant_or(fb[2 * k], one_bits)));
                 const float2 u1 = fma2(f1, bcast2(-1.0f), bcast2(2.0f));                      // (0, 1]
                 // r / sqrt(2 ln 2) = sqrt(-lg2 U1): the constant rides in lp (host), the negation in the MUFU operand
                 const float2 r = make_float2(Math<float>::sqrt(-Math<float>::lg2(u1.x)), Math<float>::sqrt(-Math<float>::lg2(u1.y)));
-                const float2 f2 = make_float2(__uint_as_float((fa[2 * k + 1] & 0x007fffffu) | 0x40000000u),
-                                              __uint_as_float((fb[2 * k + 1] & 0x007fffffu) | 0x40000000u));
+                const float2 f2 = make_float2(__uint_as_float(mant_or(fa[2 * k + 1], two_bits)), __uint_as_float(mant_or(fb[2 * k + 1], two_bits)));
                 const float2 th = fma2(f2, bcast2(kPi), bcast2(-3.0f * kPi));                 // pi (2f - 1) in [-pi, pi), one rounding
                 const float2 cs = make_float2(Math<float>::cosf_(th.x), Math<float>::cosf_(th.y));
                 const float2 sn = make_float2(Math<float>::sinf_(th.x), Math<float>::sinf_(th.y));

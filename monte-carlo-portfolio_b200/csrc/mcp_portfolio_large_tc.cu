@@ -143,12 +143,6 @@ __device__ __forceinline__ void mma6_f16_commit_elect(uint32_t d, uint32_t a_h1,
                  "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n\t}"
                  ::"r"(d), "r"(a_h1), "r"(a_h2), "r"(dlo10), "r"(dlo11), "r"(dlo20), "r"(dlo21), "r"(dhi), "r"(idesc), "r"(acc), "r"(bar) : "memory");
 }
-// (x & 0x007fffff) | expo as one LOP3 (immediate mask, exponent bits from a register)
-__device__ __forceinline__ uint32_t tc_mant_or(uint32_t x, uint32_t expo) {
-    uint32_t d;
-    asm("lop3.b32 %0, %1, 0x007fffff, %2, 0xEA;" : "=r"(d) : "r"(x), "r"(expo));
-    return d;
-}
 __device__ __forceinline__ void tc_commit_elect(uint64_t* b) {
     asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
                  "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(b)) : "memory");
@@ -249,8 +243,7 @@ __global__ void __launch_bounds__(TcCfg<F16>::THREADS, 1) large_sweep_tc(const T
         // linear sums).  It never waits for the tensor core, only for its stage to be read back (a_free).
         const int g = warp >> 2, row = tid & (TC_ROWS - 1);
         const uint32_t stage = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + TC_COL_A + TC_STAGE_COLS * (uint32_t)g;
-        uint32_t one_bits;                               // 1.0f in a register the optimiser cannot see through: (x & 0x7fffff) | 1.0f stays ONE LOP3
-        asm("mov.u32 %0, 0x3f800000;" : "=r"(one_bits));
+        const uint32_t one_bits = opaque_u32(0x3f800000u);   // (x & 0x7fffff) | 1.0f stays ONE LOP3 (mcp_device.cuh)
         uint32_t k = 0;                                  // chunks this group has produced (barrier parity)
         uint32_t first_mod = 0;                          // (tl * C) mod G
         for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -281,7 +274,7 @@ __global__ void __launch_bounds__(TcCfg<F16>::THREADS, 1) large_sweep_tc(const T
                     philox_fields<TC_KC>(c0, c1, 0u, STREAM_WEIGHTS | (uint32_t)(6 * c), a.k0, a.k1, f);
 #pragma unroll
                     for (int j = 0; j < TC_KC; j += 2) {          // U = 2 - f in (0, 1], two per FFMA2 (same values as unit_open0)
-                        const float2 m2 = make_float2(__uint_as_float(tc_mant_or(f[j], one_bits)), __uint_as_float(tc_mant_or(f[j + 1], one_bits)));
+                        const float2 m2 = make_float2(__uint_as_float(mant_or(f[j], one_bits)), __uint_as_float(mant_or(f[j + 1], one_bits)));
                         const float2 u2 = fma2(m2, bcast2(-1.0f), bcast2(2.0f));
                         l[j] = Math<float>::lg2(u2.x);
                         l[j + 1] = Math<float>::lg2(u2.y);

@@ -399,6 +399,7 @@ __global__ void __launch_bounds__(PF_BLOCK) small_sweep_packed(const __grid_cons
     uint32_t sub_s = NONE, sub_d = NONE;
     float rmin = Math<float>::inf(), rmax = -Math<float>::inf();
     uint32_t n_acc = 0;
+    const uint32_t one_bits = opaque_u32(0x3f800000u);
 
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t local0 = tile * (uint64_t)(K * PF_BLOCK) + threadIdx.x;
@@ -413,8 +414,7 @@ __global__ void __launch_bounds__(PF_BLOCK) small_sweep_packed(const __grid_cons
             philox_fields<NP>((uint32_t)gb, (uint32_t)(gb >> 32), 0u, STREAM_WEIGHTS, a.k0, a.k1, fb);
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
-                const float2 f = make_float2(__uint_as_float((fa[i] & 0x007fffffu) | 0x3f800000u),
-                                             __uint_as_float((fb[i] & 0x007fffffu) | 0x3f800000u));
+                const float2 f = make_float2(__uint_as_float(mant_or(fa[i], one_bits)), __uint_as_float(mant_or(fb[i], one_bits)));
                 const float2 u = fma2(f, bcast2(-1.0f), bcast2(2.0f));            // U = 2 - f in (0, 1]
                 l2[kp][i] = make_float2(Math<float>::lg2(u.x), Math<float>::lg2(u.y));
                 s2[kp] = fma2(l2[kp][i], bcast2(a.nmask[i]), s2[kp]);
