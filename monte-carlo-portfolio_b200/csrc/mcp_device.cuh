@@ -91,20 +91,20 @@ template <> struct Math<float> {
 };
 
 template <> struct Math<double> {
-    // log2 on the generator's domain u in [2^-32, 1] (NOT a general log2): u = 2^k m, table entry by the top 7 mantissa
-    // bits of m (mcp_lg2_table.cuh), r = fma(m, inv, -1) exact with |r| < 2^-7, degree-7 Taylor polynomial of log2(1 + r)
-    // (truncation < 3e-18).
-    // Absolute error < 4e-15 (half an ulp of the largest results), exactly 0 at u = 1; 8 DFMA instead of libdevice's ~30.
+    // log2 on the generator's domain u in [2^-32, 1] (NOT a general log2): u = 2^k m, table entry by the top 10 mantissa
+    // bits of m (mcp_lg2_table.cuh, 16 KB, L1-resident), r = fma(m, inv, -1) exact with |r| < 2^-10, degree-5 Taylor polynomial
+    // of log2(1 + r) (truncation < 3e-19).
+    // Absolute error < 4e-15 (half an ulp of the largest results), exactly 0 at u = 1; 6 DFMA instead of libdevice's ~30.
     static __device__ __forceinline__ double lg2(double u) {
         const long long b = __double_as_longlong(u);
         const int k = (int)(b >> 52) - 1023;
         const double m = __longlong_as_double((b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
-        const double2 t = MCP_LG2_TAB[(int)(b >> 45) & 127];
+        const double2 t = MCP_LG2_TAB[(int)(b >> 42) & 1023];
         const double r = ::fma(m, t.x, -1.0);
-        const double c[7] = {1.4426950408889634, -0.7213475204444817, 0.48089834696298783, -0.36067376022224085, 0.28853900817779266, -0.24044917348149392, 0.20609929155556622};
-        double p = c[6];
+        const double c[5] = {1.4426950408889634, -0.7213475204444817, 0.48089834696298783, -0.36067376022224085, 0.28853900817779266};
+        double p = c[4];
 #pragma unroll
-        for (int j = 5; j >= 0; --j) p = ::fma(p, r, c[j]);
+        for (int j = 3; j >= 0; --j) p = ::fma(p, r, c[j]);
         return ::fma(p, r, (double)k + t.y);
     }
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
