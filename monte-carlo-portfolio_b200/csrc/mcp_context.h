@@ -3,6 +3,8 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <exception>
+#include <new>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
@@ -57,6 +59,21 @@ int mcp_pinned_reserve(mcp_context* h, int slot, size_t bytes, void** out);
     do {                                                                                   \
         if (!(cond)) return mcp_fail((h), MCP_ERR_INVALID, __VA_ARGS__);                   \
     } while (0)
+
+// No C++ exception crosses the C ABI ("return int, never throw"): host-side containers can raise std::bad_alloc /
+// std::length_error; every entry point that allocates runs its body through this.
+template <typename F>
+static inline int mcp_guarded(mcp_context* h, const char* what, F&& body) noexcept {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        try { return mcp_fail(h, MCP_ERR_NOMEM, "%s: host allocation failed", what); } catch (...) { return MCP_ERR_NOMEM; }
+    } catch (const std::exception& e) {
+        try { return mcp_fail(h, MCP_ERR_INVALID, "%s: %s", what, e.what()); } catch (...) { return MCP_ERR_INVALID; }
+    } catch (...) {
+        try { return mcp_fail(h, MCP_ERR_INVALID, "%s: unknown C++ exception", what); } catch (...) { return MCP_ERR_INVALID; }
+    }
+}
 
 struct mcp_device_guard {
     int prev = -1;

@@ -508,8 +508,7 @@ static int hist_run(mcp_context* h, const mcp_hist_params* p, const double* R, m
 
 using namespace mcp;
 
-extern "C" int mcp_historical_var(mcp_handle h, const mcp_hist_params* p, const double* R, mcp_hist_out* out) {
-    if (!h) return MCP_ERR_INVALID;
+static int historical_var_impl(mcp_handle h, const mcp_hist_params* p, const double* R, mcp_hist_out* out) {
     MCP_REQUIRE(h, p && R && out, "mcp_historical_var: NULL argument");
     MCP_REQUIRE(h, p->n_assets >= 1 && p->n_assets <= 4096, "mcp_historical_var: bad n_assets %d", p->n_assets);
     MCP_REQUIRE(h, p->n_periods >= 1, "mcp_historical_var: n_periods must be >= 1 (np.percentile of an empty series is an error)");
@@ -523,4 +522,9 @@ extern "C" int mcp_historical_var(mcp_handle h, const mcp_hist_params* p, const 
     if (p->n_portfolios == 0) return MCP_OK;
     mcp_device_guard guard(h->device);
     return p->dtype == MCP_F64 ? hist_run<double>(h, p, R, out) : hist_run<float>(h, p, R, out);
+}
+
+extern "C" int mcp_historical_var(mcp_handle h, const mcp_hist_params* p, const double* R, mcp_hist_out* out) {
+    if (!h) return MCP_ERR_INVALID;
+    return mcp_guarded(h, "mcp_historical_var", [&] { return historical_var_impl(h, p, R, out); });
 }

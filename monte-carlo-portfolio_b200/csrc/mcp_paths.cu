@@ -254,9 +254,8 @@ static int path_dispatch(mcp_context* h, const mcp_path_params* p, const double*
 
 using namespace mcp;
 
-extern "C" int mcp_paths(mcp_handle h, const mcp_path_params* p, const double* mu, const double* sigma,
-                         const double* weights, void* terminal_out, double* kernel_ms) {
-    if (!h) return MCP_ERR_INVALID;
+static int paths_impl(mcp_handle h, const mcp_path_params* p, const double* mu, const double* sigma,
+                      const double* weights, void* terminal_out, double* kernel_ms) {
     MCP_REQUIRE(h, p && mu && sigma && weights && terminal_out, "mcp_paths: NULL argument");
     MCP_REQUIRE(h, p->n_assets >= 1 && p->n_assets <= 32, "mcp_paths: n_assets=%d out of range [1, 32]", p->n_assets);
     MCP_REQUIRE(h, p->dtype == MCP_F32 || p->dtype == MCP_F64, "mcp_paths: bad dtype %d", p->dtype);
@@ -296,4 +295,10 @@ extern "C" int mcp_paths(mcp_handle h, const mcp_path_params* p, const double* m
     h->last_ms = ms;
     if (kernel_ms) *kernel_ms = ms;
     return MCP_OK;
+}
+
+extern "C" int mcp_paths(mcp_handle h, const mcp_path_params* p, const double* mu, const double* sigma,
+                         const double* weights, void* terminal_out, double* kernel_ms) {
+    if (!h) return MCP_ERR_INVALID;
+    return mcp_guarded(h, "mcp_paths", [&] { return paths_impl(h, p, mu, sigma, weights, terminal_out, kernel_ms); });
 }

@@ -93,9 +93,7 @@ static void fill_selection(mcp_selection& sel, const double* rec, int n) {
     if (sel.weights) memcpy(sel.weights, rec + PF_REC_HEADER, sizeof(double) * n);
 }
 
-extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const double* mu, const double* sigma,
-                              mcp_portfolio_out* out) {
-    if (!h) return MCP_ERR_INVALID;
+static int portfolios_impl(mcp_handle h, const mcp_portfolio_params* p, const double* mu, const double* sigma, mcp_portfolio_out* out) {
     MCP_REQUIRE(h, p && mu && sigma && out, "mcp_portfolios: NULL argument");
     MCP_REQUIRE(h, p->n_assets >= 1 && p->n_assets <= 4096, "mcp_portfolios: n_assets=%d out of range [1, 4096]", p->n_assets);
     MCP_REQUIRE(h, p->dtype == MCP_F32 || p->dtype == MCP_F64, "mcp_portfolios: bad dtype %d", p->dtype);
@@ -392,9 +390,8 @@ extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const
     return MCP_OK;
 }
 
-extern "C" int mcp_envelope_arrays(mcp_handle h, int dtype, const void* risks, const void* returns, uint64_t n, uint64_t first_index,
-                                   double risk_lo, double risk_hi, int K, double* bin_best_return, uint64_t* bin_best_index) {
-    if (!h) return MCP_ERR_INVALID;
+static int envelope_arrays_impl(mcp_handle h, int dtype, const void* risks, const void* returns, uint64_t n, uint64_t first_index,
+                                double risk_lo, double risk_hi, int K, double* bin_best_return, uint64_t* bin_best_index) {
     MCP_REQUIRE(h, dtype == MCP_F32 || dtype == MCP_F64, "mcp_envelope_arrays: bad dtype %d", dtype);
     MCP_REQUIRE(h, K >= 1 && K <= ENV_MAX_BINS, "mcp_envelope_arrays: n_bins=%d out of range [1, %d]", K, ENV_MAX_BINS);
     MCP_REQUIRE(h, bin_best_return && bin_best_index, "mcp_envelope_arrays: bin outputs are NULL");
@@ -430,3 +427,15 @@ extern "C" int mcp_envelope_arrays(mcp_handle h, int dtype, const void* risks, c
     return MCP_OK;
 }
 
+extern "C" int mcp_portfolios(mcp_handle h, const mcp_portfolio_params* p, const double* mu, const double* sigma,
+                              mcp_portfolio_out* out) {
+    if (!h) return MCP_ERR_INVALID;
+    return mcp_guarded(h, "mcp_portfolios", [&] { return portfolios_impl(h, p, mu, sigma, out); });
+}
+
+extern "C" int mcp_envelope_arrays(mcp_handle h, int dtype, const void* risks, const void* returns, uint64_t n, uint64_t first_index,
+                                   double risk_lo, double risk_hi, int K, double* bin_best_return, uint64_t* bin_best_index) {
+    if (!h) return MCP_ERR_INVALID;
+    return mcp_guarded(h, "mcp_envelope_arrays",
+                       [&] { return envelope_arrays_impl(h, dtype, risks, returns, n, first_index, risk_lo, risk_hi, K, bin_best_return, bin_best_index); });
+}

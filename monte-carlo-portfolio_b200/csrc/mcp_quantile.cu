@@ -273,10 +273,9 @@ int mcp_select_hist(mcp_handle h, const void* values_dev, int dtype, uint64_t n,
     return MCP_OK;
 }
 
-int mcp_quantiles(mcp_handle h, const void* values, int space, int dtype, uint64_t n, uint64_t n_total,
-                  const double* alphas, int n_alphas, double* var_out, double* cvar_out,
-                  mcp_allreduce_fn allreduce, void* user) {
-    if (!h) return MCP_ERR_INVALID;
+static int quantiles_impl(mcp_handle h, const void* values, int space, int dtype, uint64_t n, uint64_t n_total,
+                          const double* alphas, int n_alphas, double* var_out, double* cvar_out,
+                          mcp_allreduce_fn allreduce, void* user) {
     MCP_REQUIRE(h, alphas && var_out && cvar_out, "mcp_quantiles: NULL argument");
     MCP_REQUIRE(h, values || n == 0, "mcp_quantiles: values is NULL");
     MCP_REQUIRE(h, n_alphas >= 1 && n_alphas <= MCP_MAX_ALPHAS, "mcp_quantiles: n_alphas=%d out of range [1, %d]", n_alphas, MCP_MAX_ALPHAS);
@@ -424,6 +423,14 @@ int mcp_quantiles(mcp_handle h, const void* values, int space, int dtype, uint64
     }
     h->last_ms = ms_total;
     return MCP_OK;
+}
+
+int mcp_quantiles(mcp_handle h, const void* values, int space, int dtype, uint64_t n, uint64_t n_total,
+                  const double* alphas, int n_alphas, double* var_out, double* cvar_out,
+                  mcp_allreduce_fn allreduce, void* user) {
+    if (!h) return MCP_ERR_INVALID;
+    return mcp_guarded(h, "mcp_quantiles",
+                       [&] { return quantiles_impl(h, values, space, dtype, n, n_total, alphas, n_alphas, var_out, cvar_out, allreduce, user); });
 }
 
 int mcp_set_allreduce_stream_ordered(mcp_handle h, int on) {

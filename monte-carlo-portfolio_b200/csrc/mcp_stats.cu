@@ -131,9 +131,8 @@ __global__ void __launch_bounds__(32) asset_stats_kernel(const double* __restric
 
 using namespace mcp;
 
-extern "C" int mcp_asset_stats(mcp_handle h, const double* returns_host, int n_periods, int n_assets, double risk_free,
-                               double annual_factor, double alpha, double* stats_out) {
-    if (!h) return MCP_ERR_INVALID;
+static int asset_stats_impl(mcp_handle h, const double* returns_host, int n_periods, int n_assets, double risk_free,
+                            double annual_factor, double alpha, double* stats_out) {
     MCP_REQUIRE(h, returns_host && stats_out, "mcp_asset_stats: NULL argument");
     MCP_REQUIRE(h, n_periods >= 1 && n_assets >= 1, "mcp_asset_stats: empty returns matrix");
     MCP_REQUIRE(h, annual_factor > 0 && alpha >= 0 && alpha <= 1, "mcp_asset_stats: bad annual_factor / alpha");
@@ -157,4 +156,10 @@ extern "C" int mcp_asset_stats(mcp_handle h, const double* returns_host, int n_p
     MCP_CUDA(h, cudaMemcpyAsync(stats_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
     MCP_CUDA(h, cudaStreamSynchronize(st));
     return MCP_OK;
+}
+
+extern "C" int mcp_asset_stats(mcp_handle h, const double* returns_host, int n_periods, int n_assets, double risk_free,
+                               double annual_factor, double alpha, double* stats_out) {
+    if (!h) return MCP_ERR_INVALID;
+    return mcp_guarded(h, "mcp_asset_stats", [&] { return asset_stats_impl(h, returns_host, n_periods, n_assets, risk_free, annual_factor, alpha, stats_out); });
 }
