@@ -358,14 +358,16 @@ def run_ours(args):
                                                                "settle at the sustained figure, profiles/r1h_scale_check.txt)"
         env_line["roofline"]["frac"] = env_line["roofline"]["achieved"] / tpeak["bf16_tflops"]
         env_line["roofline"]["fp32_equivalent_vs_ffma_peak"] = env_line["roofline"]["fp32_equivalent_tflops"] / fma_peak
-    roofline = {"bound": "fp32-simt", "kernel": "small_sweep_packed<16,4> (Philox, FFMA2, no write-back)", "achieved": achieved,
+    roofline = {"bound": "fp32-simt", "kernel": "small_sweep_packed<16,4,OUT=false> (Philox, FFMA2, no write-back)", "achieved": achieved,
                 "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak, "traffic": traffic,
                 "peak_source": "FFMA-chain microbenchmark (mcp_measure_fma_peak), best of 5 runs in this process; "
                                "MEASURED_PEAKS.json has no SIMT figure",
                 "algorithmic_flop_per_portfolio": flops_per_portfolio(n), "portfolios_per_launch": my_count,
                 "kernel_ms": kernel_s * 1e3,
                 "note": "RNG mode without write-back does 0 algorithmic HBM bytes; Philox (IMAD) and lg2 (MUFU) work "
-                        "is not counted as flops"}
+                        "is not counted as flops, but Philox's IMAD.WIDE runs on the same FP32 pipe: ncu measures that pipe "
+                        "61.5 % busy for this kernel (profiles/r1m_summary.md, sm__pipe_fma_cycles_active), two thirds of it FFMA2",
+                "ncu_fp32_pipe_busy_pct": 61.5}
     # quantile stage of the last path step: 3 radix passes + 1 tail pass over 4-byte values
     xq = torch.randn(my_paths, device="cuda")
     for _ in range(3):
