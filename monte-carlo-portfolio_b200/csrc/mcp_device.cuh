@@ -38,6 +38,29 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// The same generator with the ten round keys precomputed on the host (kernel parameter block -> constant-bank LOP3 operands).
+struct PhiloxKeys {
+    uint32_t k[20];                      // k[2r] = k0 + r W0, k[2r+1] = k1 + r W1
+};
+inline void philox_keys_fill(PhiloxKeys& pk, uint64_t seed) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { pk.k[2 * r] = k0; pk.k[2 * r + 1] = k1; k0 += PHILOX_W0; k1 += PHILOX_W1; }
+}
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& pk, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
+        const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ pk.k[2 * r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ pk.k[2 * r + 1];
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
 // FP32 streams spend 24 bits per uniform instead of a whole 32-bit word: uniform field i of a row is
 // bits [24 i, 24 i + 23) of the concatenation of its stream's Philox blocks 0, 1, 2, ... (word 0 of block 0
 // lowest).  Four fields share three words, so 16 uniforms cost 3 Philox calls instead of 4 (+11 % on the
@@ -61,6 +84,21 @@ __device__ __forceinline__ void philox_fields(uint32_t c0, uint32_t c1, uint32_t
     for (int b = 0; b < NB; ++b) {
         uint32_t x[4];
         philox4x32_10(c0, c1, c2, c3 + (uint32_t)b, k0, k1, x);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[4 * b + k] = x[k];
+    }
+#pragma unroll
+    for (int t = 0; t < NF / 4; ++t) fields_from_triple(w[3 * t], w[3 * t + 1], w[3 * t + 2], &f[4 * t]);
+}
+template <int NF>
+__device__ __forceinline__ void philox_fields(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& pk, uint32_t (&f)[NF]) {
+    static_assert(NF % 4 == 0, "fields come in groups of four");
+    constexpr int NB = philox_blocks_for_fields(NF);
+    uint32_t w[4 * NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        uint32_t x[4];
+        philox4x32_10(c0, c1, c2, c3 + (uint32_t)b, pk, x);
 #pragma unroll
         for (int k = 0; k < 4; ++k) w[4 * b + k] = x[k];
     }

@@ -83,6 +83,7 @@ struct TcArgs {
     uint64_t first, P;
     int n, np;
     uint32_t k0, k1;
+    PhiloxKeys rk;
     float rf, target;
     float qscale;                            // FP16 split: S' is stored times a power of two, q comes back times that; this undoes it
 };
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(TcCfg<F16>::THREADS, 1) large_sweep_tc(const T
                 } else {
                     // ---- Philox: 24-bit fields 32c .. 32c+31 = blocks 6c .. 6c+5; l = lg2(U) = -e ----
                     uint32_t f[TC_KC];
-                    philox_fields<TC_KC>(c0, c1, 0u, STREAM_WEIGHTS | (uint32_t)(6 * c), a.k0, a.k1, f);
+                    philox_fields<TC_KC>(c0, c1, 0u, STREAM_WEIGHTS | (uint32_t)(6 * c), a.rk, f);
 #pragma unroll
                     for (int j = 0; j < TC_KC; j += 2) {          // U = 2 - f in (0, 1], two per FFMA2 (same values as unit_open0)
                         const float2 m2 = make_float2(__uint_as_float(mant_or(f[j], one_bits)), __uint_as_float(mant_or(f[j + 1], one_bits)));
@@ -645,6 +646,7 @@ int pf_large_launch_tc(mcp_context* h, PfJob& job) {
     a.acc_out = job.acc_out; a.cands = job.cands; a.n_accepted = job.n_accepted;
     a.first = job.first; a.P = job.P; a.n = n; a.np = np;
     a.k0 = (uint32_t)job.seed; a.k1 = (uint32_t)(job.seed >> 32);
+    philox_keys_fill(a.rk, job.seed);
     a.rf = (float)job.rf; a.target = (float)job.target;
     a.qscale = (float)qscale;
     MCP_CHECK(f16 ? tc_launch<true>(h, job, a, table_bytes) : tc_launch<false>(h, job, a, table_bytes));

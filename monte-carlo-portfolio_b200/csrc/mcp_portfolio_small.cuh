@@ -32,6 +32,7 @@ struct SmallArgs {
     int n;                      // real asset count (<= NP); padded assets carry weight 0
     int max_tries, keep_last;
     uint32_t k0, k1;            // Philox key = seed
+    PhiloxKeys rk;              // its ten round keys (packed kernel: constant-bank LOP3 operands instead of 18 UIADD3 per tile)
     uint64_t first, P;
     const T* w_in;
     T* w_out;
@@ -410,8 +411,8 @@ __global__ void __launch_bounds__(PF_BLOCK) small_sweep_packed(const __grid_cons
             const uint64_t ga = a.first + local0 + (uint64_t)(2 * kp) * PF_BLOCK, gb = ga + PF_BLOCK;
             s2[kp] = make_float2(0.f, 0.f);
             uint32_t fa[NP], fb[NP];
-            philox_fields<NP>((uint32_t)ga, (uint32_t)(ga >> 32), 0u, STREAM_WEIGHTS, a.k0, a.k1, fa);
-            philox_fields<NP>((uint32_t)gb, (uint32_t)(gb >> 32), 0u, STREAM_WEIGHTS, a.k0, a.k1, fb);
+            philox_fields<NP>((uint32_t)ga, (uint32_t)(ga >> 32), 0u, STREAM_WEIGHTS, a.rk, fa);
+            philox_fields<NP>((uint32_t)gb, (uint32_t)(gb >> 32), 0u, STREAM_WEIGHTS, a.rk, fb);
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
                 const float2 f = make_float2(__uint_as_float(mant_or(fa[i], one_bits)), __uint_as_float(mant_or(fb[i], one_bits)));
@@ -626,6 +627,7 @@ static void fill_small_args(const PfJob& job, SmallArgs<T, NP>& a) {
     a.keep_last = job.keep_last;
     a.k0 = (uint32_t)job.seed;
     a.k1 = (uint32_t)(job.seed >> 32);
+    philox_keys_fill(a.rk, job.seed);
     a.first = job.first;
     a.P = job.P;
     a.w_in = (const T*)job.w_in;
