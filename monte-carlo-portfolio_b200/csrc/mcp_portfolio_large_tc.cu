@@ -35,9 +35,10 @@
 //   warps 4G..4G+3  epilogue + finaliser: per chunk, tcgen05.ld the 32 finished accumulator columns and the chunk's
 //                   stage (FP16: E itself; TF32: l = hi + lo exactly), release the stage, accumulate q, sum l, l.mu; per tile compute
 //                   return / risk / Sharpe (app.py:708-711), track the selections, write the arrays.
-// Measured on B200 (N = 256, FP16 split): 4.2e9 portfolios/s in a 50 ms launch, 3.7e9 in the 10^9-portfolio envelope step (TF32 split:
+// Measured on B200 (N = 256, FP16 split): 4.3e9 portfolios/s in a 50 ms launch, 3.8e9 in the 10^9-portfolio envelope step (TF32 split:
 // 3.6 / 3.1e9; SIMT kernel 5.9e8).  The kernel is bound by the SIMT issue of the generator warps (ncu: issue 59 %, ALU pipe 49 %,
-// tensor pipe 39 %): what moved it were instruction counts (DESIGN.md section 4 has the history and the ablations).
+// tensor pipe 39 %): what moved it were instruction counts -- one-LOP3 field masks, Philox round keys precomputed on the host (TcArgs::rk),
+// the fused MMA issue (DESIGN.md section 4 has the history and the ablations).
 // The Philox counter layout and the 24-bit uniform fields are those of every other FP32 sweep kernel (global index /
 // attempt 0 / block; mcp_device.cuh), so the weights are the same portfolios the SIMT kernels and oracle/philox_np.py produce.
 #include <algorithm>
