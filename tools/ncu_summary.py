@@ -70,7 +70,11 @@ def main():
             fh.write(open(launches).read())
     lines += ["## Per-kernel metrics (first launch of each distinct kernel / size)", ""]
     seen = set()
-    for r in rows[2:]:
+    # some launches come back with only the timing pass (every other metric -nan): prefer a fully measured launch
+    probe = "smsp__issue_active.avg.pct_of_peak_sustained_active"
+    full = [r for r in rows[2:] if probe not in idx or "nan" not in r[idx[probe]]]
+    partial = [r for r in rows[2:] if r not in full]
+    for r in full + partial:
         key = (r[idx["Kernel Name"]], r[idx["gpu__time_duration.sum"]][:3])
         if key in seen:
             continue
