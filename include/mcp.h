@@ -13,8 +13,10 @@
  *     mcp_last_error(handle) returns the message of the last failure on that handle.
  *   - ownership: the caller allocates and frees every input / output buffer; the library
  *     owns only handle-internal scratch.  `space` says whether array arguments are host
- *     pointers (the library stages them through pinned buffers and copies inside the
- *     call) or device pointers on the handle's device (no copies).
+ *     pointers (copies inside the call: page-locked buffers -- mcp_host_alloc -- are copied
+ *     directly; pageable ones are staged through the handle's pinned double buffers, a host
+ *     memcpy of chunk c overlapping the DMA of chunk c+1) or device pointers on the
+ *     handle's device (no copies).
  *   - threading: one handle per device; a handle is not re-entrant.  Work is ordered on
  *     the handle's stream (mcp_set_stream) and every call returns after its results are
  *     complete (synchronous from the caller's view).
@@ -32,13 +34,14 @@
 extern "C" {
 #endif
 
-#define MCP_ABI_VERSION 1
+#define MCP_ABI_VERSION 2
 
 #define MCP_OK               0
 #define MCP_ERR_INVALID     (-1)  /* bad argument / unsupported shape          */
 #define MCP_ERR_CUDA        (-2)  /* CUDA runtime failure (message has detail) */
 #define MCP_ERR_NUMERIC     (-3)  /* Sigma not positive definite (Cholesky)    */
 #define MCP_ERR_NOMEM       (-4)
+#define MCP_ERR_COMM        (-5)  /* NCCL failure / no communicator (mcp_comm_*)   */
 
 #define MCP_F32 0
 #define MCP_F64 1
@@ -56,7 +59,10 @@ int         mcp_abi_version(void);
 int         mcp_create(int device, mcp_handle* out);
 int         mcp_destroy(mcp_handle h);
 const char* mcp_last_error(mcp_handle h);            /* h == NULL: last mcp_create failure */
-int         mcp_set_stream(mcp_handle h, void* cuda_stream);   /* NULL: handle-owned stream */
+/* NULL selects the handle's own stream, which is NON-BLOCKING: it does not synchronise with the legacy default stream
+ * (handle 0).  To order the library's work behind a caller that uses the legacy default stream (torch's default), pass
+ * cudaStreamLegacy ((void*)0x1), not 0.                                                                                */
+int         mcp_set_stream(mcp_handle h, void* cuda_stream);
 int         mcp_synchronize(mcp_handle h);
 /* pinned host memory for the HOST-space fast path (plain malloc'ed buffers also work) */
 int         mcp_host_alloc(size_t bytes, void** out);
@@ -92,13 +98,16 @@ typedef struct {
     int32_t  max_tries;         /* rejection tries per portfolio (app.py:701: 100)         */
     int32_t  keep_last;         /* 1: keep the last draw on exhaustion (app.py:277)        */
     int32_t  space;             /* MCP_HOST | MCP_DEVICE for weights_in and output arrays  */
-    int32_t  reserved;
+    int32_t  comm_merge;        /* 1: this call evaluates ONE RANK'S SHARD of a job; selections, counts, risk range and
+                                   envelope bins are merged across the handle's communicator (mcp_comm_init) inside
+                                   the call, so every rank returns the whole job's picks (arrays stay local)          */
     const void*   weights_in;      /* supplied-weights mode: [P, N] dtype; NULL = Philox   */
     const double* weights_recheck; /* optional FP64 copy of weights_in (same space) used to
                                       re-rank FP32 near-ties in FP64; NULL = off           */
     /* frontier envelope (replaces the scatter app.py:726-736 at scale); 0 bins = off      */
     int32_t  n_bins;
-    int32_t  reserved2;
+    int32_t  philox_rounds;     /* 0 or 10: Philox4x32-10 (the default, and the oracle's generator); 7: Philox4x32-7,
+                                   Random123's documented Crush-resistant minimum (a different, cheaper stream)       */
     double   risk_lo, risk_hi;
 } mcp_portfolio_params;
 
@@ -126,6 +135,10 @@ typedef struct {
     mcp_selection max_sharpe;      /* np.argmax(sharpe), first occurrence (app.py:672)      */
     mcp_selection target_risk;     /* argmin |risk - target|, first occurrence              */
     double   kernel_ms;            /* device time of the sweep kernel(s)                    */
+    uint64_t n_accepted_global;    /* = n_accepted, or the sum over ranks with comm_merge    */
+    int32_t  recheck_overflow;     /* weights_recheck: 1 = more FP32 near-ties than the screen holds were found and the
+                                      tie set was re-evaluated by a full FP64 pass instead (result still exact)      */
+    int32_t  reserved;
 } mcp_portfolio_out;
 
 /* Kernel selection (internal, by shape): N <= 32 register kernels (FP32 packed FFMA2 / FP64);
@@ -151,11 +164,36 @@ typedef struct {
     int32_t  space;             /* of normals_in and terminal_out                          */
     double   dt;
     const void* normals_in;     /* supplied-normals mode: [M, S, N] dtype; NULL = Philox   */
+    int32_t  philox_rounds;     /* 0 or 10 (default) | 7, as in mcp_portfolio_params       */
+    int32_t  reserved;
 } mcp_path_params;
 
+/* Kernel selection (internal): FP32 Philox paths with N <= 256 run on the tensor cores (tcgen05: the step's normals go to
+ * tensor memory as the A operand, L' sqrt(dt) is the B operand in shared memory, FP16 operand split with FP32
+ * accumulation; MCP_PATHS_TC=0 forces the SIMT kernels for A/B measurements); supplied normals, FP64 and the SIMT
+ * fallback use the thread-per-path register kernels (N <= 32) or the shared-memory kernel (N <= 256).                  */
 int mcp_paths(mcp_handle h, const mcp_path_params* params,
               const double* mu_host, const double* sigma_host, const double* weights_host,
               void* terminal_out, double* kernel_ms);
+
+/* Paths and their VaR / CVaR in ONE call (C4): the path kernel also fills the first radix histogram of the terminal
+ * values, the remaining select passes, the interpolation and the tail sums run back to back on the handle's stream and
+ * the results come back with a single copy.  terminal_out may be NULL (the values then live in library scratch).
+ * comm_merge = 1: `params` describes this rank's shard, n_total is the whole job's path count, and histograms / tail
+ * sums are all-reduced over the handle's communicator inside the call (exact global order statistics on every rank). */
+typedef struct {
+    int32_t  n_alphas;          /* 1..MCP_MAX_ALPHAS                                         */
+    int32_t  comm_merge;
+    uint64_t n_total;           /* global path count (ignored unless comm_merge)             */
+    double   alphas[MCP_MAX_ALPHAS];
+    double   var[MCP_MAX_ALPHAS];    /* out */
+    double   cvar[MCP_MAX_ALPHAS];   /* out */
+    double   kernel_ms;              /* out: path kernel                                     */
+    double   quantile_ms;            /* out: select + tail passes (incl. their all-reduces)  */
+} mcp_path_stats;
+int mcp_paths_stats(mcp_handle h, const mcp_path_params* params,
+                    const double* mu_host, const double* sigma_host, const double* weights_host,
+                    void* terminal_out, mcp_path_stats* stats);
 
 /* ---- VaR / CVaR ------------------------------------------------------------------------
  * app.py:258-263 conventions: VaR = np.percentile(x, (1-alpha)*100) (linear), CVaR =
@@ -164,6 +202,9 @@ int mcp_paths(mcp_handle h, const mcp_path_params* params,
  * `count` uint64 (kind 0) or double (kind 1) values that must be summed in place across
  * ranks; `n_total` is the global element count (= n when allreduce is NULL).             */
 typedef int (*mcp_allreduce_fn)(void* device_buffer, size_t count, int kind, void* user);
+/* pass this as `allreduce` to sum over the handle's own communicator (mcp_comm_init): NCCL all-reduces issued by the
+ * library on the handle's stream, always stream-ordered                                                              */
+#define MCP_ALLREDUCE_COMM ((mcp_allreduce_fn)(uintptr_t)1)
 /* By default the callback is SYNCHRONOUS: libmcp drains its stream before calling it and expects the sums to be
  * in place when it returns.  With mcp_set_allreduce_stream_ordered(h, 1) the caller promises that the callback only
  * ENQUEUES the reduction on the handle's stream (mcp_set_stream; e.g. an NCCL all-reduce on that stream): the radix
@@ -211,6 +252,11 @@ typedef struct {
     uint64_t first_index;
     double   alpha;             /* 0.95 (app.py:684)                                       */
     const void* weights_in;     /* [P, N] dtype                                            */
+    int32_t  negate;            /* 1: the arrays hold -var / -cvar, the app's metric (app.py:717)                     */
+    int32_t  recheck;           /* FP32 only, 1: portfolios whose FP32 VaR (CVaR) is within rounding of the best are
+                                   re-evaluated in FP64 (series, order statistics, tail mean) and the pick is the
+                                   FP64 argmax with the lowest index -- the index np.argmin(-var) returns on the
+                                   reference's FP64 values (app.py:673-674, 747)                                      */
 } mcp_hist_params;
 
 typedef struct {
@@ -233,6 +279,13 @@ int mcp_historical_var(mcp_handle h, const mcp_hist_params* params,
 int mcp_asset_stats(mcp_handle h, const double* returns_host, int n_periods, int n_assets, double risk_free,
                     double annual_factor, double alpha, double* stats_out);
 
+/* ---- mu / Sigma estimation (app.py:679-680): mu = mean(R) * A, Sigma = cov(R, ddof = 1) * A ----------------------------
+ * returns_host: [T, N] FP64 row-major (the app's returns_df, leading fillna(0) row included); mu_out: N, sigma_out: N x N
+ * (symmetric), host FP64.  FP64 on the device: one CTA per (i, j >= i) column pair, two-pass (means first).  T = 1 gives
+ * NaN covariances, as pandas does.                                                                                      */
+int mcp_moments(mcp_handle h, const double* returns_host, int n_periods, int n_assets, double annual_factor,
+                double* mu_out, double* sigma_out);
+
 /* ---- frontier envelope of metrics that are already on the device ------------------------
  * Bins n (risk, return) pairs (DEVICE arrays of `dtype`; NaN rows = skipped portfolios are ignored)
  * exactly like mcp_portfolios does with n_bins > 0: K equal risk bins over [risk_lo, risk_hi], per bin
@@ -244,6 +297,33 @@ int mcp_asset_stats(mcp_handle h, const double* returns_host, int n_periods, int
 int mcp_envelope_arrays(mcp_handle h, int dtype, const void* risks_dev, const void* returns_dev, uint64_t n,
                         uint64_t first_index, double risk_lo, double risk_hi, int n_bins,
                         double* bin_best_return, uint64_t* bin_best_index);
+
+/* ---- multi-GPU: one NCCL communicator per handle (one handle per GPU) --------------------------------------------------
+ * The path shards by index range (first_index / n_portfolios, first_index / n_paths); the Philox counter is the GLOBAL
+ * index, so the union over ranks is the same set of portfolios / paths for any rank count.  Only results cross NVLink:
+ * selection records (all-gather), radix-select histograms and tail sums (all-reduce), risk ranges, envelope bins -- all
+ * issued by the library on the handle's stream when an entry point is called with comm_merge = 1 / MCP_ALLREDUCE_COMM.
+ * NCCL (libnccl.so.2) is bound at run time; a process that never calls mcp_comm_* does not need it.
+ *   one process per GPU : rank 0 calls mcp_comm_unique_id and ships the 128 bytes to the others (any transport), then
+ *                         every rank calls mcp_comm_init(handle, id, rank, nranks)        [ncclCommInitRank]
+ *   one process, n GPUs : mcp_comm_init_all(handles, n); then drive each handle from its own host thread
+ * After every host wait that follows a collective the library checks ncclCommGetAsyncError and returns MCP_ERR_COMM.   */
+#define MCP_COMM_ID_BYTES 128
+int mcp_comm_unique_id(void* id_out /* MCP_COMM_ID_BYTES */);
+int mcp_comm_init(mcp_handle h, const void* id, int rank, int nranks);
+int mcp_comm_init_all(mcp_handle* handles, int n);
+int mcp_comm_destroy(mcp_handle h);
+int mcp_comm_info(mcp_handle h, int* rank, int* nranks);          /* nranks = 0: no communicator */
+int mcp_comm_nccl_version(int* version);
+/* small host-buffer collectives for callers that merge their own results (e.g. envelope bins): every rank contributes
+ * `bytes` and receives nranks * bytes in rank order / reduces `count` 8-byte elements in place                          */
+#define MCP_REDUCE_U64_SUM 0
+#define MCP_REDUCE_F64_SUM 1
+#define MCP_REDUCE_F64_MIN 2
+#define MCP_REDUCE_F64_MAX 3
+#define MCP_REDUCE_U64_MAX 4
+int mcp_comm_allgather(mcp_handle h, const void* send_host, size_t bytes, void* recv_host);
+int mcp_comm_allreduce(mcp_handle h, void* inout_host, size_t count, int kind);
 
 /* ---- microbenchmarks used as roofline denominators (bench.py) ------------------------- */
 int mcp_measure_fma_peak(mcp_handle h, int dtype /* MCP_F32 | MCP_F64 | 2 = packed FP32x2 (FFMA2) */, double* tflops);

@@ -32,12 +32,14 @@ SMALL_NP = (4, 8, 16, 24, 32)
 def translation_units():
     """(object name, source, extra defines)"""
     tus = [("mcp_context", "mcp_context.cu", []),
+           ("mcp_comm", "mcp_comm.cu", []),
            ("mcp_portfolio", "mcp_portfolio.cu", []),
            ("mcp_portfolio_large", "mcp_portfolio_large.cu", []),
            ("mcp_portfolio_large_tc", "mcp_portfolio_large_tc.cu", []),
            ("mcp_envelope", "mcp_envelope.cu", []),
            ("mcp_recheck", "mcp_recheck.cu", []),
            ("mcp_paths", "mcp_paths.cu", []),
+           ("mcp_paths_tc", "mcp_paths_tc.cu", []),
            ("mcp_quantile", "mcp_quantile.cu", []),
            ("mcp_historical", "mcp_historical.cu", []),
            ("mcp_stats", "mcp_stats.cu", [])]
@@ -92,7 +94,7 @@ def _build_locked(force: bool, verbose: bool) -> str:
     tus = translation_units()
     with cf.ThreadPoolExecutor(max_workers=min(len(tus), os.cpu_count() or 4)) as ex:
         objs = list(ex.map(lambda t: _compile(t, verbose), tus))
-    cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-Xlinker", "--no-undefined"]
+    cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-ldl", "-Xlinker", "--no-undefined"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

@@ -32,10 +32,31 @@ struct mcp_context {
     // device scratch (grow-only): [0] candidates/records, [1..2] pipeline slot inputs,
     // [3..4] pipeline slot outputs, [5] quantile histograms, [6] kernel constants, [7] replay,
     // [8] envelope bins, [9..10] envelope risk/return scratch per slot, [11] recheck rows,
-    // [12..13] 1/sum(e) per portfolio of the tcgen05 sweep (per stream)
-    mcp_scratch dev[14];
-    mcp_scratch pinned[4];
+    // [12..13] 1/sum(e) per portfolio of the tcgen05 sweep (per stream), [14] host-buffer collectives (mcp_comm_allgather /
+    // allreduce), [15] merge block of a sharded call (records, counts, bins: send + gathered), [16] terminal values of
+    // mcp_paths_stats when the caller does not want them, [17] first radix histogram filled by the path kernel,
+    // [18] mu / Sigma estimation (returns matrix, results), [19] historical recheck (candidate lists, FP64 rows)
+    mcp_scratch dev[20];
+    // pinned host scratch: [0..1] HOST-space staging of pageable outputs (per pipeline slot), [2] inputs, [3] collectives,
+    // [4] small results (records / stats) read back with one copy
+    mcp_scratch pinned[6];
+    // multi-GPU (mcp_comm.cu): NCCL communicator of this handle, null until mcp_comm_init
+    struct mcp_comm_state* comm = nullptr;
+    int comm_rank = 0, comm_size = 0;
 };
+
+// reduction kinds of mcp_comm_allreduce(_dev) -- values are part of the C ABI (include/mcp.h MCP_REDUCE_*)
+int mcp_comm_allgather_dev(mcp_context* h, const void* send_dev, void* recv_dev, size_t bytes, cudaStream_t st);
+int mcp_comm_allreduce_dev(mcp_context* h, void* buf_dev, size_t count, int kind, cudaStream_t st);
+int mcp_comm_check(mcp_context* h);
+void mcp_comm_release(mcp_context* h);
+
+// select + tail passes on device-resident values (mcp_quantile.cu); hist0_dev: optional pre-filled histogram of the first radix
+// digit (2048 uint64 counts of this shard, FP32 keys only)
+constexpr int MCP_SEL_BITS = 11;
+int mcp_quantiles_device(mcp_context* h, const void* v_dev, int dtype, uint64_t n, uint64_t n_total, const double* alphas, int n_alphas,
+                         double* var_out, double* cvar_out, mcp_allreduce_fn allreduce, void* user,
+                         const unsigned long long* hist0_dev, double* ms_out);
 
 int mcp_fail(mcp_context* h, int code, const char* fmt, ...);
 int mcp_dev_reserve(mcp_context* h, int slot, size_t bytes, void** out);

@@ -20,10 +20,14 @@ constexpr uint32_t STREAM_NORMALS = 2u << 24;
 // Philox4x32-10 (Salmon et al., SC'11).  The key schedule k + r*W is uniform across the
 // grid (seed is a kernel parameter), so it lives in uniform registers; each round costs two
 // IMAD.WIDE.U32 and two LOP3 per thread.
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+// The round count is a template parameter: 10 is the default everywhere (Random123's and cuRAND's choice, and the generator
+// oracle/philox_np.py restates); 7 is Random123's documented minimum that still passes BigCrush ("Crush-resistant"), offered as an
+// option (mcp_portfolio_params.philox_rounds) -- it is a different stream, not a cheaper way to the same numbers.
+template <int ROUNDS = 10>
+__device__ __forceinline__ void philox4x32_r(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                             uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < ROUNDS; ++r) {
         const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
         const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -37,6 +41,10 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+    philox4x32_r<10>(c0, c1, c2, c3, k0, k1, out);
+}
 
 // The same generator with the ten round keys precomputed on the host (kernel parameter block -> constant-bank LOP3 operands).
 struct PhiloxKeys {
@@ -46,9 +54,10 @@ inline void philox_keys_fill(PhiloxKeys& pk, uint64_t seed) {
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     for (int r = 0; r < 10; ++r) { pk.k[2 * r] = k0; pk.k[2 * r + 1] = k1; k0 += PHILOX_W0; k1 += PHILOX_W1; }
 }
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& pk, uint32_t (&out)[4]) {
+template <int ROUNDS = 10>
+__device__ __forceinline__ void philox4x32_r(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& pk, uint32_t (&out)[4]) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < ROUNDS; ++r) {
         const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
         const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ pk.k[2 * r];
@@ -59,6 +68,9 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
         c2 = n2;
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& pk, uint32_t (&out)[4]) {
+    philox4x32_r<10>(c0, c1, c2, c3, pk, out);
 }
 
 // FP32 streams spend 24 bits per uniform instead of a whole 32-bit word: uniform field i of a row is
@@ -75,7 +87,7 @@ __device__ __forceinline__ void fields_from_triple(uint32_t a, uint32_t b, uint3
 __host__ __device__ constexpr int philox_blocks_for_fields(int nf) { return (3 * ((nf + 3) / 4) + 3) / 4; }
 
 // NF fields (multiple of 4) that start at a block boundary: field 0 = bit 0 of block `c3 & 0xffffff`.
-template <int NF>
+template <int NF, int ROUNDS = 10>
 __device__ __forceinline__ void philox_fields(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t (&f)[NF]) {
     static_assert(NF % 4 == 0, "fields come in groups of four");
     constexpr int NB = philox_blocks_for_fields(NF);
@@ -83,14 +95,14 @@ __device__ __forceinline__ void philox_fields(uint32_t c0, uint32_t c1, uint32_t
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         uint32_t x[4];
-        philox4x32_10(c0, c1, c2, c3 + (uint32_t)b, k0, k1, x);
+        philox4x32_r<ROUNDS>(c0, c1, c2, c3 + (uint32_t)b, k0, k1, x);
 #pragma unroll
         for (int k = 0; k < 4; ++k) w[4 * b + k] = x[k];
     }
 #pragma unroll
     for (int t = 0; t < NF / 4; ++t) fields_from_triple(w[3 * t], w[3 * t + 1], w[3 * t + 2], &f[4 * t]);
 }
-template <int NF>
+template <int NF, int ROUNDS = 10>
 __device__ __forceinline__ void philox_fields(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& pk, uint32_t (&f)[NF]) {
     static_assert(NF % 4 == 0, "fields come in groups of four");
     constexpr int NB = philox_blocks_for_fields(NF);
@@ -98,7 +110,7 @@ __device__ __forceinline__ void philox_fields(uint32_t c0, uint32_t c1, uint32_t
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         uint32_t x[4];
-        philox4x32_10(c0, c1, c2, c3 + (uint32_t)b, pk, x);
+        philox4x32_r<ROUNDS>(c0, c1, c2, c3 + (uint32_t)b, pk, x);
 #pragma unroll
         for (int k = 0; k < 4; ++k) w[4 * b + k] = x[k];
     }

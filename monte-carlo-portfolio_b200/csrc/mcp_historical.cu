@@ -57,6 +57,7 @@ struct HistArgs {
     int n, T_, t_pad;
     int k_lo, k_hi;         // 0-based order statistics
     T gamma;                // interpolation weight
+    T out_sign;             // +1, or -1 when the arrays hold the app's metric -var / -cvar (app.py:717); picks use the unsigned values
 };
 
 template <typename T> __device__ __forceinline__ T warp_sum(T v) {
@@ -175,8 +176,8 @@ __global__ void __launch_bounds__(HV_BLOCK) hist_var_kernel(const HistArgs<T> a)
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         const T cvar = cnt > 0 ? s / (T)cnt : var;
         if (lane == 0) {
-            if (a.var_out) a.var_out[p] = var;
-            if (a.cvar_out) a.cvar_out[p] = cvar;
+            if (a.var_out) a.var_out[p] = a.out_sign * var;
+            if (a.cvar_out) a.cvar_out[p] = a.out_sign * cvar;
         }
         const uint64_t g = a.first + p;
         if (var > best_v) { best_v = var; idx_v = g; }          // p ascends per warp: first occurrence kept
@@ -350,8 +351,8 @@ __global__ void __launch_bounds__(HV_BLOCK) hist_var_fast(const HistArgs<float> 
             const uint64_t p = p0 + (uint64_t)pp;
             if (p < a.P) {
                 if (lane == 0) {
-                    if (a.var_out) a.var_out[p] = var;
-                    if (a.cvar_out) a.cvar_out[p] = cvar;
+                    if (a.var_out) a.var_out[p] = a.out_sign * var;
+                    if (a.cvar_out) a.cvar_out[p] = a.out_sign * cvar;
                 }
                 const uint64_t g = a.first + p;
                 if (var > best_v) { best_v = var; idx_v = g; }          // p ascends per warp: first occurrence kept
@@ -430,63 +431,122 @@ static int hist_dispatch(mcp_context* h, const HistArgs<T>& a, size_t smem, int 
     return mcp_fail(h, MCP_ERR_INVALID, "mcp_historical_var: n_periods=%d exceeds the supported maximum of 2048", a.T_);
 }
 
+// ---- FP32 near-tie recheck of the 'VaR' / 'CVaR' picks (mcp_hist_params.recheck) --------------------------------------------
+// np.argmin(-var) on the reference's FP64 values (app.py:673-674, 747) can land on another row than the FP32 argmax when two
+// portfolios' VaR differ by less than FP32 rounding.  The FP32 pass screens: every row whose value is within a rounding
+// tolerance of the best is recorded, those few rows are re-evaluated in FP64 (series, order statistics, tail mean: the plain
+// kernel in double) and the pick is the FP64 maximum with the lowest index.
+__global__ void __launch_bounds__(256) hv_collect(const float* __restrict__ var, const float* __restrict__ cvar, uint64_t n, uint64_t base,
+                                                  const PfCand* __restrict__ fin, float sign, float tol, RcLists* lists) {
+    const PfCand f = *fin;
+    if (f.idx_s == MCP_NO_INDEX) return;
+    const float thr_v = (float)f.key_s - tol, thr_c = (float)f.key_d - tol;
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256) {
+        const float v = sign * var[i], c = sign * cvar[i];
+        if (v >= thr_v) {
+            const unsigned slot = atomicAdd(&lists->count[0], 1u);
+            if (slot < RC_CAP) { lists->idx[0][slot] = base + i; lists->key[0][slot] = v; }
+        }
+        if (c >= thr_c) {
+            const unsigned slot = atomicAdd(&lists->count[1], 1u);
+            if (slot < RC_CAP) { lists->idx[1][slot] = base + i; lists->key[1][slot] = c; }
+        }
+    }
+}
+
+// rows[k][:] = (double) w[idx[k] - base][:]
+__global__ void __launch_bounds__(256) hv_gather_rows(const float* __restrict__ w, const unsigned long long* __restrict__ idx, uint64_t base,
+                                                      int count, int n, double* __restrict__ rows) {
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < count * n; e += gridDim.x * 256) {
+        const int k = e / n, i = e - k * n;
+        rows[e] = (double)w[(idx[k] - base) * (uint64_t)n + (uint64_t)i];
+    }
+}
+
+// transposed, padded copy of R in the kernel's arithmetic type at `dst` (device); returns the padded period count
 template <typename T>
-static int hist_run(mcp_context* h, const mcp_hist_params* p, const double* R, mcp_hist_out* out) {
-    const int n = p->n_assets, Tn = p->n_periods;
-    const uint64_t P = p->n_portfolios;
-    cudaStream_t st = h->stream;
-    const int vpl = (Tn + 31) / 32;
-    MCP_REQUIRE(h, vpl <= 64, "mcp_historical_var: n_periods=%d exceeds the supported maximum of 2048", Tn);
-    // padded lanes read columns up to 32 * VPL_template; pad to the dispatch bucket
-    int bucket = 64;
-    for (int v : {1, 2, 4, 8, 12, 16, 24, 32, 64}) if (vpl <= v) { bucket = v; break; }
-    const int tp = 32 * bucket;
+static int hist_upload_r(mcp_context* h, const double* R, int n, int Tn, T* dst, int tp, cudaStream_t st) {
     std::vector<T> rt((size_t)n * tp, (T)0);
     for (int t = 0; t < Tn; ++t)
         for (int i = 0; i < n; ++i) rt[(size_t)i * tp + t] = (T)R[(size_t)t * n + i];
-    const size_t smem = ((size_t)n * tp + (size_t)HV_WARPS * n) * sizeof(T);
-    MCP_REQUIRE(h, smem <= h->prop.sharedMemPerBlockOptin, "mcp_historical_var: T=%d x N=%d needs %zu B of shared memory (max %zu)",
-                Tn, n, smem, (size_t)h->prop.sharedMemPerBlockOptin);
+    MCP_CUDA(h, cudaMemcpyAsync(dst, rt.data(), rt.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    MCP_CUDA(h, cudaStreamSynchronize(st));               // `rt` is pageable and dies at scope exit
+    return MCP_OK;
+}
 
-    const int max_blocks = h->prop.multiProcessorCount * 16;
-    unsigned char* base = nullptr;
-    const size_t off_rt = sizeof(PfCand) * (size_t)(max_blocks + 1);
-    MCP_CHECK(mcp_dev_reserve(h, 0, off_rt + rt.size() * sizeof(T) + 256, (void**)&base));
-    PfCand* cands = (PfCand*)base;
-    PfCand* fin = cands + max_blocks;
-    T* d_rt = (T*)(base + (off_rt + 255) / 256 * 256);
-    MCP_CUDA(h, cudaMemcpyAsync(d_rt, rt.data(), rt.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+static int hist_bucket(int Tn) {
+    const int vpl = (Tn + 31) / 32;
+    for (int v : {1, 2, 4, 8, 12, 16, 24, 32, 64}) if (vpl <= v) return v;
+    return 64;
+}
 
-    const T* d_w = (const T*)p->weights_in;
-    T* d_var = (T*)out->var;
-    T* d_cvar = (T*)out->cvar;
-    if (p->space == MCP_HOST) {
-        void* q = nullptr;
-        MCP_CHECK(mcp_dev_reserve(h, 1, P * n * sizeof(T), &q));
-        MCP_CUDA(h, cudaMemcpyAsync(q, p->weights_in, P * n * sizeof(T), cudaMemcpyHostToDevice, st));
-        d_w = (const T*)q;
-        if (out->var || out->cvar) {
-            MCP_CHECK(mcp_dev_reserve(h, 3, 2 * P * sizeof(T), &q));
-            d_var = out->var ? (T*)q : nullptr;
-            d_cvar = out->cvar ? (T*)q + P : nullptr;
-        }
-    }
+// one pass of the historical kernel over device rows; leaves ev[0] / ev[1] around the kernel and the merged candidate in *fin
+template <typename T>
+static int hist_exec(mcp_context* h, const T* d_w, T* d_var, T* d_cvar, uint64_t P, uint64_t first, int n, int Tn, int tp, double alpha,
+                     T out_sign, const T* d_rt, PfCand* cands, PfCand* fin, int max_blocks, cudaStream_t st) {
     // order statistics of np.percentile(x, (1-alpha)*100), 'linear': h = (T-1) q  (app.py:259)
-    const double percent = (1 - p->alpha) * 100, q = percent / 100.0, hidx = (double)(Tn - 1) * q;
+    const double percent = (1 - alpha) * 100, q = percent / 100.0, hidx = (double)(Tn - 1) * q;
     int k_lo, k_hi;
     if (hidx >= (double)(Tn - 1)) k_lo = k_hi = Tn - 1;
     else if (hidx < 0) k_lo = k_hi = 0;
     else { k_lo = (int)std::floor(hidx); k_hi = k_lo + 1; }
     HistArgs<T> a;
     a.w_in = d_w; a.r_t = d_rt; a.var_out = d_var; a.cvar_out = d_cvar; a.cands = cands;
-    a.first = p->first_index; a.P = P; a.n = n; a.T_ = Tn; a.t_pad = tp;
-    a.k_lo = k_lo; a.k_hi = k_hi; a.gamma = (T)(hidx - std::floor(hidx));
+    a.first = first; a.P = P; a.n = n; a.T_ = Tn; a.t_pad = tp;
+    a.k_lo = k_lo; a.k_hi = k_hi; a.gamma = (T)(hidx - std::floor(hidx)); a.out_sign = out_sign;
+    const size_t smem = ((size_t)n * tp + (size_t)HV_WARPS * n) * sizeof(T);
+    MCP_REQUIRE(h, smem <= h->prop.sharedMemPerBlockOptin, "mcp_historical_var: T=%d x N=%d needs %zu B of shared memory (max %zu)",
+                Tn, n, smem, (size_t)h->prop.sharedMemPerBlockOptin);
     int blocks = 0;
     MCP_CUDA(h, cudaEventRecord(h->ev[0], st));
     MCP_CHECK(hist_dispatch<T>(h, a, smem, max_blocks, &blocks, st));
     MCP_CUDA(h, cudaEventRecord(h->ev[1], st));
-    MCP_CHECK(pf_reduce_launch(h, cands, blocks, fin, 0, st));
-    if (p->space == MCP_HOST) {
+    return pf_reduce_launch(h, cands, blocks, fin, 0, st);
+}
+
+template <typename T>
+static int hist_run(mcp_context* h, const mcp_hist_params* p, const double* R, mcp_hist_out* out) {
+    const int n = p->n_assets, Tn = p->n_periods;
+    const uint64_t P = p->n_portfolios;
+    cudaStream_t st = h->stream;
+    MCP_REQUIRE(h, (Tn + 31) / 32 <= 64, "mcp_historical_var: n_periods=%d exceeds the supported maximum of 2048", Tn);
+    const int tp = 32 * hist_bucket(Tn);        // padded lanes read columns up to 32 * VPL_template: pad to the dispatch bucket
+    const bool recheck = sizeof(T) == 4 && p->recheck != 0;
+
+    const int max_blocks = h->prop.multiProcessorCount * 16;
+    unsigned char* base = nullptr;
+    const size_t off_rt = sizeof(PfCand) * (size_t)(max_blocks + 1);
+    MCP_CHECK(mcp_dev_reserve(h, 0, off_rt + (size_t)n * tp * sizeof(T) + 256, (void**)&base));
+    PfCand* cands = (PfCand*)base;
+    PfCand* fin = cands + max_blocks;
+    T* d_rt = (T*)(base + (off_rt + 255) / 256 * 256);
+    MCP_CHECK(hist_upload_r<T>(h, R, n, Tn, d_rt, tp, st));
+
+    const T* d_w = (const T*)p->weights_in;
+    T* d_var = (T*)out->var;
+    T* d_cvar = (T*)out->cvar;
+    const bool stage = p->space == MCP_HOST;
+    if (stage) {
+        void* q = nullptr;
+        MCP_CHECK(mcp_dev_reserve(h, 1, P * n * sizeof(T), &q));
+        MCP_CUDA(h, cudaMemcpyAsync(q, p->weights_in, P * n * sizeof(T), cudaMemcpyHostToDevice, st));
+        d_w = (const T*)q;
+    }
+    if (stage || (recheck && !(out->var && out->cvar))) {
+        // device copies of the arrays: HOST space always, DEVICE space when the recheck needs values the caller did not ask for
+        void* q = nullptr;
+        MCP_CHECK(mcp_dev_reserve(h, 3, 2 * P * sizeof(T), &q));
+        if (stage) {
+            d_var = (out->var || recheck) ? (T*)q : nullptr;
+            d_cvar = (out->cvar || recheck) ? (T*)q + P : nullptr;
+        } else {
+            if (!d_var) d_var = (T*)q;
+            if (!d_cvar) d_cvar = (T*)q + P;
+        }
+    }
+    const T sign = p->negate ? (T)-1 : (T)1;
+    MCP_CHECK(hist_exec<T>(h, d_w, d_var, d_cvar, P, p->first_index, n, Tn, tp, p->alpha, sign, d_rt, cands, fin, max_blocks, st));
+    if (stage) {
         if (out->var) MCP_CUDA(h, cudaMemcpyAsync(out->var, d_var, P * sizeof(T), cudaMemcpyDeviceToHost, st));
         if (out->cvar) MCP_CUDA(h, cudaMemcpyAsync(out->cvar, d_cvar, P * sizeof(T), cudaMemcpyDeviceToHost, st));
     }
@@ -501,6 +561,59 @@ static int hist_run(mcp_context* h, const mcp_hist_params* p, const double* R, m
     out->best_cvar = f.key_d;
     out->kernel_ms = ms;
     h->last_ms = ms;
+
+    if constexpr (sizeof(T) == 4) {
+        if (recheck && f.idx_s != MCP_NO_INDEX) {
+            double rmax = 0;
+            for (size_t i = 0; i < (size_t)Tn * n; ++i) rmax = std::max(rmax, std::fabs(R[i]));
+            // FP32 error of a series value: eps * sum_i |R_ti w_i| <= eps * max|R| * sum|w|; 64 ulps of headroom (sum|w| = 1 for
+            // Dirichlet weights, and the tail mean adds less than one ulp per term)
+            const float tol = (float)(5.96e-8 * 64 * (rmax + std::max(std::fabs(f.key_s), std::fabs(f.key_d))));
+            unsigned char* rb = nullptr;
+            const size_t rows_cap = (size_t)RC_CAP * n * sizeof(double);
+            const size_t off_rows = (sizeof(RcLists) + 255) / 256 * 256, off_vals = off_rows + (rows_cap + 255) / 256 * 256;
+            const size_t off_rt64 = off_vals + (size_t)2 * RC_CAP * sizeof(double) + 256;
+            const size_t off_c64 = off_rt64 + ((size_t)n * tp * sizeof(double) + 255) / 256 * 256;
+            MCP_CHECK(mcp_dev_reserve(h, 19, off_c64 + sizeof(PfCand) * (size_t)(max_blocks + 1) + 256, (void**)&rb));
+            RcLists* d_lists = (RcLists*)rb;
+            double* d_rows = (double*)(rb + off_rows);
+            double* d_vals = (double*)(rb + off_vals);
+            double* d_rt64 = (double*)(rb + off_rt64);
+            PfCand* c64 = (PfCand*)(rb + off_c64);
+            MCP_CUDA(h, cudaMemsetAsync(d_lists, 0, 16, st));
+            const uint64_t g = std::max<uint64_t>(1, std::min<uint64_t>((P + 255) / 256, (uint64_t)h->prop.multiProcessorCount * 8));
+            hv_collect<<<(unsigned)g, 256, 0, st>>>((const float*)d_var, (const float*)d_cvar, P, p->first_index, fin, (float)sign, tol, d_lists);
+            MCP_CUDA(h, cudaGetLastError());
+            h->launches++;
+            std::vector<unsigned char> raw(sizeof(RcLists));
+            MCP_CUDA(h, cudaMemcpyAsync(raw.data(), d_lists, sizeof(RcLists), cudaMemcpyDeviceToHost, st));
+            MCP_CUDA(h, cudaStreamSynchronize(st));
+            const RcLists* Lh = reinterpret_cast<const RcLists*>(raw.data());
+            bool r_up = false;
+            for (int c = 0; c < 2; ++c) {
+                if (Lh->count[c] <= 1) continue;                         // no near-tie: the FP32 pick stands
+                MCP_REQUIRE(h, Lh->count[c] <= RC_CAP, "mcp_historical_var: more than %u portfolios tie with the best %s within FP32 rounding; "
+                            "run with dtype = MCP_F64 for an exact pick", RC_CAP, c == 0 ? "VaR" : "CVaR");
+                std::vector<unsigned long long> idx(Lh->idx[c], Lh->idx[c] + Lh->count[c]);
+                std::sort(idx.begin(), idx.end());
+                const int cnt = (int)idx.size();
+                // the sorted indices go back into the list slot (device) for the gather
+                MCP_CUDA(h, cudaMemcpyAsync(d_lists->idx[c], idx.data(), sizeof(unsigned long long) * cnt, cudaMemcpyHostToDevice, st));
+                hv_gather_rows<<<std::max(1, std::min(1024, (cnt * n + 255) / 256)), 256, 0, st>>>((const float*)d_w, d_lists->idx[c], p->first_index, cnt, n, d_rows);
+                MCP_CUDA(h, cudaGetLastError());
+                h->launches++;
+                if (!r_up) { MCP_CHECK(hist_upload_r<double>(h, R, n, Tn, d_rt64, tp, st)); r_up = true; }
+                MCP_CHECK(hist_exec<double>(h, d_rows, d_vals, d_vals + RC_CAP, (uint64_t)cnt, 0, n, Tn, tp, p->alpha, 1.0, d_rt64, c64, c64 + max_blocks, max_blocks, st));
+                std::vector<double> vals((size_t)cnt);
+                MCP_CUDA(h, cudaMemcpyAsync(vals.data(), c == 0 ? d_vals : d_vals + RC_CAP, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+                MCP_CUDA(h, cudaStreamSynchronize(st));
+                int best = 0;
+                for (int k = 1; k < cnt; ++k) if (vals[k] > vals[best]) best = k;      // ascending index: first occurrence wins ties
+                if (c == 0) { out->best_var_index = idx[best]; out->best_var = vals[best]; }
+                else { out->best_cvar_index = idx[best]; out->best_cvar = vals[best]; }
+            }
+        }
+    }
     return MCP_OK;
 }
 

@@ -82,6 +82,24 @@ static int pf_replay(mcp_context* h, const PfJob& job, const PfReplay& rp) {
 
 using namespace mcp;
 
+// Is this host pointer page-locked (cudaHostAlloc / cudaHostRegister / managed)?  Pageable memory is staged.
+static bool host_is_pinned(const void* p) {
+    if (!p) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// larger key wins, ties go to the lower global index (numpy's first occurrence, app.py:672); NaN keys never win
+static bool record_better(double ka, uint64_t ia, double kb, uint64_t ib) {
+    if (ia == MCP_NO_INDEX || std::isnan(ka)) return false;
+    if (ib == MCP_NO_INDEX || std::isnan(kb)) return true;
+    return ka > kb || (ka == kb && ia < ib);
+}
+
 static void fill_selection(mcp_selection& sel, const double* rec, int n) {
     uint64_t idx;
     memcpy(&idx, &rec[0], 8);
@@ -101,6 +119,9 @@ static int portfolios_impl(mcp_handle h, const mcp_portfolio_params* p, const do
     MCP_REQUIRE(h, p->n_portfolios <= (1ull << 39), "mcp_portfolios: n_portfolios=%llu exceeds 2^39 per call; shard the range",
                 (unsigned long long)p->n_portfolios);
     MCP_REQUIRE(h, p->max_tries >= 1, "mcp_portfolios: max_tries must be >= 1");
+    MCP_REQUIRE(h, p->philox_rounds == 0 || p->philox_rounds == 10 || p->philox_rounds == 7,
+                "mcp_portfolios: philox_rounds=%d (supported: 10 = default, 7)", p->philox_rounds);
+    MCP_REQUIRE(h, !p->comm_merge || h->comm != nullptr, "mcp_portfolios: comm_merge needs a communicator on this handle (mcp_comm_init)");
     const int N = p->n_assets;
     for (int i = 0; i < N; ++i) {
         MCP_REQUIRE(h, std::isfinite(mu[i]), "mcp_portfolios: mean_returns[%d] is not finite", i);
@@ -110,8 +131,12 @@ static int portfolios_impl(mcp_handle h, const mcp_portfolio_params* p, const do
     const size_t es = p->dtype == MCP_F64 ? 8 : 4;
     const uint64_t P = p->n_portfolios;
     const bool supplied = p->weights_in != nullptr;
+    const bool empty = P == 0;             // only reachable with comm_merge: the rank still joins the collective
 
     out->n_accepted = 0;
+    out->n_accepted_global = 0;
+    out->recheck_overflow = 0;
+    out->reserved = 0;
     out->kernel_ms = 0;
     out->risk_min = out->risk_max = NAN;
     for (mcp_selection* s : {&out->max_sharpe, &out->target_risk}) {
@@ -126,7 +151,7 @@ static int portfolios_impl(mcp_handle h, const mcp_portfolio_params* p, const do
                     "mcp_portfolios: envelope needs finite risk_lo < risk_hi");
         for (int b = 0; b < K; ++b) { out->bin_best_return[b] = -INFINITY; out->bin_best_index[b] = MCP_NO_INDEX; }
     }
-    if (P == 0) return MCP_OK;          // empty arrays, no selection (app.py:719-722 on empty lists)
+    if (P == 0 && !p->comm_merge) return MCP_OK;          // empty arrays, no selection (app.py:719-722 on empty lists)
 
     // ---- scratch layout (device slot 0) ----
     const int max_blocks = h->prop.multiProcessorCount * 16;
@@ -186,6 +211,7 @@ static int portfolios_impl(mcp_handle h, const mcp_portfolio_params* p, const do
         }
     }
     job.seed = p->seed;
+    job.rounds = p->philox_rounds == 7 ? 7 : 10;
     job.rf = p->risk_free;
     job.target = p->risk_target;
     job.sigma = sigma;
@@ -206,7 +232,9 @@ static int portfolios_impl(mcp_handle h, const mcp_portfolio_params* p, const do
     double kernel_ms = 0;
     bool env_slot1 = false;
 
-    if (p->space == MCP_DEVICE) {
+    if (empty) {
+        // nothing to sweep on this rank: it still takes part in the merge below
+    } else if (p->space == MCP_DEVICE) {
         // one launch, unless the envelope needs (risk, return) scratch: then chunks of 2^26
         const bool s_ret = K > 0 && !out->returns, s_risk = (K > 0 || recheck) && !out->risks, s_sharpe = recheck && !out->sharpes;
         const bool any_scratch = s_ret || s_risk || s_sharpe;
@@ -243,8 +271,14 @@ static int portfolios_impl(mcp_handle h, const mcp_portfolio_params* p, const do
         const bool want_sharpe = out->sharpes != nullptr || recheck;
         const size_t out_row = (want_w ? (size_t)N * es : 0) + (want_ret ? es : 0) + (want_risk ? es : 0) +
                                (want_sharpe ? es : 0) + (out->accepted ? 1 : 0);
+        // Pageable caller memory is staged through the handle's pinned buffers (one per pipeline slot): the DMA of chunk c runs
+        // at full PCIe rate while the host memcpy of chunk c-1 into (or chunk c+1 out of) the caller's pages overlaps it.  Smaller
+        // chunks then, so that there is something to overlap with.  Page-locked buffers (mcp_host_alloc) are copied directly.
+        const bool stage_in = in_row && !host_is_pinned(p->weights_in);
+        const bool stage_out = out_row && !(host_is_pinned(out->weights) && host_is_pinned(out->returns) && host_is_pinned(out->risks) &&
+                                            host_is_pinned(out->sharpes) && host_is_pinned(out->accepted));
         uint64_t chunk = P;
-        const size_t budget = (size_t)96 << 20;            // bytes per slot and direction
+        const size_t budget = (stage_in || stage_out) ? (size_t)16 << 20 : (size_t)96 << 20;            // bytes per slot and direction
         if (in_row) chunk = std::min<uint64_t>(chunk, std::max<size_t>(budget / in_row, 1024));
         if (out_row) chunk = std::min<uint64_t>(chunk, std::max<size_t>(budget / out_row, 1024));
         chunk = (chunk + PF_BLOCK - 1) / PF_BLOCK * PF_BLOCK;
@@ -252,6 +286,18 @@ static int portfolios_impl(mcp_handle h, const mcp_portfolio_params* p, const do
         const uint64_t n_chunks = (P + chunk - 1) / chunk;
         bool used[2] = {false, false};
         bool timed[2] = {false, false};
+        // staged output of the chunk a slot carried last: copied to the caller's arrays once the slot's stream has drained
+        struct Pending { bool on = false; uint64_t r0 = 0, rows = 0; unsigned char *w = nullptr, *r = nullptr, *k = nullptr, *s = nullptr, *a = nullptr; } pend[2];
+        auto flush = [&](int s) {
+            Pending& q = pend[s];
+            if (!q.on) return;
+            if (q.w) memcpy((unsigned char*)out->weights + q.r0 * N * es, q.w, q.rows * N * es);
+            if (q.r) memcpy((unsigned char*)out->returns + q.r0 * es, q.r, q.rows * es);
+            if (q.k) memcpy((unsigned char*)out->risks + q.r0 * es, q.k, q.rows * es);
+            if (q.s) memcpy((unsigned char*)out->sharpes + q.r0 * es, q.s, q.rows * es);
+            if (q.a) memcpy(out->accepted + q.r0, q.a, q.rows);
+            q.on = false;
+        };
         for (uint64_t c = 0; c < n_chunks; ++c) {
             const int s = (int)(c & 1);
             cudaStream_t ss = n_chunks == 1 ? st : h->side_stream[s];
@@ -263,17 +309,30 @@ static int portfolios_impl(mcp_handle h, const mcp_portfolio_params* p, const do
                     MCP_CUDA(h, cudaEventElapsedTime(&ms, h->ev[2 * s], h->ev[2 * s + 1]));
                     kernel_ms += ms;
                 }
+                flush(s);
             }
             unsigned char* d_in = nullptr;
             unsigned char* d_out = nullptr;
             if (in_row) MCP_CHECK(mcp_dev_reserve(h, 1 + s, (size_t)chunk * in_row, (void**)&d_in));
             if (out_row) MCP_CHECK(mcp_dev_reserve(h, 3 + s, (size_t)chunk * (out_row + 16), (void**)&d_out));
-            if (in_row)
-                MCP_CUDA(h, cudaMemcpyAsync(d_in, (const unsigned char*)p->weights_in + r0 * in_row, rows * in_row,
-                                            cudaMemcpyHostToDevice, ss));
-            // carve the output slot
+            if (in_row) {
+                const unsigned char* src = (const unsigned char*)p->weights_in + r0 * in_row;
+                if (stage_in) {
+                    unsigned char* pin = nullptr;
+                    MCP_CHECK(mcp_pinned_reserve(h, 2 + s, (size_t)chunk * in_row, (void**)&pin));     // slots 2, 3: inputs
+                    memcpy(pin, src, rows * in_row);
+                    src = pin;
+                }
+                MCP_CUDA(h, cudaMemcpyAsync(d_in, src, rows * in_row, cudaMemcpyHostToDevice, ss));
+            }
+            // carve the output slot (device) and, when staging, the same layout in the slot's pinned buffer
+            unsigned char* p_out = nullptr;
+            if (stage_out) MCP_CHECK(mcp_pinned_reserve(h, s, (size_t)chunk * (out_row + 16), (void**)&p_out));   // slots 0, 1: outputs
             size_t o = 0;
+            size_t offs[5] = {0, 0, 0, 0, 0};
+            int n_carved = 0;
             auto carve = [&](bool want, size_t bytes_per_row) -> unsigned char* {
+                offs[n_carved++] = o;
                 if (!want) return nullptr;
                 unsigned char* q = d_out + o;
                 o += (chunk * bytes_per_row + 255) / 256 * 256;
@@ -304,11 +363,24 @@ static int portfolios_impl(mcp_handle h, const mcp_portfolio_params* p, const do
                 env_slot1 = env_slot1 || (s == 1 && n_chunks > 1);
             }
             if (recheck) MCP_CHECK(rc_collect_launch(h, ds, dk, rows, job.first, running + s, rf_mu, p->risk_target, d_lists, ss));
-            if (dw) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->weights + r0 * N * es, dw, rows * N * es, cudaMemcpyDeviceToHost, ss));
-            if (dr && out->returns) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->returns + r0 * es, dr, rows * es, cudaMemcpyDeviceToHost, ss));
-            if (dk && out->risks) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->risks + r0 * es, dk, rows * es, cudaMemcpyDeviceToHost, ss));
-            if (ds && out->sharpes) MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)out->sharpes + r0 * es, ds, rows * es, cudaMemcpyDeviceToHost, ss));
-            if (da) MCP_CUDA(h, cudaMemcpyAsync(out->accepted + r0, da, rows, cudaMemcpyDeviceToHost, ss));
+            Pending& q = pend[s];
+            auto back = [&](unsigned char* dsrc, void* user, size_t row_bytes, int which, unsigned char*& staged) {
+                staged = nullptr;
+                if (!dsrc || !user) return cudaSuccess;
+                if (stage_out) {
+                    staged = p_out + offs[which];
+                    return cudaMemcpyAsync(staged, dsrc, rows * row_bytes, cudaMemcpyDeviceToHost, ss);
+                }
+                return cudaMemcpyAsync((unsigned char*)user + r0 * row_bytes, dsrc, rows * row_bytes, cudaMemcpyDeviceToHost, ss);
+            };
+            MCP_CUDA(h, back(dw, out->weights, (size_t)N * es, 0, q.w));
+            MCP_CUDA(h, back(dr, out->returns, es, 1, q.r));
+            MCP_CUDA(h, back(dk, out->risks, es, 2, q.k));
+            MCP_CUDA(h, back(ds, out->sharpes, es, 3, q.s));
+            MCP_CUDA(h, back(da, out->accepted, 1, 4, q.a));
+            q.on = stage_out;
+            q.r0 = r0;
+            q.rows = rows;
             used[s] = true;
         }
         for (int s = 0; s < 2; ++s) {
@@ -320,75 +392,147 @@ static int portfolios_impl(mcp_handle h, const mcp_portfolio_params* p, const do
                 MCP_CUDA(h, cudaEventElapsedTime(&ms, h->ev[2 * s], h->ev[2 * s + 1]));
                 kernel_ms += ms;
             }
+            flush(s);
         }
         const int n_run = used[1] ? 2 : 1;
         MCP_CHECK(pf_reduce_launch(h, running, n_run, final_cand, 0, st));
     }
 
+
     // ---- winners: indices to the host, rows (supplied mode) to scratch, replay, records back ----
     PfCand fin;
+    fin.key_s = fin.key_d = -INFINITY;
+    fin.idx_s = fin.idx_d = MCP_NO_INDEX;
+    fin.rmin = INFINITY;
+    fin.rmax = -INFINITY;
     unsigned long long n_acc = 0;
-    MCP_CUDA(h, cudaMemcpyAsync(&fin, final_cand, sizeof fin, cudaMemcpyDeviceToHost, st));
-    MCP_CUDA(h, cudaMemcpyAsync(&n_acc, d_acc, 8, cudaMemcpyDeviceToHost, st));
-    MCP_CUDA(h, cudaStreamSynchronize(st));
-    if (p->space == MCP_DEVICE) {
-        float ms = 0;
-        MCP_CUDA(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
-        kernel_ms = ms;
+    if (!empty) {
+        MCP_CUDA(h, cudaMemcpyAsync(&fin, final_cand, sizeof fin, cudaMemcpyDeviceToHost, st));
+        MCP_CUDA(h, cudaMemcpyAsync(&n_acc, d_acc, 8, cudaMemcpyDeviceToHost, st));
+        MCP_CUDA(h, cudaStreamSynchronize(st));
+        if (p->space == MCP_DEVICE) {
+            float ms = 0;
+            MCP_CUDA(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+            kernel_ms = ms;
+        }
     }
     out->n_accepted = n_acc;
+    out->n_accepted_global = n_acc;
     out->kernel_ms = kernel_ms;
     h->last_ms = kernel_ms;
-    if (K > 0) {
+    std::vector<unsigned long long> hb(2 * (size_t)std::max(K, 1), 0ull);       // local envelope bins: keys, then indices
+    if (K > 0 && !empty) {
         if (env_slot1) MCP_CHECK(env_fold(h, K, fmax(1), fidx(1), fmax(0), fidx(0), st));
-        std::vector<unsigned long long> hb(2 * (size_t)K);
         MCP_CUDA(h, cudaMemcpyAsync(hb.data(), fmax(0), sizeof(unsigned long long) * K, cudaMemcpyDeviceToHost, st));
         MCP_CUDA(h, cudaMemcpyAsync(hb.data() + K, fidx(0), sizeof(unsigned long long) * K, cudaMemcpyDeviceToHost, st));
         MCP_CUDA(h, cudaStreamSynchronize(st));
+    }
+    const bool have_local = n_acc != 0 && fin.idx_s != MCP_NO_INDEX;
+    std::vector<double> rec(rec_doubles, NAN);
+    {
+        const uint64_t none = MCP_NO_INDEX;
+        memcpy(&rec[0], &none, 8);
+        memcpy(&rec[PF_REC_HEADER + N], &none, 8);
+    }
+    if (have_local) {
+        PfReplay rp;
+        rp.n_sel = 2;
+        rp.idx[0] = fin.idx_s;
+        rp.idx[1] = fin.idx_d;
+        rp.rec = d_rec;
+        job.first = p->first_index;
+        job.P = P;
+        job.stream = st;
+        const void* row_src = p->weights_in;
+        size_t row_es = es;
+        if (recheck) {
+            // FP32 screen -> FP64 decision among the near-ties; the records are then FP64 too
+            int overflow = 0;
+            MCP_CHECK(rc_decide(h, p, job, fin, rf_mu, d_lists, cands, max_blocks, d_acc, rp.idx, &overflow));
+            if (overflow) {
+                // more near-ties than the lists hold (many duplicated / equal rows): decide on a full FP64 pass instead
+                out->recheck_overflow = 1;
+                MCP_CHECK(rc_full_fp64(h, p, job, cands, max_blocks, d_acc, rp.idx));
+            }
+            job.dtype = MCP_F64;
+            row_src = p->weights_recheck;
+            row_es = 8;
+        }
+        if (supplied) {
+            for (int k = 0; k < 2; ++k) {
+                const size_t row = (size_t)(rp.idx[k] - p->first_index) * N * row_es;
+                MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)d_rows + (size_t)k * N * row_es, (const unsigned char*)row_src + row,
+                                            (size_t)N * row_es, p->space == MCP_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+            }
+            rp.rows = d_rows;
+        }
+        MCP_CHECK(pf_replay(h, job, rp));
+        MCP_CUDA(h, cudaMemcpyAsync(rec.data(), d_rec, rec_doubles * sizeof(double), cudaMemcpyDeviceToHost, st));
+        MCP_CUDA(h, cudaStreamSynchronize(st));
+    }
+    double rmin = have_local ? fin.rmin : INFINITY, rmax = have_local ? fin.rmax : -INFINITY;
+
+    if (p->comm_merge) {
+        // ---- cross-rank merge inside the library: ONE all-gather of this rank's block
+        //      [2 records | n_accepted | risk range | K bin keys | K bin indices], the same deterministic pick on every rank ----
+        const size_t blk = rec_doubles + 3 + 2 * (size_t)K;                   // 8-byte words per rank
+        const int world = h->comm_size;
+        std::vector<double> mine(blk), all(blk * (size_t)world);
+        memcpy(mine.data(), rec.data(), rec_doubles * 8);
+        memcpy(&mine[rec_doubles], &n_acc, 8);
+        mine[rec_doubles + 1] = rmin;
+        mine[rec_doubles + 2] = rmax;
+        if (K > 0) memcpy(&mine[rec_doubles + 3], hb.data(), 2 * (size_t)K * 8);
+        MCP_CHECK(mcp_comm_allgather(h, mine.data(), blk * 8, all.data()));
+        const int stride = PF_REC_HEADER + N;
+        uint64_t best_i[2] = {MCP_NO_INDEX, MCP_NO_INDEX};
+        double best_k[2] = {NAN, NAN};
+        int best_r[2] = {-1, -1};
+        unsigned long long total_acc = 0;
+        rmin = INFINITY;
+        rmax = -INFINITY;
+        std::fill(hb.begin(), hb.end(), 0ull);
+        for (int r = 0; r < world; ++r) {
+            const double* b = all.data() + (size_t)r * blk;
+            for (int c = 0; c < 2; ++c) {
+                uint64_t idx;
+                memcpy(&idx, &b[(size_t)c * stride], 8);
+                // record key: Sharpe (larger wins) / |risk - target| (smaller wins)
+                const double key = c == 0 ? b[(size_t)c * stride + 1] : -b[(size_t)c * stride + 1];
+                if (record_better(key, idx, best_k[c], best_i[c])) { best_k[c] = key; best_i[c] = idx; best_r[c] = r; }
+            }
+            unsigned long long a8;
+            memcpy(&a8, &b[rec_doubles], 8);
+            total_acc += a8;
+            if (a8) { rmin = std::min(rmin, b[rec_doubles + 1]); rmax = std::max(rmax, b[rec_doubles + 2]); }
+            for (int k = 0; k < K; ++k) {
+                unsigned long long key, idx;
+                memcpy(&key, &b[rec_doubles + 3 + k], 8);
+                memcpy(&idx, &b[rec_doubles + 3 + K + k], 8);
+                if (key == 0ull) continue;                                     // empty bin on that rank
+                if (key > hb[k] || (key == hb[k] && idx < hb[K + k])) { hb[k] = key; hb[K + k] = idx; }
+            }
+        }
+        for (int c = 0; c < 2; ++c)
+            if (best_r[c] >= 0) memcpy(&rec[(size_t)c * stride], all.data() + (size_t)best_r[c] * blk + (size_t)c * stride, (size_t)stride * 8);
+        out->n_accepted_global = total_acc;
+        n_acc = total_acc;
+    }
+    if (K > 0) {
         for (int b = 0; b < K; ++b) {
             if (hb[b] == 0ull) continue;                 // empty bin: -inf / MCP_NO_INDEX
             out->bin_best_return[b] = mcp_key_to_value(hb[b], p->dtype);
             out->bin_best_index[b] = hb[K + b];
         }
     }
-    if (n_acc == 0 || fin.idx_s == MCP_NO_INDEX) return MCP_OK;
-    out->risk_min = fin.rmin;
-    out->risk_max = fin.rmax;
-
-    PfReplay rp;
-    rp.n_sel = 2;
-    rp.idx[0] = fin.idx_s;
-    rp.idx[1] = fin.idx_d;
-    rp.rec = d_rec;
-    job.first = p->first_index;
-    job.P = P;
-    job.stream = st;
-    const void* row_src = p->weights_in;
-    size_t row_es = es;
-    if (recheck) {
-        // FP32 screen -> FP64 decision among the near-ties; the records are then FP64 too
-        int overflow = 0;
-        MCP_CHECK(rc_decide(h, p, job, fin, rf_mu, d_lists, cands, max_blocks, d_acc, rp.idx, &overflow));
-        job.dtype = MCP_F64;
-        row_src = p->weights_recheck;
-        row_es = 8;
-    }
-    if (supplied) {
-        for (int k = 0; k < 2; ++k) {
-            const size_t row = (size_t)(rp.idx[k] - p->first_index) * N * row_es;
-            MCP_CUDA(h, cudaMemcpyAsync((unsigned char*)d_rows + (size_t)k * N * row_es, (const unsigned char*)row_src + row,
-                                        (size_t)N * row_es, p->space == MCP_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-        }
-        rp.rows = d_rows;
-    }
-    MCP_CHECK(pf_replay(h, job, rp));
-    std::vector<double> rec(rec_doubles);
-    MCP_CUDA(h, cudaMemcpyAsync(rec.data(), d_rec, rec_doubles * sizeof(double), cudaMemcpyDeviceToHost, st));
-    MCP_CUDA(h, cudaStreamSynchronize(st));
+    if (n_acc == 0) return MCP_OK;
+    out->risk_min = rmin;
+    out->risk_max = rmax;
     fill_selection(out->max_sharpe, rec.data(), N);
     fill_selection(out->target_risk, rec.data() + PF_REC_HEADER + N, N);
     return MCP_OK;
 }
+
 
 static int envelope_arrays_impl(mcp_handle h, int dtype, const void* risks, const void* returns, uint64_t n, uint64_t first_index,
                                 double risk_lo, double risk_hi, int K, double* bin_best_return, uint64_t* bin_best_index) {

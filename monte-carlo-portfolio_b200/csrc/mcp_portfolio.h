@@ -51,6 +51,9 @@ struct PfJob {
     int blocks_used = 0;               // out: grid size of the launch
     uint64_t tc_table_epoch = 0;       // != 0: the tcgen05 sweep's S' / mu table of THIS call sits in slot 6 under that epoch
     int tc_table_f16 = -1;             // operand split the table in slot 6 was built for (1: FP16 images, 0: TF32 + BF16)
+    uint64_t lg_table_epoch = 0;       // != 0: the SIMT large-sweep constants (S' / Sigma, mu, bounds) of THIS call sit in slot 6 under that epoch
+    int lg_table_kind = -1;            // which kernel family / dtype they were laid out for (0 tiled FP32, 1 generic FP32, 2 generic FP64)
+    int rounds = 10;                   // Philox4x32 rounds (10 default, 7 optional)
 };
 
 // Replay of selected portfolios: regenerates (RNG mode) or re-reads (supplied mode, `rows`
@@ -86,6 +89,9 @@ int rc_collect_launch(mcp_context* h, const void* sharpe, const void* risk, uint
 int rc_decide(mcp_context* h, const mcp_portfolio_params* p, const PfJob& job32, const PfCand& fin, double rf_mu,
               RcLists* d_lists, PfCand* d_cand_scratch, int max_blocks, unsigned long long* d_acc_scratch, uint64_t out_idx[2],
               int* overflow);
+// overflow of the near-tie lists: the whole range re-evaluated in FP64 from weights_recheck (exact, slow, rare)
+int rc_full_fp64(mcp_context* h, const mcp_portfolio_params* p, const PfJob& job32, PfCand* d_cand_scratch, int max_blocks,
+                 unsigned long long* d_acc_scratch, uint64_t out_idx[2]);
 
 int pf_small_launch(mcp_context* h, PfJob& job);
 int pf_small_replay(mcp_context* h, const PfJob& job, const PfReplay& rp);

@@ -504,9 +504,14 @@ static int large_launch_tiled(mcp_context* h, PfJob& job) {
     }
     float* dev = nullptr;
     MCP_CHECK(mcp_dev_reserve(h, 6, host.size() * sizeof(float), (void**)&dev));
-    ++h->const_epoch;
-    MCP_CUDA(h, cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, job.stream));
-    MCP_CUDA(h, cudaStreamSynchronize(job.stream));        // `host` is pageable and dies at scope exit
+    // once per mcp_portfolios call: later chunks (other pipeline streams included) and the replays reuse the table
+    if (job.lg_table_epoch == 0 || job.lg_table_epoch != h->const_epoch || job.lg_table_kind != 0) {
+        MCP_CUDA(h, cudaDeviceSynchronize());                  // another pipeline stream may still read the previous table
+        MCP_CUDA(h, cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, job.stream));
+        MCP_CUDA(h, cudaStreamSynchronize(job.stream));        // `host` is pageable and dies at scope exit
+        job.lg_table_epoch = ++h->const_epoch;
+        job.lg_table_kind = 0;
+    }
 
     LargeArgs a;
     a.st = dev; a.mu = dev + st_floats; a.lo = a.mu + np; a.hi = a.lo + np;
@@ -550,9 +555,14 @@ static int large_launch_generic(mcp_context* h, PfJob& job) {
     }
     T* dev = nullptr;
     MCP_CHECK(mcp_dev_reserve(h, 6, host.size() * sizeof(T), (void**)&dev));
-    ++h->const_epoch;
-    MCP_CUDA(h, cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, job.stream));
-    MCP_CUDA(h, cudaStreamSynchronize(job.stream));
+    const int kind = sizeof(T) == 8 ? 2 : 1;
+    if (job.lg_table_epoch == 0 || job.lg_table_epoch != h->const_epoch || job.lg_table_kind != kind) {
+        MCP_CUDA(h, cudaDeviceSynchronize());
+        MCP_CUDA(h, cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, job.stream));
+        MCP_CUDA(h, cudaStreamSynchronize(job.stream));
+        job.lg_table_epoch = ++h->const_epoch;
+        job.lg_table_kind = kind;
+    }
     GenArgs<T> a;
     a.sigma = dev; a.mu = dev + (size_t)n * n; a.lo = a.mu + np; a.hi = a.lo + np;
     a.w_in = (const T*)job.w_in; a.w_out = (T*)job.w_out;

@@ -12,6 +12,7 @@
 // L2-resident after the first pass.  A last pass accumulates the tail sums in FP64.
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstring>
 #include <vector>
 
@@ -20,7 +21,7 @@
 
 namespace mcp {
 
-constexpr int SEL_BITS = 11;
+constexpr int SEL_BITS = MCP_SEL_BITS;
 constexpr int SEL_BLOCK = 256;
 
 struct SelSlots {
@@ -75,18 +76,16 @@ __global__ void __launch_bounds__(SEL_BLOCK) select_hist_kernel(const T* __restr
     }
 }
 
-struct TailArgs {
-    double thr[MCP_MAX_ALPHAS];
-};
-
-// sums[t] += sum of v_i <= thr[t] (FP64), counts[t] += their number
+// sums[t] += sum of v_i <= thr[t] (FP64), counts[t] += their number; thr lives in device memory (written by
+// select_finish_kernel, or uploaded by the host state machine)
 template <typename T>
 __global__ void __launch_bounds__(SEL_BLOCK) tail_sum_kernel(const T* __restrict__ v, uint64_t n, int nt,
-                                                             const __grid_constant__ TailArgs a, double* __restrict__ sums,
+                                                             const double* __restrict__ thr, double* __restrict__ sums,
                                                              double* __restrict__ counts) {
     double s[MCP_MAX_ALPHAS], c[MCP_MAX_ALPHAS];
+    struct { double thr[MCP_MAX_ALPHAS]; } a;
 #pragma unroll
-    for (int t = 0; t < MCP_MAX_ALPHAS; ++t) s[t] = c[t] = 0.0;
+    for (int t = 0; t < MCP_MAX_ALPHAS; ++t) { s[t] = c[t] = 0.0; a.thr[t] = t < nt ? thr[t] : 0.0; }
     for (uint64_t i = (uint64_t)blockIdx.x * SEL_BLOCK + threadIdx.x; i < n; i += (uint64_t)gridDim.x * SEL_BLOCK) {
         const double x = (double)v[i];
 #pragma unroll
@@ -162,6 +161,28 @@ __global__ void __launch_bounds__(256) select_advance_kernel(const unsigned long
     }
     __syncthreads();
     if (threadIdx.x == 0 && !found) st->error = 1;
+}
+
+// VaR from the final prefixes, on the device (so that a sharded call needs no host round trip between the select passes and
+// the tail pass): numpy's _lerp on the two exact order statistics, with explicitly rounded operations -- the host code this
+// replaces is compiled without FMA contraction, and the results are compared bit for bit with np.percentile.
+struct FinishArgs {
+    int n_alphas, dtype;
+    int lo_t[MCP_MAX_ALPHAS], hi_t[MCP_MAX_ALPHAS];
+    double gamma[MCP_MAX_ALPHAS];
+};
+__device__ __forceinline__ double key_value_dev(unsigned long long key, int dtype) {
+    if (dtype == MCP_F64) return __longlong_as_double((long long)key_to_f64(key));
+    return (double)__uint_as_float(key_to_f32((uint32_t)key));
+}
+__global__ void select_finish_kernel(const SelDevState* st, const __grid_constant__ FinishArgs f, double* var_thr) {
+    const int a = threadIdx.x;
+    if (a >= f.n_alphas) return;
+    const double lo = key_value_dev(st->prefix[f.lo_t[a]], f.dtype), hi = key_value_dev(st->prefix[f.hi_t[a]], f.dtype);
+    const double t = f.gamma[a], diff = __dsub_rn(hi, lo);
+    double r = __dadd_rn(lo, __dmul_rn(diff, t));
+    if (t >= 0.5) r = __dsub_rn(hi, __dmul_rn(diff, __dsub_rn(1.0, t)));
+    var_thr[a] = r;
 }
 
 static void assign_slots(mcp_select_state* s) {
@@ -273,30 +294,33 @@ int mcp_select_hist(mcp_handle h, const void* values_dev, int dtype, uint64_t n,
     return MCP_OK;
 }
 
-static int quantiles_impl(mcp_handle h, const void* values, int space, int dtype, uint64_t n, uint64_t n_total,
-                          const double* alphas, int n_alphas, double* var_out, double* cvar_out,
-                          mcp_allreduce_fn allreduce, void* user) {
-    MCP_REQUIRE(h, alphas && var_out && cvar_out, "mcp_quantiles: NULL argument");
-    MCP_REQUIRE(h, values || n == 0, "mcp_quantiles: values is NULL");
-    MCP_REQUIRE(h, n_alphas >= 1 && n_alphas <= MCP_MAX_ALPHAS, "mcp_quantiles: n_alphas=%d out of range [1, %d]", n_alphas, MCP_MAX_ALPHAS);
-    MCP_REQUIRE(h, dtype == MCP_F32 || dtype == MCP_F64, "mcp_quantiles: bad dtype %d", dtype);
-    MCP_REQUIRE(h, space == MCP_HOST || space == MCP_DEVICE, "mcp_quantiles: bad space %d", space);
+}  // extern "C" (reopened below)
+
+// The select + tail passes on device-resident values.  `allreduce` may be NULL (single shard), a caller callback, or
+// MCP_ALLREDUCE_COMM (the handle's NCCL communicator, always stream-ordered).  `hist0_dev` (optional): this shard's
+// histogram of the FIRST radix digit, 1 << SEL_BITS uint64 counts, already filled on the stream by the producer of the values
+// (the path kernels do it in their epilogue): pass 0 then skips its sweep over the data.
+int mcp_quantiles_device(mcp_context* h, const void* v, int dtype, uint64_t n, uint64_t n_total, const double* alphas, int n_alphas,
+                         double* var_out, double* cvar_out, mcp_allreduce_fn allreduce, void* user,
+                         const unsigned long long* hist0_dev, double* ms_out) {
+    const bool use_comm = allreduce == MCP_ALLREDUCE_COMM;
+    if (use_comm) MCP_REQUIRE(h, h->comm != nullptr, "mcp_quantiles: MCP_ALLREDUCE_COMM needs a communicator on this handle (mcp_comm_init)");
     if (!allreduce) n_total = n;
     MCP_REQUIRE(h, n_total >= 1 && n_total >= n, "mcp_quantiles: empty input (np.percentile of an empty array is an error)");
-    mcp_device_guard guard(h->device);
     cudaStream_t st = h->stream;
-    const size_t es = dtype == MCP_F64 ? 8 : 4;
-    const void* v = values;
-    if (space == MCP_HOST && n) {
-        void* d = nullptr;
-        MCP_CHECK(mcp_dev_reserve(h, 3, n * es, &d));
-        MCP_CUDA(h, cudaMemcpyAsync(d, values, n * es, cudaMemcpyHostToDevice, st));
-        v = d;
-    }
+    // reduction over ranks of a device buffer, on this stream
+    auto reduce = [&](void* buf, size_t count, int kind) -> int {
+        if (!allreduce) return MCP_OK;
+        if (use_comm) return mcp_comm_allreduce_dev(h, buf, count, kind == 0 ? MCP_REDUCE_U64_SUM : MCP_REDUCE_F64_SUM, st);
+        if (allreduce(buf, count, kind, user) != 0) return mcp_fail(h, MCP_ERR_INVALID, "mcp_quantiles: allreduce callback failed");
+        return MCP_OK;
+    };
     // ---- order-statistic ranks: numpy 'linear' (virtual index (n-1) q, q = percent / 100) ----
     uint64_t ranks[MCP_MAX_TARGETS];
-    double gamma[MCP_MAX_ALPHAS];
-    int lo_t[MCP_MAX_ALPHAS], hi_t[MCP_MAX_ALPHAS];
+    FinishArgs fin;
+    memset(&fin, 0, sizeof fin);
+    fin.n_alphas = n_alphas;
+    fin.dtype = dtype;
     int nt = 0;
     auto add_rank = [&](uint64_t r) {
         for (int k = 0; k < nt; ++k) if (ranks[k] == r) return k;
@@ -312,56 +336,67 @@ static int quantiles_impl(mcp_handle h, const void* values, int space, int dtype
         if (hidx >= (double)(n_total - 1)) lo = hi = n_total - 1;
         else if (hidx < 0) lo = hi = 0;
         else { lo = (uint64_t)std::floor(hidx); hi = lo + 1; }
-        gamma[a] = hidx - std::floor(hidx);
-        lo_t[a] = add_rank(lo);
-        hi_t[a] = add_rank(hi);
+        fin.gamma[a] = hidx - std::floor(hidx);
+        fin.lo_t[a] = add_rank(lo);
+        fin.hi_t[a] = add_rank(hi);
     }
+    // device block: histograms | results (state, thresholds = VaR, tail sums, tail counts): ONE copy back
     const size_t hist_elems = (size_t)MCP_MAX_TARGETS << SEL_BITS;
+    struct Results {
+        SelDevState state;
+        double var[MCP_MAX_ALPHAS];
+        double sums[MCP_MAX_ALPHAS];
+        double counts[MCP_MAX_ALPHAS];
+    };
     unsigned long long* d_hist = nullptr;
-    MCP_CHECK(mcp_dev_reserve(h, 5, hist_elems * 8 + 64 * 8 + sizeof(SelDevState), (void**)&d_hist));
-    SelDevState* d_state = (SelDevState*)(d_hist + hist_elems + 64);
-    double ms_total = 0;
-    uint64_t final_prefix[MCP_MAX_TARGETS];
+    MCP_CHECK(mcp_dev_reserve(h, 5, hist_elems * 8 + sizeof(Results) + 64, (void**)&d_hist));
+    Results* d_res = (Results*)(d_hist + hist_elems);
+    Results* h_res = nullptr;
+    MCP_CHECK(mcp_pinned_reserve(h, 4, sizeof(Results), (void**)&h_res));
+    const bool device_resident = !allreduce || use_comm || h->allreduce_stream_ordered;
     MCP_CUDA(h, cudaEventRecord(h->ev[0], st));
-    if (!allreduce || h->allreduce_stream_ordered) {
-        // ---- device-resident refinement: histogram -> (all-reduce on this stream) -> digit selection, pass after pass,
-        // one host round trip at the end.  One slot per target (no prefix sharing: <= 16 histograms of 2048 bins).
+    memset(h_res, 0, sizeof *h_res);
+    auto launch_hist = [&](int slots_now, int shift, int bits, const unsigned long long* dev_prefix, const SelSlots& slots) -> int {
+        const size_t cnt = (size_t)slots_now << bits;
+        const size_t smem = sizeof(unsigned int) * cnt;
+        if (dtype == MCP_F64) {
+            if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(select_hist_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            select_hist_kernel<double><<<grid_for(h, n, 4), SEL_BLOCK, smem, st>>>((const double*)v, n, slots_now, slots, shift, bits, d_hist, dev_prefix);
+        } else {
+            if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(select_hist_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            select_hist_kernel<float><<<grid_for(h, n, 4), SEL_BLOCK, smem, st>>>((const float*)v, n, slots_now, slots, shift, bits, d_hist, dev_prefix);
+        }
+        MCP_CUDA(h, cudaGetLastError());
+        h->launches++;
+        return MCP_OK;
+    };
+    if (device_resident) {
+        // ---- device-resident refinement: histogram -> (all-reduce on this stream) -> digit selection, pass after pass; then the
+        // interpolation and the tail sums, still on the stream; one host wait at the very end.  One slot per target.
         const int key_bits = dtype == MCP_F64 ? 64 : 32;
-        SelDevState hs;
-        memset(&hs, 0, sizeof hs);
-        for (int t = 0; t < nt; ++t) hs.rank[t] = ranks[t];
-        MCP_CUDA(h, cudaMemcpyAsync(d_state, &hs, sizeof hs, cudaMemcpyHostToDevice, st));
+        for (int t = 0; t < nt; ++t) h_res->state.rank[t] = ranks[t];
+        MCP_CUDA(h, cudaMemcpyAsync(d_res, h_res, sizeof(Results), cudaMemcpyHostToDevice, st));
         SelSlots unused;
         memset(&unused, 0, sizeof unused);
         for (int done = 0; done < key_bits;) {
             const int bits = std::min(SEL_BITS, key_bits - done), shift = key_bits - done - bits;
             const int slots_now = done == 0 ? 1 : nt;                 // pass 0: one histogram serves all targets
             const size_t cnt = (size_t)slots_now << bits;
-            MCP_CUDA(h, cudaMemsetAsync(d_hist, 0, cnt * 8, st));
-            if (n) {
-                const size_t smem = sizeof(unsigned int) * cnt;
-                if (dtype == MCP_F64) {
-                    if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(select_hist_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    select_hist_kernel<double><<<grid_for(h, n, 4), SEL_BLOCK, smem, st>>>((const double*)v, n, slots_now, unused, shift, bits, d_hist, d_state->prefix);
-                } else {
-                    if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(select_hist_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    select_hist_kernel<float><<<grid_for(h, n, 4), SEL_BLOCK, smem, st>>>((const float*)v, n, slots_now, unused, shift, bits, d_hist, d_state->prefix);
-                }
-                MCP_CUDA(h, cudaGetLastError());
-                h->launches++;
+            if (done == 0 && hist0_dev) {
+                MCP_CUDA(h, cudaMemcpyAsync(d_hist, hist0_dev, cnt * 8, cudaMemcpyDeviceToDevice, st));
+            } else {
+                MCP_CUDA(h, cudaMemsetAsync(d_hist, 0, cnt * 8, st));
+                if (n) MCP_CHECK(launch_hist(slots_now, shift, bits, d_res->state.prefix, unused));
             }
-            if (allreduce && allreduce(d_hist, cnt, 0, user) != 0) return mcp_fail(h, MCP_ERR_INVALID, "mcp_quantiles: allreduce callback failed");
-            select_advance_kernel<<<nt, 256, 0, st>>>(d_hist, bits, d_state, done == 0 ? 1 : 0);
+            MCP_CHECK(reduce(d_hist, cnt, 0));
+            select_advance_kernel<<<nt, 256, 0, st>>>(d_hist, bits, &d_res->state, done == 0 ? 1 : 0);
             MCP_CUDA(h, cudaGetLastError());
             h->launches++;
             done += bits;
         }
-        MCP_CUDA(h, cudaMemcpyAsync(&hs, d_state, sizeof hs, cudaMemcpyDeviceToHost, st));
-        MCP_CUDA(h, cudaStreamSynchronize(st));
-        if (hs.error)
-            return mcp_fail(h, MCP_ERR_INVALID, "mcp_quantiles: rank outside the population (n_total=%llu inconsistent with the data?)",
-                            (unsigned long long)n_total);
-        for (int t = 0; t < nt; ++t) final_prefix[t] = hs.prefix[t];
+        select_finish_kernel<<<1, 32, 0, st>>>(&d_res->state, fin, d_res->var);
+        MCP_CUDA(h, cudaGetLastError());
+        h->launches++;
     } else {
         // ---- synchronous callback: the host state machine (mcp_select_*) scans the all-reduced histograms ----
         mcp_select_state sel;
@@ -373,57 +408,76 @@ static int quantiles_impl(mcp_handle h, const void* values, int space, int dtype
             const size_t cnt = (size_t)sel.n_slots << bits;
             MCP_CHECK(mcp_select_hist(h, v, dtype, n, &sel, (uint64_t*)d_hist));
             MCP_CUDA(h, cudaStreamSynchronize(st));
-            if (allreduce(d_hist, cnt, 0, user) != 0) return mcp_fail(h, MCP_ERR_INVALID, "mcp_quantiles: allreduce callback failed");
+            MCP_CHECK(reduce(d_hist, cnt, 0));
             MCP_CUDA(h, cudaMemcpyAsync(h_hist.data(), d_hist, cnt * 8, cudaMemcpyDeviceToHost, st));
             MCP_CUDA(h, cudaStreamSynchronize(st));
             if (mcp_select_advance(&sel, h_hist.data()) != MCP_OK)
                 return mcp_fail(h, MCP_ERR_INVALID, "mcp_quantiles: rank outside the population (n_total=%llu inconsistent with the data?)",
                                 (unsigned long long)n_total);
         }
-        for (int t = 0; t < nt; ++t) final_prefix[t] = sel.prefix[t];
+        // numpy's _lerp on the two exact order statistics
+        for (int a = 0; a < n_alphas; ++a) {
+            const double lo = mcp_key_to_value(sel.prefix[fin.lo_t[a]], dtype);
+            const double hi = mcp_key_to_value(sel.prefix[fin.hi_t[a]], dtype);
+            const double t = fin.gamma[a], diff = hi - lo;
+            double r = lo + diff * t;
+            if (t >= 0.5) r = hi - diff * (1 - t);
+            h_res->var[a] = r;
+        }
+        MCP_CUDA(h, cudaMemcpyAsync(d_res, h_res, sizeof(Results), cudaMemcpyHostToDevice, st));
     }
-    // ---- VaR: numpy's _lerp on the two exact order statistics ----
-    TailArgs ta;
-    memset(&ta, 0, sizeof ta);
-    for (int a = 0; a < n_alphas; ++a) {
-        const double lo = mcp_key_to_value(final_prefix[lo_t[a]], dtype);
-        const double hi = mcp_key_to_value(final_prefix[hi_t[a]], dtype);
-        const double t = gamma[a], diff = hi - lo;
-        double r = lo + diff * t;
-        if (t >= 0.5) r = hi - diff * (1 - t);
-        var_out[a] = r;
-        ta.thr[a] = r;
-    }
-    // ---- CVaR: FP64 tail sums ----
-    double* d_sums = (double*)(d_hist + hist_elems);
-    double* d_counts = d_sums + MCP_MAX_ALPHAS;
-    MCP_CUDA(h, cudaMemsetAsync(d_sums, 0, sizeof(double) * 2 * MCP_MAX_ALPHAS, st));
+    // ---- CVaR: FP64 tail sums (thresholds = the VaR values, read from device memory) ----
     if (n) {
-        if (dtype == MCP_F64) tail_sum_kernel<double><<<grid_for(h, n, 8), SEL_BLOCK, 0, st>>>((const double*)v, n, n_alphas, ta, d_sums, d_counts);
-        else tail_sum_kernel<float><<<grid_for(h, n, 8), SEL_BLOCK, 0, st>>>((const float*)v, n, n_alphas, ta, d_sums, d_counts);
+        if (dtype == MCP_F64) tail_sum_kernel<double><<<grid_for(h, n, 8), SEL_BLOCK, 0, st>>>((const double*)v, n, n_alphas, d_res->var, d_res->sums, d_res->counts);
+        else tail_sum_kernel<float><<<grid_for(h, n, 8), SEL_BLOCK, 0, st>>>((const float*)v, n, n_alphas, d_res->var, d_res->sums, d_res->counts);
         MCP_CUDA(h, cudaGetLastError());
         h->launches++;
     }
-    MCP_CUDA(h, cudaEventRecord(h->ev[1], st));
     if (allreduce) {
-        if (!h->allreduce_stream_ordered) MCP_CUDA(h, cudaStreamSynchronize(st));
-        if (allreduce(d_sums, 2 * MCP_MAX_ALPHAS, 1, user) != 0) return mcp_fail(h, MCP_ERR_INVALID, "mcp_quantiles: allreduce callback failed");
+        if (!device_resident) MCP_CUDA(h, cudaStreamSynchronize(st));
+        static_assert(offsetof(Results, counts) == offsetof(Results, sums) + sizeof(double) * MCP_MAX_ALPHAS, "sums and counts are reduced as one buffer");
+        MCP_CHECK(reduce(d_res->sums, 2 * MCP_MAX_ALPHAS, 1));
     }
-    double sums[2 * MCP_MAX_ALPHAS];
-    MCP_CUDA(h, cudaMemcpyAsync(sums, d_sums, sizeof sums, cudaMemcpyDeviceToHost, st));
+    MCP_CUDA(h, cudaEventRecord(h->ev[1], st));
+    MCP_CUDA(h, cudaMemcpyAsync(h_res, d_res, sizeof(Results), cudaMemcpyDeviceToHost, st));
     MCP_CUDA(h, cudaStreamSynchronize(st));
+    if (use_comm) MCP_CHECK(mcp_comm_check(h));
+    if (device_resident && h_res->state.error)
+        return mcp_fail(h, MCP_ERR_INVALID, "mcp_quantiles: rank outside the population (n_total=%llu inconsistent with the data?)",
+                        (unsigned long long)n_total);
     for (int a = 0; a < n_alphas; ++a) {
-        const double cnt = sums[MCP_MAX_ALPHAS + a];
-        cvar_out[a] = cnt > 0 ? sums[a] / cnt : var_out[a];
+        var_out[a] = h_res->var[a];
+        const double cnt = h_res->counts[a];
+        cvar_out[a] = cnt > 0 ? h_res->sums[a] / cnt : var_out[a];
     }
     float ms = 0;
-    if (!allreduce) {
-        MCP_CUDA(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
-        ms_total = ms;
-    }
-    h->last_ms = ms_total;
+    MCP_CUDA(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    h->last_ms = ms;
+    if (ms_out) *ms_out = ms;
     return MCP_OK;
 }
+
+static int quantiles_impl(mcp_handle h, const void* values, int space, int dtype, uint64_t n, uint64_t n_total,
+                          const double* alphas, int n_alphas, double* var_out, double* cvar_out,
+                          mcp_allreduce_fn allreduce, void* user) {
+    MCP_REQUIRE(h, alphas && var_out && cvar_out, "mcp_quantiles: NULL argument");
+    MCP_REQUIRE(h, values || n == 0, "mcp_quantiles: values is NULL");
+    MCP_REQUIRE(h, n_alphas >= 1 && n_alphas <= MCP_MAX_ALPHAS, "mcp_quantiles: n_alphas=%d out of range [1, %d]", n_alphas, MCP_MAX_ALPHAS);
+    MCP_REQUIRE(h, dtype == MCP_F32 || dtype == MCP_F64, "mcp_quantiles: bad dtype %d", dtype);
+    MCP_REQUIRE(h, space == MCP_HOST || space == MCP_DEVICE, "mcp_quantiles: bad space %d", space);
+    mcp_device_guard guard(h->device);
+    const size_t es = dtype == MCP_F64 ? 8 : 4;
+    const void* v = values;
+    if (space == MCP_HOST && n) {
+        void* d = nullptr;
+        MCP_CHECK(mcp_dev_reserve(h, 3, n * es, &d));
+        MCP_CUDA(h, cudaMemcpyAsync(d, values, n * es, cudaMemcpyHostToDevice, h->stream));
+        v = d;
+    }
+    return mcp_quantiles_device(h, v, dtype, n, n_total, alphas, n_alphas, var_out, cvar_out, allreduce, user, nullptr, nullptr);
+}
+
+extern "C" {
 
 int mcp_quantiles(mcp_handle h, const void* values, int space, int dtype, uint64_t n, uint64_t n_total,
                   const double* alphas, int n_alphas, double* var_out, double* cvar_out,

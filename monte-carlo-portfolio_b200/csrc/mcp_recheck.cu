@@ -32,13 +32,17 @@ __global__ void __launch_bounds__(256) rc_collect(const float* __restrict__ shar
                                                   RcLists* lists) {
     const PfCand run = *running;
     if (run.idx_s == MCP_NO_INDEX) return;
+    // The running best can be off by its own rounding error (bounded with the running minimum risk, which is <= the risk of
+    // the running best); a candidate by ITS error, which scales with 1 / its own risk -- so a later chunk that lowers the
+    // minimum risk cannot invalidate what an earlier chunk decided.  The recorded key is the candidate's upper bound s + e.
     const float thr_s = (float)(run.key_s - rc_tol_sharpe(run.key_s, run.rmin, rf_mu));
     const float thr_d = (float)(run.key_d - rc_tol_dist(run.key_d, target));
     for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256) {
         const float s = sharpe[i], k = risk[i];
-        if (s >= thr_s) {
+        const float su = s + (float)rc_tol_sharpe((double)s, (double)k, rf_mu);
+        if (su >= thr_s) {
             const unsigned slot = atomicAdd(&lists->count[0], 1u);
-            if (slot < RC_CAP) { lists->idx[0][slot] = base + i; lists->key[0][slot] = s; }
+            if (slot < RC_CAP) { lists->idx[0][slot] = base + i; lists->key[0][slot] = su; }
         }
         const float d = -fabsf(k - (float)target);
         if (d >= thr_d) {
@@ -110,6 +114,49 @@ int rc_decide(mcp_context* h, const mcp_portfolio_params* p, const PfJob& job32,
         const uint64_t pos = c == 0 ? best.idx_s : best.idx_d;
         if (pos != MCP_NO_INDEX && pos < idx.size()) out_idx[c] = idx[pos];
     }
+    return MCP_OK;
+}
+
+// Exact fallback when the near-tie lists overflowed: every row of weights_recheck evaluated in FP64 by the same sweep
+// kernels (device space: one launch; host space: chunks through scratch slot 11), picks = the FP64 sweep's own.
+int rc_full_fp64(mcp_context* h, const mcp_portfolio_params* p, const PfJob& job32, PfCand* d_cand_scratch, int max_blocks,
+                 unsigned long long* d_acc_scratch, uint64_t out_idx[2]) {
+    cudaStream_t st = job32.stream;
+    const int N = p->n_assets;
+    const uint64_t P = p->n_portfolios;
+    PfJob j = job32;
+    j.dtype = MCP_F64;
+    j.w_out = j.ret_out = j.risk_out = j.sharpe_out = nullptr;
+    j.acc_out = nullptr;
+    j.cands = d_cand_scratch;
+    j.max_blocks = max_blocks;
+    j.n_accepted = d_acc_scratch;
+    j.n_bins = 0;
+    PfCand* running = d_cand_scratch + max_blocks;
+    const uint64_t chunk = p->space == MCP_DEVICE ? P : std::max<uint64_t>(1024, ((uint64_t)32 << 20) / ((uint64_t)N * 8));
+    int first = 1;
+    for (uint64_t r0 = 0; r0 < P; r0 += chunk) {
+        const uint64_t rows = std::min<uint64_t>(chunk, P - r0);
+        const double* src = p->weights_recheck + r0 * (uint64_t)N;
+        if (p->space == MCP_HOST) {
+            double* d_rows = nullptr;
+            MCP_CHECK(mcp_dev_reserve(h, 11, chunk * (size_t)N * 8, (void**)&d_rows));
+            MCP_CUDA(h, cudaMemcpyAsync(d_rows, src, rows * (size_t)N * 8, cudaMemcpyHostToDevice, st));
+            src = d_rows;
+        }
+        j.first = p->first_index + r0;
+        j.P = rows;
+        j.w_in = src;
+        MCP_CHECK(j.n <= PF_SMALL_MAX_N ? pf_small_launch(h, j) : pf_large_launch(h, j));
+        MCP_CHECK(pf_reduce_launch(h, d_cand_scratch, j.blocks_used, running, first ? 0 : 1, st));
+        first = 0;
+        if (p->space == MCP_HOST) MCP_CUDA(h, cudaStreamSynchronize(st));      // the scratch rows are reused by the next chunk
+    }
+    PfCand best;
+    MCP_CUDA(h, cudaMemcpyAsync(&best, running, sizeof best, cudaMemcpyDeviceToHost, st));
+    MCP_CUDA(h, cudaStreamSynchronize(st));
+    if (best.idx_s != MCP_NO_INDEX) out_idx[0] = best.idx_s;
+    if (best.idx_d != MCP_NO_INDEX) out_idx[1] = best.idx_d;
     return MCP_OK;
 }
 

@@ -163,3 +163,86 @@ extern "C" int mcp_asset_stats(mcp_handle h, const double* returns_host, int n_p
     if (!h) return MCP_ERR_INVALID;
     return mcp_guarded(h, "mcp_asset_stats", [&] { return asset_stats_impl(h, returns_host, n_periods, n_assets, risk_free, annual_factor, alpha, stats_out); });
 }
+
+// ---------------------------------------------------------------------------------------------
+// mu / Sigma estimation (app.py:679-680): mean_returns = returns_df.mean() * A, cov_matrix = returns_df.cov() * A
+// (pandas: ddof = 1; the leading fillna(0) row of the returns frame counts like any other row).  FP64 throughout, two
+// passes so that the covariance sums products of CENTRED values (what np.cov / pandas' nancorr do): one CTA per column
+// for the means, one CTA per (i, j >= i) pair for the co-moments.
+// ---------------------------------------------------------------------------------------------
+namespace mcp {
+
+constexpr int MOM_BLOCK = 128;
+
+__device__ __forceinline__ double mom_block_sum(double v, double* sh) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double s = 0;
+    for (int w = 0; w < MOM_BLOCK / 32; ++w) s += sh[w];
+    __syncthreads();
+    return s;
+}
+
+__global__ void __launch_bounds__(MOM_BLOCK) moments_mean_kernel(const double* __restrict__ R, int T, int N, double* __restrict__ mean) {
+    __shared__ double sh[MOM_BLOCK / 32];
+    const int i = blockIdx.x;
+    double s = 0;
+    for (int t = threadIdx.x; t < T; t += MOM_BLOCK) s += R[(size_t)t * N + i];
+    s = mom_block_sum(s, sh);
+    if (threadIdx.x == 0) mean[i] = s / (double)T;
+}
+
+__global__ void __launch_bounds__(MOM_BLOCK) moments_cov_kernel(const double* __restrict__ R, int T, int N, const double* __restrict__ mean,
+                                                                double A, double* __restrict__ mu, double* __restrict__ sigma) {
+    __shared__ double sh[MOM_BLOCK / 32];
+    // pair index -> (i, j), j >= i, row-major over the upper triangle
+    int p = blockIdx.x, i = 0;
+    while (p >= N - i) { p -= N - i; ++i; }
+    const int j = i + p;
+    const double mi = mean[i], mj = mean[j];
+    double s = 0;
+    for (int t = threadIdx.x; t < T; t += MOM_BLOCK) s = fma(R[(size_t)t * N + i] - mi, R[(size_t)t * N + j] - mj, s);
+    s = mom_block_sum(s, sh);
+    if (threadIdx.x == 0) {
+        const double c = s / (double)(T - 1) * A;             // T = 1: 0 / 0 = NaN, as pandas
+        sigma[(size_t)i * N + j] = c;
+        sigma[(size_t)j * N + i] = c;
+        if (i == j) mu[i] = mi * A;
+    }
+}
+
+}  // namespace mcp
+
+static int moments_impl(mcp_handle h, const double* returns_host, int T, int N, double A, double* mu_out, double* sigma_out) {
+    MCP_REQUIRE(h, returns_host && mu_out && sigma_out, "mcp_moments: NULL argument");
+    MCP_REQUIRE(h, T >= 1 && N >= 1 && N <= 4096, "mcp_moments: bad shape T=%d N=%d", T, N);
+    MCP_REQUIRE(h, std::isfinite(A), "mcp_moments: annual_factor is not finite");
+    mcp_device_guard guard(h->device);
+    cudaStream_t st = h->stream;
+    const size_t in_b = sizeof(double) * (size_t)T * N, out_d = (size_t)N * N + 2 * (size_t)N;
+    unsigned char* d = nullptr;
+    MCP_CHECK(mcp_dev_reserve(h, 18, in_b + out_d * sizeof(double) + 256, (void**)&d));
+    double* d_in = (double*)d;
+    double* d_sigma = (double*)(d + (in_b + 255) / 256 * 256);
+    double* d_mu = d_sigma + (size_t)N * N;
+    double* d_mean = d_mu + N;
+    MCP_CUDA(h, cudaMemcpyAsync(d_in, returns_host, in_b, cudaMemcpyHostToDevice, st));
+    moments_mean_kernel<<<N, MOM_BLOCK, 0, st>>>(d_in, T, N, d_mean);
+    MCP_CUDA(h, cudaGetLastError());
+    moments_cov_kernel<<<(unsigned)((size_t)N * (N + 1) / 2), MOM_BLOCK, 0, st>>>(d_in, T, N, d_mean, A, d_mu, d_sigma);
+    MCP_CUDA(h, cudaGetLastError());
+    h->launches += 2;
+    MCP_CUDA(h, cudaMemcpyAsync(sigma_out, d_sigma, sizeof(double) * (size_t)N * N, cudaMemcpyDeviceToHost, st));
+    MCP_CUDA(h, cudaMemcpyAsync(mu_out, d_mu, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+    MCP_CUDA(h, cudaStreamSynchronize(st));
+    return MCP_OK;
+}
+
+extern "C" int mcp_moments(mcp_handle h, const double* returns_host, int n_periods, int n_assets, double annual_factor,
+                           double* mu_out, double* sigma_out) {
+    if (!h) return MCP_ERR_INVALID;
+    return mcp_guarded(h, "mcp_moments", [&] { return moments_impl(h, returns_host, n_periods, n_assets, annual_factor, mu_out, sigma_out); });
+}

@@ -12,12 +12,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(PKG_ROOT, "lib", "libmcp.so")
 
-MCP_OK, MCP_ERR_INVALID, MCP_ERR_CUDA, MCP_ERR_NUMERIC, MCP_ERR_NOMEM = 0, -1, -2, -3, -4
+MCP_OK, MCP_ERR_INVALID, MCP_ERR_CUDA, MCP_ERR_NUMERIC, MCP_ERR_NOMEM, MCP_ERR_COMM = 0, -1, -2, -3, -4, -5
+MCP_ABI_VERSION = 2
 MCP_F32, MCP_F64 = 0, 1
 MCP_HOST, MCP_DEVICE = 0, 1
 MCP_NO_INDEX = 0xFFFFFFFFFFFFFFFF
 MCP_MAX_ALPHAS = 8
 MCP_MAX_TARGETS = 16
+MCP_COMM_ID_BYTES = 128
+MCP_REDUCE_U64_SUM, MCP_REDUCE_F64_SUM, MCP_REDUCE_F64_MIN, MCP_REDUCE_F64_MAX, MCP_REDUCE_U64_MAX = 0, 1, 2, 3, 4
 
 
 class McpError(RuntimeError):
@@ -37,9 +40,9 @@ class PortfolioParams(C.Structure):
                 ("risk_free", C.c_double), ("risk_target", C.c_double),
                 ("min_weights", C.c_void_p), ("max_weights", C.c_void_p),
                 ("max_tries", C.c_int32), ("keep_last", C.c_int32),
-                ("space", C.c_int32), ("reserved", C.c_int32),
+                ("space", C.c_int32), ("comm_merge", C.c_int32),
                 ("weights_in", C.c_void_p), ("weights_recheck", C.c_void_p),
-                ("n_bins", C.c_int32), ("reserved2", C.c_int32),
+                ("n_bins", C.c_int32), ("philox_rounds", C.c_int32),
                 ("risk_lo", C.c_double), ("risk_hi", C.c_double)]
 
 
@@ -53,14 +56,21 @@ class PortfolioOut(C.Structure):
                 ("sharpes", C.c_void_p), ("accepted", C.c_void_p),
                 ("bin_best_return", C.c_void_p), ("bin_best_index", C.c_void_p),
                 ("n_accepted", C.c_uint64), ("risk_min", C.c_double), ("risk_max", C.c_double),
-                ("max_sharpe", Selection), ("target_risk", Selection), ("kernel_ms", C.c_double)]
+                ("max_sharpe", Selection), ("target_risk", Selection), ("kernel_ms", C.c_double),
+                ("n_accepted_global", C.c_uint64), ("recheck_overflow", C.c_int32), ("reserved", C.c_int32)]
 
 
 class PathParams(C.Structure):
     _fields_ = [("n_assets", C.c_int32), ("dtype", C.c_int32),
                 ("n_paths", C.c_uint64), ("first_index", C.c_uint64), ("seed", C.c_uint64),
                 ("n_steps", C.c_int32), ("space", C.c_int32), ("dt", C.c_double),
-                ("normals_in", C.c_void_p)]
+                ("normals_in", C.c_void_p), ("philox_rounds", C.c_int32), ("reserved", C.c_int32)]
+
+
+class PathStats(C.Structure):
+    _fields_ = [("n_alphas", C.c_int32), ("comm_merge", C.c_int32), ("n_total", C.c_uint64),
+                ("alphas", C.c_double * MCP_MAX_ALPHAS), ("var", C.c_double * MCP_MAX_ALPHAS),
+                ("cvar", C.c_double * MCP_MAX_ALPHAS), ("kernel_ms", C.c_double), ("quantile_ms", C.c_double)]
 
 
 class SelectState(C.Structure):
@@ -73,7 +83,7 @@ class SelectState(C.Structure):
 class HistParams(C.Structure):
     _fields_ = [("n_assets", C.c_int32), ("n_periods", C.c_int32), ("dtype", C.c_int32),
                 ("space", C.c_int32), ("n_portfolios", C.c_uint64), ("first_index", C.c_uint64),
-                ("alpha", C.c_double), ("weights_in", C.c_void_p)]
+                ("alpha", C.c_double), ("weights_in", C.c_void_p), ("negate", C.c_int32), ("recheck", C.c_int32)]
 
 
 class HistOut(C.Structure):
@@ -83,6 +93,7 @@ class HistOut(C.Structure):
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
+ALLREDUCE_COMM = C.cast(C.c_void_p(1), ALLREDUCE_FN)       # MCP_ALLREDUCE_COMM: sum over the handle's own NCCL communicator
 
 # every symbol include/mcp.h declares: (restype, argtypes)
 SYMBOLS = {
@@ -115,6 +126,17 @@ SYMBOLS = {
     "mcp_set_allreduce_stream_ordered": (C.c_int, [C.c_void_p, C.c_int]),
     "mcp_envelope_arrays": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_double, C.c_double,
                                       C.c_int, C.c_void_p, C.c_void_p]),
+    "mcp_paths_stats": (C.c_int, [C.c_void_p, C.POINTER(PathParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.POINTER(PathStats)]),
+    "mcp_moments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
+    "mcp_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "mcp_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "mcp_comm_init_all": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "mcp_comm_destroy": (C.c_int, [C.c_void_p]),
+    "mcp_comm_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mcp_comm_nccl_version": (C.c_int, [C.POINTER(C.c_int)]),
+    "mcp_comm_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mcp_comm_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
 }
 
 _lib = None

@@ -12,6 +12,12 @@ collective exists; only results cross NVLink (NCCL), all latency-bound:
   all-reduce of the FP64 tail sums (``make_allreduce`` is the callback libmcp calls).
 
 Per-portfolio arrays are never moved between GPUs.
+
+Over NCCL the merges run INSIDE libmcp (``init_comm``: the library's own communicator, created from an id that rank 0
+broadcasts through torch.distributed; entry points are then called with ``comm_merge``): the collectives are issued on
+the handle's stream between the library's kernels and a sharded call costs one host wait.  The Python merges below
+(``merge_records``, ``all_gather_flat`` ...) remain for the gloo backend -- the CPU tests of the host logic -- and as the
+specification of what the library's merge does.
 """
 from __future__ import annotations
 
@@ -103,6 +109,34 @@ def _with_global(rec):
     return None if rec is None else dict(rec, index=rec["global_index"])
 
 
+_COMM_GROUPS = {}
+
+
+def init_comm(group=None, device=None):
+    """Give this rank's engine a libmcp communicator spanning `group` (idempotent).  Rank 0 creates the NCCL id, the 128
+    bytes travel through torch.distributed, every rank calls mcp_comm_init.  Returns the engine."""
+    import torch
+    import torch.distributed as dist
+    eng = api.get_engine(device)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    key = (eng.device, id(group) if group is not None else 0, world)
+    if _COMM_GROUPS.get(key) is eng and eng.comm_info() == (rank, world):
+        return eng
+    if eng.comm_info()[1]:
+        eng.comm_destroy()
+    box = [api.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group,
+                               device=torch.device("cuda", eng.device) if dist.get_backend(group) == "nccl" else None)
+    eng.comm_init(box[0], rank, world)
+    _COMM_GROUPS[key] = eng
+    return eng
+
+
+def _use_comm(group, kw) -> bool:
+    import torch.distributed as dist
+    return dist.get_backend(group) == "nccl"
+
+
 def simulate_portfolios_sharded(mean_returns, cov_matrix, n_portfolios, *, group=None, **kw):
     """`simulate_portfolios` over the whole job: this rank evaluates its block, selections are
     merged across ranks.  Arrays (if requested) stay local to the rank that produced them."""
@@ -111,6 +145,12 @@ def simulate_portfolios_sharded(mean_returns, cov_matrix, n_portfolios, *, group
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     first, count = shard_range(n_portfolios, rank, world)
     n = len(np.asarray(mean_returns))
+    if _use_comm(group, kw):
+        # the merge happens inside libmcp (one all-gather on the handle's stream, one host wait)
+        init_comm(group, kw.get("device"))
+        r = api.simulate_portfolios(mean_returns, cov_matrix, count, first_index=first, comm_merge=True, **kw)
+        r.extra["shard"] = (first, count)
+        return r
     r = api.simulate_portfolios(mean_returns, cov_matrix, count, first_index=first, **kw)
     dev = torch.device("cuda", api.get_engine(kw.get("device")).device) if dist.get_backend(group) == "nccl" else None
     L = _REC_HEAD + n
@@ -139,6 +179,38 @@ def frontier_envelope_sharded(mean_returns, cov_matrix, n_portfolios, n_bins=512
     nccl = dist.get_backend(group) == "nccl"
     dev = torch.device("cuda", eng.device) if nccl else torch.device("cpu")
     kw = dict(kw, return_arrays=False)
+    if nccl:
+        # picks and the risk range are merged inside libmcp; the bins through its host-buffer all-gather
+        init_comm(group, kw.get("device"))
+        single = risk_range is None and kw.get("weights") is None and api._metrics_fit(count, kw)
+        if risk_range is None:                  # every rank must take the same route: all or none keep their metrics
+            single = bool(eng.allreduce(np.array([0.0 if single else 1.0]), "max")[0] == 0.0)
+        if single:
+            r = api.simulate_portfolios(mean_returns, cov_matrix, count, first_index=first, comm_merge=True,
+                                        **dict(kw, return_arrays="device-metrics"))
+            if r.extra["n_accepted_global"] == 0:
+                raise ValueError("no portfolio satisfied the bounds; the envelope is empty")
+            risk_range = api._widen(r.risk_range)
+            env = api.envelope_from_arrays(r.risks, r.returns, n_bins, risk_range, first_index=first, device=kw.get("device"))
+            r.risks = r.returns = None
+        else:
+            if risk_range is None:
+                probe = api.simulate_portfolios(mean_returns, cov_matrix, count, first_index=first, comm_merge=True, **kw)
+                if probe.extra["n_accepted_global"] == 0:
+                    raise ValueError("no portfolio satisfied the bounds; the envelope is empty")
+                risk_range = api._widen(probe.risk_range)
+            r = api.simulate_portfolios(mean_returns, cov_matrix, count, first_index=first, n_bins=n_bins, risk_range=risk_range,
+                                        comm_merge=True, **kw)
+            r.extra["risk_range_global"] = risk_range
+            return r                             # n_bins > 0 with comm_merge: the library merged the bins as well
+        K = int(n_bins)
+        flat = np.concatenate([np.asarray(env["best_return"], dtype=np.float64), np.asarray(env["best_index"], dtype=np.int64).view(np.float64)])
+        G = eng.allgather(flat)
+        env["best_return"], env["best_index"] = merge_envelopes([row[:K] for row in G],
+                                                                [np.ascontiguousarray(row[K:2 * K]).view(np.int64) for row in G])
+        r.extra["envelope"] = env
+        r.extra["risk_range_global"] = risk_range
+        return r
 
     def global_range(r):
         lo, hi = r.risk_range if r.n_accepted else (float("inf"), float("-inf"))
@@ -230,6 +302,12 @@ def simulate_paths_sharded(mean_returns, cov_matrix, weights, n_paths, n_steps=2
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     first, count = shard_range(n_paths, rank, world)
     eng = api.get_engine(kw.get("device"))
+    if dist.get_backend(group) == "nccl" and not kw.pop("legacy_callback", False):
+        # libmcp's own communicator: path kernel (+ first histogram), select passes with their all-reduces, interpolation,
+        # tail sums and their all-reduce all on the handle's stream; ONE host wait and one copy back
+        init_comm(group, kw.get("device"))
+        return api.simulate_paths(mean_returns, cov_matrix, weights, count, n_steps, first_index=first, comm_merge=True,
+                                  n_total=n_paths, **kw)
     if not (world > 1 and dist.get_backend(group) == "nccl"):
         return api.simulate_paths(mean_returns, cov_matrix, weights, count, n_steps, first_index=first,
                                   allreduce=make_allreduce(eng.device, group) if world > 1 else None,

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(mcp):
     L = mcp.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.mcp_abi_version() == 1
+    assert L.mcp_abi_version() == _lib.MCP_ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header(mcp):
@@ -34,8 +34,10 @@ def test_struct_layouts_match_header(mcp):
     from mcportfolio import _lib
     assert C.sizeof(_lib.PortfolioParams) == 8 + 24 + 16 + 16 + 8 + 8 + 16 + 8 + 16
     assert C.sizeof(_lib.Selection) == 48
-    assert C.sizeof(_lib.PortfolioOut) == 7 * 8 + 8 + 16 + 2 * 48 + 8
-    assert C.sizeof(_lib.PathParams) == 8 + 24 + 8 + 8 + 8
+    assert C.sizeof(_lib.PortfolioOut) == 7 * 8 + 8 + 16 + 2 * 48 + 8 + 8 + 8
+    assert C.sizeof(_lib.PathParams) == 8 + 24 + 8 + 8 + 8 + 8
+    assert C.sizeof(_lib.PathStats) == 8 + 8 + 3 * 8 * _lib.MCP_MAX_ALPHAS + 16
+    assert C.sizeof(_lib.HistParams) == 16 + 16 + 8 + 8 + 8
     assert C.sizeof(_lib.SelectState) == 16 + 16 * 8 * 2 + 16 * 4 + 16 * 8
 
 

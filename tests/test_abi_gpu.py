@@ -86,7 +86,7 @@ def test_bad_arguments_return_error_classes_and_keep_the_handle_alive(abi):
     term = np.empty(100, dtype=np.float32)
     ms = C.c_double()
     assert L.mcp_paths(h, C.byref(pp), ptr(mu), ptr(sigma), None, ptr(term), C.byref(ms)) == _lib.MCP_ERR_INVALID
-    for field, value in (("n_assets", 33), ("n_steps", 0), ("dt", 0.0), ("dt", float("nan")), ("dtype", 2)):
+    for field, value in (("n_assets", 1025), ("n_steps", 0), ("dt", 0.0), ("dt", float("nan")), ("dtype", 2)):
         old = getattr(pp, field)
         setattr(pp, field, value)
         assert L.mcp_paths(h, C.byref(pp), ptr(mu), ptr(sigma), ptr(w), ptr(term), C.byref(ms)) == _lib.MCP_ERR_INVALID, field
