@@ -88,6 +88,58 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def build_digest():
+    try:
+        with open(os.path.join(ROOT, "monte-carlo-portfolio_b200", "build", "stamp")) as fh:
+            return fh.read().strip()
+    except OSError:
+        return None
+
+
+def ncu_figures(kernel: str):
+    """ncu counters of `kernel` from profiles/roofline_figures.json (written by tools/ncu_figures.py from a committed
+    `ncu --set full` report), with `digest_matches_build`: was the profiled libmcp.so built from the sources that built
+    the one running now?  Nothing is hard-coded here."""
+    path = os.path.join(ROOT, "profiles", "roofline_figures.json")
+    if not os.path.isfile(path):
+        return None
+    with open(path) as fh:
+        k = json.load(fh).get("kernels", {}).get(kernel)
+    if k is None:
+        return None
+    out = {key: k.get(key) for key in ("fp32_pipe_busy_pct", "issue_active_pct", "fma_inst_pct", "alu_pipe_pct", "xu_pipe_pct",
+                                       "tensor_pipe_busy_pct", "registers_per_thread", "dram_bytes", "duration_ms", "source", "build_digest")}
+    out["digest_matches_build"] = k.get("build_digest") == build_digest()
+    return out
+
+
+def check_expected(line, args, world):
+    """Seed-0 picks / VaR / envelope of the default job against tests/golden/c3c4c5_expected.json -> list of mismatches.
+    Indices, counts and bins are exact (the Philox counter is the global index: any GPU count gives the same job);
+    VaR / CVaR are compared at 2e-6 (the tcgen05 and SIMT path kernels round the contraction differently)."""
+    path = os.path.join(ROOT, "tests", "golden", "c3c4c5_expected.json")
+    if not os.path.isfile(path):
+        return ["tests/golden/c3c4c5_expected.json is missing"]
+    with open(path) as fh:
+        want = json.load(fh)
+    bad = []
+    if args.portfolios == P_TOTAL:
+        for k in ("max_sharpe_index", "target_risk_index"):
+            if line["selected"][k] != want["c3"][k]:
+                bad.append(f"C3 {k}: got {line['selected'][k]}, expected {want['c3'][k]}")
+        if args.paths == M_PATHS:
+            for a, (v, c) in want["c4"]["stats"].items():
+                gv, gc_ = line["paths"]["stats"][a]
+                if abs(gv - v) > 2e-6 or abs(gc_ - c) > 2e-6:
+                    bad.append(f"C4 alpha={a}: got ({gv}, {gc_}), expected ({v}, {c})")
+    if line.get("envelope") and args.envelope_portfolios == P_LARGE:
+        e = line["envelope"]
+        if e["target_risk"]["index"] != want["c5"]["target_risk_index"] or e["filled_bins"] != want["c5"]["filled_bins"]:
+            bad.append(f"C5: got idx {e['target_risk']['index']} / {e['filled_bins']} bins, expected "
+                       f"{want['c5']['target_risk_index']} / {want['c5']['filled_bins']}")
+    return bad
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -181,6 +233,7 @@ def run_reference(args):
             "paths": {"metric": "path-steps/sec (16 assets, 252 steps)", "value": pr["value"], "unit": "path-steps/s",
                       "cpu_baseline": pr},
             "gpu_launches": 0}
+    line["summary"] = {"impl": "reference", "c3_pfs": float(f"{value:.5g}"), "c4_path_steps_s": float(f"{pr['value']:.5g}"), "cores": cores}
     print(json.dumps(line), flush=True)
 
 
@@ -202,9 +255,14 @@ def run_ours(args):
     sys.stdout.flush()
     json_fd = os.dup(1)
     os.dup2(2, 1)
-    if world != args.gpus:
+    sp = bool(args.single_process)                  # ONE process drives all GPUs (the Streamlit caller's mode): devices=[0..N-1]
+    if world != args.gpus and not sp:
         if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU), or with --single-process")
+    if sp and world != 1:
+        raise SystemExit("--single-process is a plain `python bench.py --gpus N --single-process` launch")
+    devs = list(range(args.gpus)) if sp else None
+    ndev = args.gpus if sp else world                # GPUs the job is sharded over
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -222,12 +280,15 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
 
-    def sweep(p=p_total):
+    def sweep(p=p_total, **kw):
+        if sp and ndev > 1:
+            return mcp.simulate_portfolios(mu, sigma, p, risk_free=RISK_FREE, risk_target=RISK_TARGET, seed=SEED,
+                                           dtype="float32", return_arrays=False, devices=devs, **kw)
         if world > 1:
             return mdist.simulate_portfolios_sharded(mu, sigma, p, risk_free=RISK_FREE, risk_target=RISK_TARGET,
-                                                     seed=SEED, dtype="float32", return_arrays=False, device=local)
+                                                     seed=SEED, dtype="float32", return_arrays=False, device=local, **kw)
         return mcp.simulate_portfolios(mu, sigma, p, risk_free=RISK_FREE, risk_target=RISK_TARGET, seed=SEED,
-                                       dtype="float32", return_arrays=False, device=local)
+                                       dtype="float32", return_arrays=False, device=local, **kw)
 
     def timed(fn, steps, warmup):
         """-> (device seconds max over ranks, host wall seconds max over ranks, kernel ms list, last result)"""
@@ -275,24 +336,31 @@ def run_ours(args):
     launches_timed = launches * args.steps // (args.steps + args.warmup)
     value = p_total * args.steps / dev_s
     e2e_value = p_total * args.steps / host_s
-    my_first, my_count = mdist.shard_range(p_total, rank, world)
+    my_first, my_count = mdist.shard_range(p_total, rank, ndev)
     kernel_s = statistics.mean(kms) * 1e-3
     n = N_ASSETS
 
     # ---- second metric: C4 correlated paths + VaR/CVaR ----
     w_sel = res.max_sharpe["weights"] if res.max_sharpe else np.full(n, 1 / n)
 
-    def paths():
+    def paths(**kw):
+        if sp and ndev > 1:
+            return mcp.simulate_paths(mu, sigma, w_sel, m_total, N_STEPS, seed=SEED, dtype="float32", devices=devs, **kw)
         if world > 1:
             return mdist.simulate_paths_sharded(mu, sigma, w_sel, m_total, N_STEPS, seed=SEED, dtype="float32",
-                                                return_terminal=False, device=local)
+                                                return_terminal=False, device=local, **kw)
         return mcp.simulate_paths(mu, sigma, w_sel, m_total, N_STEPS, seed=SEED, dtype="float32",
-                                  return_terminal=False, device=local)
+                                  return_terminal=False, device=local, **kw)
 
     p_dev_s, p_host_s, p_kms, p_res = timed(paths, args.steps, args.warmup)
     paths_value = m_total * N_STEPS * args.steps / p_dev_s
     paths_kernel_s = statistics.mean(p_kms) * 1e-3
-    my_paths = mdist.shard_range(m_total, rank, world)[1]
+    my_paths = mdist.shard_range(m_total, rank, ndev)[1]
+
+    # ---- the same two workloads on Philox4x32-7 (an option: another stream of the same law; 10 rounds is the default) ----
+    r7_steps = max(1, min(args.steps, 2))
+    r7_dev_s, _, r7_kms, r7_res = timed(lambda: sweep(philox_rounds=7), r7_steps, 1)
+    r7p_dev_s, _, r7p_kms, r7p_res = timed(lambda: paths(philox_rounds=7), r7_steps, 1)
 
     # ---- third workload: C5 envelope, N = 256 (two sweeps per step: risk range, then binning) ----
     env_line = None
@@ -301,6 +369,9 @@ def run_ours(args):
         pl = args.envelope_portfolios
 
         def envelope():
+            if sp and ndev > 1:
+                return mcp.frontier_envelope(mu_l, sigma_l, pl, N_BINS, risk_free=RISK_FREE, risk_target=RISK_TARGET, seed=SEED,
+                                             dtype="float32", devices=devs)
             if world > 1:
                 return mdist.frontier_envelope_sharded(mu_l, sigma_l, pl, N_BINS, risk_free=RISK_FREE, risk_target=RISK_TARGET,
                                                        seed=SEED, dtype="float32", device=local)
@@ -309,7 +380,7 @@ def run_ours(args):
 
         e_steps = max(1, min(args.steps, 2))
         e_dev_s, e_host_s, e_kms, e_res = timed(envelope, e_steps, 1)
-        my_pl = mdist.shard_range(pl, rank, world)[1]
+        my_pl = mdist.shard_range(pl, rank, ndev)[1]
         env = e_res.extra["envelope"]
         env_line = {"metric": "portfolios/sec (256 assets, envelope)", "value": pl * e_steps / e_dev_s, "unit": "portfolios/s",
                     "ms_per_step": e_dev_s / e_steps * 1e3, "steps": e_steps, "warmup": 1,
@@ -341,6 +412,7 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    solo = world == 1 and ndev == 1
     # ---- roofline (rank 0's kernel): SIMT FP32 pipe, measured live ----
     fma_peak = max(eng.measure_fma_peak("float32") for _ in range(5))      # a peak is a maximum: best of 5 runs of the microbenchmark
     achieved = my_count * flops_per_portfolio(n) / kernel_s / 1e12
@@ -358,16 +430,20 @@ def run_ours(args):
                                                                "settle at the sustained figure, profiles/r1h_scale_check.txt)"
         env_line["roofline"]["frac"] = env_line["roofline"]["achieved"] / tpeak["bf16_tflops"]
         env_line["roofline"]["fp32_equivalent_vs_ffma_peak"] = env_line["roofline"]["fp32_equivalent_tflops"] / fma_peak
-    roofline = {"bound": "fp32-simt", "kernel": "small_sweep_packed<16,4,OUT=false> (Philox, FFMA2, no write-back)", "achieved": achieved,
+    sweep_ncu = ncu_figures("small_sweep_packed<16, 4, 0, 10>") or ncu_figures("small_sweep_packed<16, 4, 0>")
+    if sweep_ncu and sweep_ncu.get("dram_bytes") is not None:
+        traffic = sweep_ncu["dram_bytes"]            # dram__bytes_read + write of one 1e10-portfolio launch (ncu --set full)
+    roofline = {"bound": "fp32-simt", "kernel": "small_sweep_packed<16,4,OUT=false,ROUNDS=10> (Philox, FFMA2, no write-back)", "achieved": achieved,
                 "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak, "traffic": traffic,
                 "peak_source": "FFMA-chain microbenchmark (mcp_measure_fma_peak), best of 5 runs in this process; "
                                "MEASURED_PEAKS.json has no SIMT figure",
                 "algorithmic_flop_per_portfolio": flops_per_portfolio(n), "portfolios_per_launch": my_count,
                 "kernel_ms": kernel_s * 1e3,
                 "note": "RNG mode without write-back does 0 algorithmic HBM bytes; Philox (IMAD) and lg2 (MUFU) work "
-                        "is not counted as flops, but Philox's IMAD.WIDE runs on the same FP32 pipe: ncu measures that pipe "
-                        "61.5 % busy for this kernel (profiles/r1m_summary.md, sm__pipe_fma_cycles_active), two thirds of it FFMA2",
-                "ncu_fp32_pipe_busy_pct": 61.5}
+                        "is not counted as flops, but Philox's IMAD.WIDE runs on the same FP32 pipe (`ncu`: sm__pipe_fma_cycles_active "
+                        "and the other counters of the profiled build, read from profiles/roofline_figures.json)",
+                "ncu": sweep_ncu,
+                "ncu_fp32_pipe_busy_pct": sweep_ncu["fp32_pipe_busy_pct"] if sweep_ncu else None}
     # quantile stage of the last path step: 3 radix passes + 1 tail pass over 4-byte values
     xq = torch.randn(my_paths, device="cuda")
     for _ in range(3):
@@ -379,13 +455,21 @@ def run_ours(args):
                          "note": "4 B/value/pass, 3 radix passes + digit-selection kernels + tail pass, device-resident (one host round trip); 40 MB stays L2-resident after pass 1"}
     del xq
     p_achieved = my_paths * N_STEPS * flops_per_path_step(n) / paths_kernel_s / 1e12
-    paths_roofline = {"bound": "fp32-simt", "kernel": "path_kernel_packed<16> (Philox, FFMA2)", "achieved": p_achieved, "peak": fma_peak,
-                      "unit": "TFLOP/s", "frac": p_achieved / fma_peak, "traffic": None,
-                      "algorithmic_flop_per_path_step": flops_per_path_step(n), "kernel_ms": paths_kernel_s * 1e3}
+    tc_paths = os.environ.get("MCP_PATHS_TC", "1") != "0"
+    paths_ncu = ncu_figures("path_kernel_tc" if tc_paths else "path_kernel_packed<16>")
+    paths_roofline = {"bound": "fp32-simt",
+                      "kernel": ("path_kernel_tc<16> (Philox + Box-Muller on SIMT warps, L.z on tcgen05: FP16-split normals from TMEM x L' images in "
+                                 "shared memory, FP32 accumulate; histogram of the terminal values in the epilogue)") if tc_paths else
+                                "path_kernel_packed<16> (Philox, FFMA2)",
+                      "achieved": p_achieved, "peak": fma_peak,
+                      "unit": "TFLOP/s", "frac": p_achieved / fma_peak, "traffic": paths_ncu["dram_bytes"] if paths_ncu else None,
+                      "algorithmic_flop_per_path_step": flops_per_path_step(n), "kernel_ms": paths_kernel_s * 1e3, "ncu": paths_ncu,
+                      "note": "algorithmic FP32 flop (N^2 + 3N per path-step) over the kernel time against the FFMA-chain peak; the generator "
+                              "(Philox IMAD/LOP3, Box-Muller MUFU) is not counted as flop and is most of the instruction stream"}
 
     # ---- HBM-bound mode of the same kernel: write-back of all arrays (76 B / portfolio) ----
     wb = None
-    if world == 1:
+    if solo:
         Pw = 50_000_000
         for _ in range(2):
             r = mcp.simulate_portfolios(mu, sigma, Pw, risk_free=RISK_FREE, seed=SEED, return_arrays="device", device=local)
@@ -398,24 +482,24 @@ def run_ours(args):
 
     # ---- the FP64 arithmetic of the same sweep (the parity dtype), against the measured FP64 FMA peak ----
     fp64 = None
-    if world == 1:
+    if solo:
         P64 = 2_000_000_000
         for _ in range(2):
             r64 = mcp.simulate_portfolios(mu, sigma, P64, risk_free=RISK_FREE, seed=SEED, return_arrays=False, dtype="float64", device=local)
         peak64 = max(eng.measure_fma_peak("float64") for _ in range(3))
         a64 = P64 * flops_per_portfolio(n) / (r64.kernel_ms * 1e-3) / 1e12
         fp64 = {"metric": "portfolios/sec (16 assets, FP64)", "value": P64 / (r64.kernel_ms * 1e-3), "unit": "portfolios/s", "dtype": "f64",
-                "roofline": {"bound": "fp64-simt", "kernel": "small_sweep<double,16,K=2> (Philox, 32-bit uniforms, table + degree-9 polynomial log2)",
+                "roofline": {"bound": "fp64-simt", "kernel": "small_sweep<double,16,K=2> (Philox, 32-bit uniforms, 1024-entry table + degree-5 polynomial log2)",
                              "achieved": a64, "peak": peak64, "unit": "TFLOP/s", "frac": a64 / peak64,
                              "peak_source": "DFMA-chain microbenchmark (mcp_measure_fma_peak), best of 3",
                              "algorithmic_flop_per_portfolio": flops_per_portfolio(n), "kernel_ms": r64.kernel_ms,
-                             "note": "the FP64 log2 of the 16 uniforms (software: ~10 DFMA each after the table lookup; libdevice's "
+                             "note": "the FP64 log2 of the 16 uniforms (software: 6 DFMA each after the table lookup; libdevice's "
                                      "log2 made this kernel 2.1x slower) shares the FP64 pipe with the 184 DFMA of the forms; FP64 "
                                      "is the parity dtype, not the throughput path"}}
 
     # ---- e2e with full arrays back to host (C2-shaped: 1e6 portfolios, 76 MB D2H per step) ----
     e2e_arrays = None
-    if world == 1:
+    if solo:
         Pa = 1_000_000
         out = {"weights": mcp.pinned_empty((Pa, n), np.float32), "returns": mcp.pinned_empty((Pa,), np.float32),
                "risks": mcp.pinned_empty((Pa,), np.float32), "sharpes": mcp.pinned_empty((Pa,), np.float32),
@@ -432,7 +516,7 @@ def run_ours(args):
 
     # ---- the reference's actual loop body (app.py:699-717 incl. historical VaR/CVaR), f1 ----
     hist_line = None
-    if world == 1:
+    if solo:
         Th, Ph = 365, 1_000_000
         Rh = np.random.default_rng(0).standard_normal((Th, n)) * 0.05
         for _ in range(2):
@@ -449,7 +533,8 @@ def run_ours(args):
         hist_line = {"metric": "portfolios/sec, full reference loop body (return, risk, Sharpe, historical VaR+CVaR over T=365)",
                      "value": Ph / dt, "unit": "portfolios/s", "ms_per_step": dt * 1e3,
                      "workload": "simulate_method('CVaR'): 1e6 Philox portfolios, all arrays to host, T=365 x N=16 returns matrix "
-                                 "(e2e through the public API; pageable host arrays)",
+                                 "(e2e through the public API: mu/Sigma estimated on the device, weights kept on the GPU between the sweep and "
+                                 "the historical kernel, -cvar written by the kernel, one copy per array into pooled page-locked memory)",
                      "opt_idx": mo["opt_idx"],
                      "kernel": {"name": "hist_var_fast<12> (4 portfolios per warp, FFMA2 series, sorting network + REDUX pop-min)", "portfolios_per_s": Ph / (hv["kernel_ms"] * 1e-3),
                                 "kernel_ms": hv["kernel_ms"],
@@ -463,7 +548,7 @@ def run_ours(args):
 
     # ---- the app's own size: one rerun of tab 3 = 5 methods x 2500 portfolios (app.py:681-682) ----
     app_line = None
-    if world == 1:
+    if solo:
         Ra = np.random.default_rng(1).standard_normal((365, n)) * 0.05
         def rerun():
             for m in mcp.METHODS:
@@ -480,7 +565,7 @@ def run_ours(args):
 
     # ---- CPU baseline on this box's host cores (bounded sample) ----
     cpu, cpu_paths, verbatim = None, None, None
-    if world == 1 and not args.no_cpu_baseline:
+    if solo and not args.no_cpu_baseline:
         from oracle import cpu_baseline as cb
         cores = cb.host_cores()
         pool = cb._pool(cores)
@@ -494,15 +579,16 @@ def run_ours(args):
 
     rec_bytes = 2 * (5 + n) * 8 + 48 + 8
     line = {
-        "metric": "portfolios/sec (16 assets)", "value": value, "unit": "portfolios/s", "n_gpus": world,
+        "metric": "portfolios/sec (16 assets)", "value": value, "unit": "portfolios/s", "n_gpus": ndev,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"C3: synthetic 16-asset mu/Sigma, {p_total:.0e} random-weight portfolios per step sharded over "
-                               f"{world} GPU(s), in-kernel Philox4x32-10, no write-back, max-Sharpe + 30%-risk picks, "
-                               "NCCL all_gather merge" + ("" if p_total == P_TOTAL else " (REDUCED --portfolios)"),
+                               f"{ndev} GPU(s), in-kernel Philox4x32-10, no write-back, max-Sharpe + 30%-risk picks, "
+                               + ("one process, one host thread + libmcp handle per GPU, " if sp and ndev > 1 else "")
+                               + "selection records merged by ncclAllGather inside libmcp" + ("" if p_total == P_TOTAL else " (REDUCED --portfolios)"),
                    "n_assets": n, "portfolios_per_step": p_total, "risk_free": RISK_FREE, "risk_target": RISK_TARGET,
                    "seed": SEED, "l2": "256 MiB fill between steps (outside the event pairs); the kernel reads no global memory",
-                   "parallelism": f"index-range sharding x{world}, no data-path collective"},
+                   "parallelism": f"index-range sharding x{ndev}, no data-path collective" + (" (single process)" if sp and ndev > 1 else "")},
         "selected": {"max_sharpe_index": res.max_sharpe["global_index"], "max_sharpe": res.max_sharpe["sharpe"],
                      "target_risk_index": res.target_risk["global_index"], "target_risk": res.target_risk["risk"]},
         "e2e": {"value": e2e_value, "unit": "portfolios/s", "h2d_bytes_per_step": 8 * (n + n * n),
@@ -525,7 +611,31 @@ def run_ours(args):
         "historical": hist_line,
         "app_rerun": app_line,
     }
+    line["philox7"] = {"note": "same workloads on Philox4x32-7 (philox_rounds=7: Random123's Crush-resistant minimum; a different stream of the "
+                               "same law, tested value by value against the 7-round restatement and statistically; NOT the default)",
+                       "sweep": {"value": p_total * r7_steps / r7_dev_s, "unit": "portfolios/s", "kernel_ms": statistics.mean(r7_kms),
+                                 "max_sharpe_index": r7_res.max_sharpe["global_index"], "target_risk_index": r7_res.target_risk["global_index"]},
+                       "paths": {"value": m_total * N_STEPS * r7_steps / r7p_dev_s, "unit": "path-steps/s", "kernel_ms": statistics.mean(r7p_kms),
+                                 "stats": {str(a): list(v) for a, v in r7p_res["stats"].items()}}}
+    mismatches = check_expected(line, args, ndev)
+    r5 = lambda x: float(f"{x:.5g}")
+    st = p_res["stats"]
+    # compact and LAST: the driver keeps the tail of stdout, so the second metric and the cross-N invariants must sit here
+    line["summary"] = {
+        "n": ndev, "sp": int(sp), "c3_pfs": r5(value), "c3_ms": r5(dev_s / args.steps * 1e3), "c3_kern_ms": r5(kernel_s * 1e3), "c3_frac": r5(roofline["frac"]),
+        "idx_sharpe": res.max_sharpe["global_index"], "idx_risk": res.target_risk["global_index"],
+        "c4_path_steps_s": r5(paths_value), "c4_ms": r5(p_dev_s / args.steps * 1e3), "c4_kern_ms": r5(paths_kernel_s * 1e3), "c4_frac": r5(paths_roofline["frac"]),
+        "var_cvar": {str(a): [round(v, 9), round(c, 9)] for a, (v, c) in st.items()},
+        "c5_pfs": r5(env_line["value"]) if env_line else None, "c5_bins": env_line["filled_bins"] if env_line else None,
+        "c5_idx": env_line["target_risk"]["index"] if env_line else None,
+        "r7_c3_pfs": r5(line["philox7"]["sweep"]["value"]), "r7_c4": r5(line["philox7"]["paths"]["value"]),
+        "expected": "ok" if not mismatches else mismatches}
     os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if mismatches:
+        print("bench: results differ from tests/golden/c3c4c5_expected.json: " + "; ".join(mismatches), file=sys.stderr)
+        if world > 1:
+            dist.destroy_process_group()
+        sys.exit(3)
     if world > 1:
         dist.destroy_process_group()
 
@@ -540,6 +650,8 @@ def main():
     ap.add_argument("--paths", type=int, default=M_PATHS, help="paths per step (default: C4's 1e7)")
     ap.add_argument("--envelope-portfolios", type=int, default=P_LARGE, help="C5 portfolios per step (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--single-process", action="store_true",
+                    help="with --gpus N: ONE process drives all N GPUs (devices=[0..N-1], NCCL inside libmcp) instead of torchrun ranks")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print(f"note: --warmup {args.warmup} < 3 breaks the timing rules", file=sys.stderr)

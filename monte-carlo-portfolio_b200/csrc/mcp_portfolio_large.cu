@@ -73,6 +73,7 @@ __host__ __device__ inline int lg_row_offset(int k, int np) {
 // slot states
 constexpr int ST_INACTIVE = 0, ST_PENDING = 1, ST_ACCEPTED = 2, ST_SKIPPED = 3;
 
+template <int ROUNDS>
 __global__ void __launch_bounds__(LG_THREADS, 1) large_sweep(const LargeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* sSt = reinterpret_cast<float*>(smem_raw);                 // [st_floats]
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) large_sweep(const LargeArgs a) 
                 const bool live = sState[gp] == ST_PENDING;
                 for (int G = gc; G < a.np / 16; G += 4) {          // 16-asset group = 16 fields = Philox blocks 3G .. 3G+2
                     uint32_t f[16];
-                    philox_fields<16>(c0, c1, (uint32_t)attempt, STREAM_WEIGHTS | (uint32_t)(3 * G), a.k0, a.k1, f);
+                    philox_fields<16, ROUNDS>(c0, c1, (uint32_t)attempt, STREAM_WEIGHTS | (uint32_t)(3 * G), a.k0, a.k1, f);
 #pragma unroll
                     for (int k = 0; k < 16; ++k) {
                         const int i = 16 * G + k;
@@ -339,7 +340,7 @@ template <typename T> __device__ __forceinline__ T warp_sum_t(T v) {
     return v;
 }
 
-template <typename T>
+template <typename T, int ROUNDS>
 __global__ void __launch_bounds__(GEN_THREADS) generic_sweep(const GenArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -370,8 +371,8 @@ __global__ void __launch_bounds__(GEN_THREADS) generic_sweep(const GenArgs<T> a)
                         // 24-bit fields 4b .. 4b+3 = words 3b .. 3b+2 of the stream (one or two Philox blocks)
                         const int w0 = 3 * b, b0 = w0 >> 2, b1 = (w0 + 2) >> 2;
                         uint32_t y0[4], y1[4];
-                        philox4x32_10(c0, c1, (uint32_t)attempt, STREAM_WEIGHTS | (uint32_t)b0, a.k0, a.k1, y0);
-                        if (b1 != b0) philox4x32_10(c0, c1, (uint32_t)attempt, STREAM_WEIGHTS | (uint32_t)b1, a.k0, a.k1, y1);
+                        philox4x32_r<ROUNDS>(c0, c1, (uint32_t)attempt, STREAM_WEIGHTS | (uint32_t)b0, a.k0, a.k1, y0);
+                        if (b1 != b0) philox4x32_r<ROUNDS>(c0, c1, (uint32_t)attempt, STREAM_WEIGHTS | (uint32_t)b1, a.k0, a.k1, y1);
                         uint32_t w3[3];
 #pragma unroll
                         for (int j = 0; j < 3; ++j) {
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(GEN_THREADS) generic_sweep(const GenArgs<T> a)
                         }
                         fields_from_triple(w3[0], w3[1], w3[2], x);
                     } else {
-                        philox4x32_10(c0, c1, (uint32_t)attempt, STREAM_WEIGHTS | (uint32_t)b, a.k0, a.k1, x);
+                        philox4x32_r<ROUNDS>(c0, c1, (uint32_t)attempt, STREAM_WEIGHTS | (uint32_t)b, a.k0, a.k1, x);
                     }
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -528,12 +529,13 @@ static int large_launch_tiled(mcp_context* h, PfJob& job) {
     if (smem > h->prop.sharedMemPerBlockOptin)
         return mcp_fail(h, MCP_ERR_INVALID, "large_sweep: N=%d needs %zu B of shared memory (max %zu)", n, smem,
                         (size_t)h->prop.sharedMemPerBlockOptin);
-    MCP_CUDA(h, cudaFuncSetAttribute(large_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = job.rounds == 7 ? large_sweep<7> : large_sweep<10>;
+    MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t n_tiles = (job.P + LG_TP - 1) / LG_TP;
     uint64_t grid = std::min<uint64_t>((uint64_t)h->prop.multiProcessorCount, n_tiles);
     grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, job.max_blocks));
     job.blocks_used = (int)grid;
-    large_sweep<<<(unsigned)grid, LG_THREADS, smem, job.stream>>>(a);
+    kern<<<(unsigned)grid, LG_THREADS, smem, job.stream>>>(a);
     MCP_CUDA(h, cudaGetLastError());
     h->launches++;
     return MCP_OK;
@@ -573,14 +575,15 @@ static int large_launch_generic(mcp_context* h, PfJob& job) {
     a.k0 = (uint32_t)job.seed; a.k1 = (uint32_t)(job.seed >> 32);
     a.rf = (T)job.rf; a.target = (T)job.target;
     const size_t smem = (size_t)GEN_WARPS * np * sizeof(T);
-    if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(generic_sweep<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = job.rounds == 7 ? generic_sweep<T, 7> : generic_sweep<T, 10>;
+    if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    MCP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, generic_sweep<T>, GEN_THREADS, smem));
+    MCP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GEN_THREADS, smem));
     if (per_sm < 1) return mcp_fail(h, MCP_ERR_CUDA, "generic_sweep: zero occupancy (smem %zu B)", smem);
     uint64_t grid = std::min<uint64_t>((uint64_t)h->prop.multiProcessorCount * per_sm, (job.P + GEN_WARPS - 1) / GEN_WARPS);
     grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, job.max_blocks));
     job.blocks_used = (int)grid;
-    generic_sweep<T><<<(unsigned)grid, GEN_THREADS, smem, job.stream>>>(a);
+    kern<<<(unsigned)grid, GEN_THREADS, smem, job.stream>>>(a);
     MCP_CUDA(h, cudaGetLastError());
     h->launches++;
     return MCP_OK;

@@ -93,7 +93,7 @@ struct TcArgs {
 __host__ __device__ inline uint32_t tc_hi_off(int c) { return 2048u * (uint32_t)(c * (c + 1)); }     // bytes before chunk c
 __host__ __device__ inline uint32_t tc_lo_off(int c) { return 1024u * (uint32_t)(c * (c + 1)); }
 
-template <bool F16>
+template <bool F16, int ROUNDS>
 __global__ void __launch_bounds__(TcCfg<F16>::THREADS, 1) large_sweep_tc(const TcArgs a) {
     constexpr int TC_GROUPS = TcCfg<F16>::GROUPS, TC_EPI_WARP0 = TcCfg<F16>::EPI_WARP0, TC_MMA_WARP = TcCfg<F16>::MMA_WARP;
     constexpr uint32_t TC_STAGE_COLS = TcCfg<F16>::STAGE_COLS;
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(TcCfg<F16>::THREADS, 1) large_sweep_tc(const T
                 } else {
                     // ---- Philox: 24-bit fields 32c .. 32c+31 = blocks 6c .. 6c+5; l = lg2(U) = -e ----
                     uint32_t f[TC_KC];
-                    philox_fields<TC_KC>(c0, c1, 0u, STREAM_WEIGHTS | (uint32_t)(6 * c), a.rk, f);
+                    philox_fields<TC_KC, ROUNDS>(c0, c1, 0u, STREAM_WEIGHTS | (uint32_t)(6 * c), a.rk, f);
 #pragma unroll
                     for (int j = 0; j < TC_KC; j += 2) {          // U = 2 - f in (0, 1], two per FFMA2 (same values as unit_open0)
                         const float2 m2 = make_float2(__uint_as_float(mant_or(f[j], one_bits)), __uint_as_float(mant_or(f[j + 1], one_bits)));
@@ -470,7 +470,7 @@ static bool tc_use_f16(const PfJob& job) {
 
 template <bool F16>
 static int tc_launch(mcp_context* h, PfJob& job, const TcArgs& a, size_t table_bytes) {
-    auto kern = large_sweep_tc<F16>;
+    auto kern = job.rounds == 7 ? large_sweep_tc<F16, 7> : large_sweep_tc<F16, 10>;
     const size_t smem = table_bytes + (3 * TC_MAX_GROUPS + 3) * sizeof(uint64_t) + 4 * sizeof(PfCand) + 4 * sizeof(unsigned int) + 8 * sizeof(uint4) + 32;
     if (smem > h->prop.sharedMemPerBlockOptin)
         return mcp_fail(h, MCP_ERR_INVALID, "large_sweep_tc: N=%d needs %zu B of shared memory (max %zu)", job.n, smem, (size_t)h->prop.sharedMemPerBlockOptin);

@@ -46,13 +46,13 @@ struct SmallArgs {
 
 // One flat-Dirichlet draw: e[i] = -lg2(U_i), s = sum over the real assets (padded assets keep a
 // draw but are masked out of s, and their Sigma / mu entries are 0, so they never contribute).
-template <typename T, int NP>
+template <typename T, int NP, int ROUNDS>
 __device__ __forceinline__ void draw_exponentials(const SmallArgs<T, NP>& a, uint32_t c0, uint32_t c1,
                                                   uint32_t attempt, T (&e)[NP], T& s) {
     s = (T)0;
     if constexpr (sizeof(T) == 4) {           // FP32: 24-bit fields, 3 Philox calls per 16 uniforms
         uint32_t f[NP];
-        philox_fields<NP>(c0, c1, attempt, STREAM_WEIGHTS, a.k0, a.k1, f);
+        philox_fields<NP, ROUNDS>(c0, c1, attempt, STREAM_WEIGHTS, a.k0, a.k1, f);
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
             e[i] = -Math<T>::lg2(Math<T>::unit_open0(f[i]));
@@ -62,7 +62,7 @@ __device__ __forceinline__ void draw_exponentials(const SmallArgs<T, NP>& a, uin
 #pragma unroll
         for (int b = 0; b < NP / 4; ++b) {
             uint32_t x[4];
-            philox4x32_10(c0, c1, attempt, STREAM_WEIGHTS | (uint32_t)b, a.k0, a.k1, x);
+            philox4x32_r<ROUNDS>(c0, c1, attempt, STREAM_WEIGHTS | (uint32_t)b, a.k0, a.k1, x);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int i = 4 * b + k;
@@ -100,16 +100,16 @@ __device__ __forceinline__ bool in_bounds(const SmallArgs<T, NP>& a, const T (&e
 }
 
 // Draw with bounds rejection (app.py:700-707): returns accepted?; e / s hold the last draw.
-template <typename T, int NP, bool BOUNDS>
+template <typename T, int NP, bool BOUNDS, int ROUNDS>
 __device__ __forceinline__ bool draw_accepted(const SmallArgs<T, NP>& a, uint64_t gidx, T (&e)[NP], T& s) {
     const uint32_t c0 = (uint32_t)gidx, c1 = (uint32_t)(gidx >> 32);
     if (!BOUNDS) {
-        draw_exponentials<T, NP>(a, c0, c1, 0u, e, s);
+        draw_exponentials<T, NP, ROUNDS>(a, c0, c1, 0u, e, s);
         return true;
     }
     bool ok = false;
     for (int t = 0; t < a.max_tries && !ok; ++t) {
-        draw_exponentials<T, NP>(a, c0, c1, (uint32_t)t, e, s);
+        draw_exponentials<T, NP, ROUNDS>(a, c0, c1, (uint32_t)t, e, s);
         ok = in_bounds<T, NP>(a, e, Math<T>::rcp(s));
     }
     return ok || (a.keep_last != 0);
@@ -196,7 +196,7 @@ __device__ __forceinline__ void quad_and_dot_k(const SmallArgs<T, NP>& a, const 
     }
 }
 
-template <typename T, int NP, int K, int SRC /*0 Philox, 1 supplied*/, bool BOUNDS>
+template <typename T, int NP, int K, int SRC /*0 Philox, 1 supplied*/, bool BOUNDS, int ROUNDS>
 __global__ void __launch_bounds__(PF_BLOCK) small_sweep(const __grid_constant__ SmallArgs<T, NP> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -265,14 +265,14 @@ __global__ void __launch_bounds__(PF_BLOCK) small_sweep(const __grid_constant__ 
                 }
                 if (BOUNDS) accepted[k] = active && (in_bounds<T, NP>(a, e[k], (T)1) || a.keep_last != 0);
             } else if (BOUNDS) {
-                if (active) accepted[k] = draw_accepted<T, NP, true>(a, a.first + local, e[k], s[k]);
+                if (active) accepted[k] = draw_accepted<T, NP, true, ROUNDS>(a, a.first + local, e[k], s[k]);
                 else {
 #pragma unroll
                     for (int i = 0; i < NP; ++i) e[k][i] = (T)0;
                 }
             } else {
                 // no rejection loop: draw unconditionally (tail threads draw too, results unused)
-                draw_accepted<T, NP, false>(a, a.first + local, e[k], s[k]);
+                draw_accepted<T, NP, false, ROUNDS>(a, a.first + local, e[k], s[k]);
             }
         }
 
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(PF_BLOCK) small_sweep(const __grid_constant__ 
 // OUT = false is the instance the 10^10-portfolio sweep runs: nothing is written per portfolio, so the
 // per-portfolio pointer tests, staging addresses and stores are not even compiled in (the kernel is
 // issue-bound: they were about 1/8 of its instruction stream).
-template <int NP, int K, bool OUT>
+template <int NP, int K, bool OUT, int ROUNDS>
 __global__ void __launch_bounds__(PF_BLOCK) small_sweep_packed(const __grid_constant__ SmallArgs<float, NP> a) {
     static_assert(K % 2 == 0, "packed sweep pairs portfolios");
     constexpr int KP = K / 2;
@@ -411,8 +411,8 @@ __global__ void __launch_bounds__(PF_BLOCK) small_sweep_packed(const __grid_cons
             const uint64_t ga = a.first + local0 + (uint64_t)(2 * kp) * PF_BLOCK, gb = ga + PF_BLOCK;
             s2[kp] = make_float2(0.f, 0.f);
             uint32_t fa[NP], fb[NP];
-            philox_fields<NP>((uint32_t)ga, (uint32_t)(ga >> 32), 0u, STREAM_WEIGHTS, a.rk, fa);
-            philox_fields<NP>((uint32_t)gb, (uint32_t)(gb >> 32), 0u, STREAM_WEIGHTS, a.rk, fb);
+            philox_fields<NP, ROUNDS>((uint32_t)ga, (uint32_t)(ga >> 32), 0u, STREAM_WEIGHTS, a.rk, fa);
+            philox_fields<NP, ROUNDS>((uint32_t)gb, (uint32_t)(gb >> 32), 0u, STREAM_WEIGHTS, a.rk, fb);
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
                 const float2 f = make_float2(__uint_as_float(mant_or(fa[i], one_bits)), __uint_as_float(mant_or(fb[i], one_bits)));
@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(PF_BLOCK) small_sweep_packed(const __grid_cons
 
 // Re-evaluates the selected portfolios with exactly the sweep's arithmetic and emits
 // (index, key, ret, risk, sharpe, weights[N]) records in FP64.
-template <typename T, int NP>
+template <typename T, int NP, int ROUNDS>
 __global__ void small_replay(const __grid_constant__ SmallArgs<T, NP> a, int n_sel, uint64_t idx0, uint64_t idx1,
                              const T* rows, int bounds, double* rec) {
     const int k = threadIdx.x;
@@ -587,9 +587,9 @@ __global__ void small_replay(const __grid_constant__ SmallArgs<T, NP> a, int n_s
 #pragma unroll
         for (int i = 0; i < NP; ++i) e[i] = i < a.n ? rows[(size_t)k * a.n + i] : (T)0;
     } else if (bounds) {
-        draw_accepted<T, NP, true>(a, gidx, e, s);
+        draw_accepted<T, NP, true, ROUNDS>(a, gidx, e, s);
     } else {
-        draw_accepted<T, NP, false>(a, gidx, e, s);
+        draw_accepted<T, NP, false, ROUNDS>(a, gidx, e, s);
     }
     T q, r, ret, risk, sharpe;
     quad_and_dot<T, NP>(a, e, q, r);
@@ -643,8 +643,10 @@ static void fill_small_args(const PfJob& job, SmallArgs<T, NP>& a) {
 template <typename T, int NP, int K>
 static int small_launch_k(mcp_context* h, PfJob& job, const SmallArgs<T, NP>& a) {
     void (*kern)(SmallArgs<T, NP>) = nullptr;
-    if (job.w_in) kern = job.bounds ? small_sweep<T, NP, K, 1, true> : small_sweep<T, NP, K, 1, false>;
-    else kern = job.bounds ? small_sweep<T, NP, K, 0, true> : small_sweep<T, NP, K, 0, false>;
+    const bool r7 = job.rounds == 7;                 // supplied weights draw nothing: one instance
+    if (job.w_in) kern = job.bounds ? small_sweep<T, NP, K, 1, true, 10> : small_sweep<T, NP, K, 1, false, 10>;
+    else if (job.bounds) kern = r7 ? small_sweep<T, NP, K, 0, true, 7> : small_sweep<T, NP, K, 0, true, 10>;
+    else kern = r7 ? small_sweep<T, NP, K, 0, false, 7> : small_sweep<T, NP, K, 0, false, 10>;
     const bool staging = job.w_in != nullptr || job.w_out != nullptr;
     const size_t smem = staging ? (size_t)(PF_BLOCK / 32) * 32 * (job.n + 4) * sizeof(T) : 0;
     if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -666,7 +668,8 @@ static int small_launch_k(mcp_context* h, PfJob& job, const SmallArgs<T, NP>& a)
 template <int NP, int K>
 static int small_launch_packed(mcp_context* h, PfJob& job, const SmallArgs<float, NP>& a) {
     const bool any_out = job.w_out || job.ret_out || job.risk_out || job.sharpe_out || job.acc_out;
-    auto kern = any_out ? small_sweep_packed<NP, K, true> : small_sweep_packed<NP, K, false>;
+    auto kern = any_out ? small_sweep_packed<NP, K, true, 10> : small_sweep_packed<NP, K, false, 10>;
+    if (job.rounds == 7) kern = any_out ? small_sweep_packed<NP, K, true, 7> : small_sweep_packed<NP, K, false, 7>;
     const size_t smem = job.w_out ? (size_t)(PF_BLOCK / 32) * 32 * (job.n + 4) * sizeof(float) : 0;
     if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -708,8 +711,8 @@ template <typename T, int NP>
 int pf_small_replay_t(mcp_context* h, const PfJob& job, const PfReplay& rp) {
     SmallArgs<T, NP> a;
     fill_small_args<T, NP>(job, a);
-    small_replay<T, NP><<<1, 32, 0, job.stream>>>(a, rp.n_sel, rp.idx[0], rp.idx[1], (const T*)rp.rows,
-                                                 job.bounds ? 1 : 0, rp.rec);
+    auto kern = job.rounds == 7 ? small_replay<T, NP, 7> : small_replay<T, NP, 10>;
+    kern<<<1, 32, 0, job.stream>>>(a, rp.n_sel, rp.idx[0], rp.idx[1], (const T*)rp.rows, job.bounds ? 1 : 0, rp.rec);
     MCP_CUDA(h, cudaGetLastError());
     h->launches++;
     return MCP_OK;

@@ -54,7 +54,7 @@ def philox4x32(c0, c1, c2, c3, k0, k1, rounds: int = 10):
     return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
 
 
-def _raw_outputs(index, sub, n_outputs, stream, seed):
+def _raw_outputs(index, sub, n_outputs, stream, seed, rounds=10):
     """uint32 array (len(index), n_outputs): output j = word j%4 of block j//4."""
     index = np.asarray(index, dtype=np.uint64)
     lo = (index & MASK32)[:, None]
@@ -65,15 +65,15 @@ def _raw_outputs(index, sub, n_outputs, stream, seed):
     sub = np.asarray(sub, dtype=np.uint64)
     sub = sub[:, None] if sub.ndim == 1 else sub
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-    r = philox4x32(lo, hi, sub, c3, seed & 0xFFFFFFFF, seed >> 32)
+    r = philox4x32(lo, hi, sub, c3, seed & 0xFFFFFFFF, seed >> 32, rounds)
     out = np.stack(r, axis=-1).reshape(index.shape[0], nblk * 4)
     return out[:, :n_outputs]
 
 
-def _fields24(index, sub, n_fields, stream, seed):
+def _fields24(index, sub, n_fields, stream, seed, rounds=10):
     """uint32 array (len(index), n_fields) of 23-bit fractions: the float32 kernels' uniform fields."""
     n_trip = (n_fields + 3) // 4
-    w = _raw_outputs(index, sub, 3 * n_trip + ((-3 * n_trip) % 4), stream, seed).astype(np.uint64)
+    w = _raw_outputs(index, sub, 3 * n_trip + ((-3 * n_trip) % 4), stream, seed, rounds).astype(np.uint64)
     a, b, c = w[:, 0:3 * n_trip:3], w[:, 1:3 * n_trip:3], w[:, 2:3 * n_trip:3]
     f = np.empty((w.shape[0], 4 * n_trip), dtype=np.uint64)
     f[:, 0::4] = a
@@ -83,7 +83,7 @@ def _fields24(index, sub, n_fields, stream, seed):
     return (f[:, :n_fields] & np.uint64(0x7FFFFF)).astype(np.uint32)
 
 
-def exponentials(index, attempt, n_assets, seed, dtype="float32"):
+def exponentials(index, attempt, n_assets, seed, dtype="float32", rounds=10):
     """Base-2 exponentials e = -log2(U), U in (0, 1].
 
     float32: U = 1 - field * 2^-23 (23 mantissa bits, built on the GPU with one LOP3 as a
@@ -92,15 +92,15 @@ def exponentials(index, attempt, n_assets, seed, dtype="float32"):
     """
     sub = np.broadcast_to(np.asarray(attempt, dtype=np.uint64), np.shape(index))
     if dtype == "float32":
-        u = 1.0 - _fields24(index, sub, n_assets, STREAM_WEIGHTS, seed).astype(np.float64) * 2.0 ** -23
+        u = 1.0 - _fields24(index, sub, n_assets, STREAM_WEIGHTS, seed, rounds).astype(np.float64) * 2.0 ** -23
     else:
-        x = _raw_outputs(index, sub, n_assets, STREAM_WEIGHTS, seed)
+        x = _raw_outputs(index, sub, n_assets, STREAM_WEIGHTS, seed, rounds)
         u = 1.0 - x.astype(np.float64) * 2.0 ** -32
     return -np.log2(u)
 
 
 def dirichlet_weights(first_index, n_portfolios, n_assets, seed, dtype="float32",
-                      min_weights=None, max_weights=None, max_tries=100, keep_last=False):
+                      min_weights=None, max_weights=None, max_tries=100, keep_last=False, rounds=10):
     """Flat-Dirichlet weights for global indices [first, first+P) with bounds rejection.
 
     Mirrors the reference's loop (app.py:699-707): attempt t = 0..max_tries-1, accept the
@@ -116,7 +116,7 @@ def dirichlet_weights(first_index, n_portfolios, n_assets, seed, dtype="float32"
         sel = np.nonzero(pending)[0]
         if sel.size == 0:
             break
-        e = exponentials(idx[sel], t, n_assets, seed, dtype)
+        e = exponentials(idx[sel], t, n_assets, seed, dtype, rounds)
         w = e / e.sum(axis=1, keepdims=True)
         if dtype == "float32":
             # bounds are compared in the kernel's arithmetic type
@@ -140,7 +140,7 @@ def dirichlet_weights(first_index, n_portfolios, n_assets, seed, dtype="float32"
     return W, valid
 
 
-def normals(first_index, n_paths, n_steps, n_assets, seed, dtype="float32"):
+def normals(first_index, n_paths, n_steps, n_assets, seed, dtype="float32", rounds=10):
     """Standard normals Z[m, s, i] by Box-Muller on output pairs (2k, 2k+1).
 
     U1 in (0,1] from output 2k, angle fraction f in [0,1) from output 2k+1:
@@ -153,9 +153,9 @@ def normals(first_index, n_paths, n_steps, n_assets, seed, dtype="float32"):
     Z = np.empty((n_paths, n_steps, n_assets))
     for s in range(n_steps):
         if dtype == "float32":
-            f = _fields24(idx, np.full(n_paths, s, dtype=np.uint64), n_even, STREAM_NORMALS, seed).astype(np.float64) * 2.0 ** -23
+            f = _fields24(idx, np.full(n_paths, s, dtype=np.uint64), n_even, STREAM_NORMALS, seed, rounds).astype(np.float64) * 2.0 ** -23
         else:
-            x = _raw_outputs(idx, np.full(n_paths, s, dtype=np.uint64), n_even, STREAM_NORMALS, seed)
+            x = _raw_outputs(idx, np.full(n_paths, s, dtype=np.uint64), n_even, STREAM_NORMALS, seed, rounds)
             f = x.astype(np.float64) * 2.0 ** -32
         u1 = 1.0 - f[:, 0::2]
         th = np.pi * (2.0 * f[:, 1::2] - 1.0)

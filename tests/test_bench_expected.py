@@ -1,0 +1,50 @@
+"""CPU tier: bench.py's expected-results gate (tests/golden/c3c4c5_expected.json) and its compact summary contract."""
+import argparse
+import copy
+import json
+import os
+
+import bench
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _line(want):
+    return {"selected": dict(want["c3"]), "paths": {"stats": {a: list(v) for a, v in want["c4"]["stats"].items()}},
+            "envelope": {"target_risk": {"index": want["c5"]["target_risk_index"]}, "filled_bins": want["c5"]["filled_bins"]}}
+
+
+def test_expected_file_and_gate():
+    with open(os.path.join(ROOT, "tests", "golden", "c3c4c5_expected.json")) as fh:
+        want = json.load(fh)
+    assert set(want["c4"]["stats"]) == {"0.95", "0.99"}
+    for v, c in want["c4"]["stats"].values():
+        assert c < v                                   # CVaR = mean of the tail below the VaR quantile (app.py:258-263)
+    args = argparse.Namespace(portfolios=bench.P_TOTAL, paths=bench.M_PATHS, envelope_portfolios=bench.P_LARGE)
+    good = _line(want)
+    assert bench.check_expected(good, args, 1) == []
+    # a kernel variant that rounds the contraction differently moves VaR by ~1e-7: inside the tolerance
+    near = copy.deepcopy(good)
+    near["paths"]["stats"]["0.95"][0] += 3e-7
+    assert bench.check_expected(near, args, 8) == []
+    for mutate in (lambda l: l["selected"].__setitem__("max_sharpe_index", 1),
+                   lambda l: l["selected"].__setitem__("target_risk_index", 2),
+                   lambda l: l["paths"]["stats"]["0.99"].__setitem__(1, 0.3),
+                   lambda l: l["envelope"].__setitem__("filled_bins", 433),
+                   lambda l: l["envelope"]["target_risk"].__setitem__("index", 5)):
+        bad = copy.deepcopy(good)
+        mutate(bad)
+        assert len(bench.check_expected(bad, args, 1)) == 1
+    # reduced sizes are not the golden job: nothing to compare
+    small = argparse.Namespace(portfolios=10 ** 6, paths=1000, envelope_portfolios=0)
+    bad = copy.deepcopy(good)
+    bad["selected"]["max_sharpe_index"] = 1
+    bad["envelope"] = None
+    assert bench.check_expected(bad, small, 1) == []
+
+
+def test_ncu_figures_come_from_the_committed_file():
+    f = bench.ncu_figures("small_sweep_packed<16, 4, 0, 10>") or bench.ncu_figures("small_sweep_packed<16, 4, 0>")
+    assert f is not None and 0 < f["fp32_pipe_busy_pct"] < 100 and f["source"].startswith("profiles/")
+    assert isinstance(f["digest_matches_build"], bool)
+    assert bench.ncu_figures("no such kernel") is None

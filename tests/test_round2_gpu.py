@@ -127,6 +127,20 @@ def test_philox7_is_a_different_stream_with_the_same_distribution(mcp):
     assert np.allclose(r7.weights.var(0), 15 / (16 * 16 * 17), rtol=0.03)
     own = ref.evaluate(np.asarray(r7.weights, dtype=np.float64), mu, sigma, 0.0, 0.30)
     assert np.allclose(r7.risks, own["risks"], rtol=1e-4) and r7.max_sharpe["index"] == int(np.argmax(r7.sharpes))
+    # value by value against the 7-round restatement: every sweep kernel family and the path kernels
+    W7, _ = philox_np.dirichlet_weights(0, 3000, 16, seed=3, rounds=7)
+    assert np.allclose(r7.weights[:3000], W7, atol=2e-6)
+    sel = mcp.simulate_portfolios(mu, sigma, 200_000, seed=3, philox_rounds=7, return_arrays=False)     # packed, selection only
+    assert sel.max_sharpe["global_index"] == r7.max_sharpe["index"] and sel.target_risk["global_index"] == r7.target_risk["index"]
+    for n, dt in ((16, "float64"), (70, "float32"), (40, "float64"), (300, "float32")):
+        mu_n, s_n = synthetic_inputs(n)
+        lo = np.zeros(n) if n == 70 else None                      # N = 70 with (vacuous) bounds: the tiled SIMT kernel, else tcgen05
+        rr = mcp.simulate_portfolios(mu_n, s_n, 500, seed=11, philox_rounds=7, dtype=dt, min_weights=lo)
+        Wn, _ = philox_np.dirichlet_weights(0, 500, n, seed=11, dtype=dt, rounds=7)
+        assert np.allclose(rr.weights, Wn, atol=2e-6 if dt == "float32" else 1e-12), (n, dt)
+    Z7 = philox_np.normals(77, 300, 9, 16, 5, "float32", rounds=7)
+    p7 = mcp.simulate_paths(mu, sigma, w, 300, 9, seed=5, first_index=77, return_terminal=True, philox_rounds=7)
+    assert np.allclose(p7["terminal"] + 1.0, paths_np.terminal_returns(mu, sigma, w, Z7) + 1.0, rtol=1e-4)
 
 
 # ---- wide universes (32 < N) -----------------------------------------------------------------------------------------
@@ -239,7 +253,7 @@ def test_pinned_pool_recycles_blocks(mcp):
     gc.collect()
     b = mcp.pinned_empty((1 << 20,), np.float32)
     assert b.ctypes.data == addr                    # same block, no new cudaHostAlloc
-    assert api._pinned_pool.idle == 0
+    assert not api._pinned_pool.free.get(4 << 20)   # ... and it left the idle list of its size class
     del b
 
 
@@ -279,9 +293,12 @@ def test_recheck_overflow_falls_back_to_a_full_fp64_pass(mcp):
     occurrence, and the call says that it took the slow route."""
     mu, sigma = synthetic_inputs(16)
     rng = np.random.default_rng(5)
-    W = np.tile(np.full(16, 1 / 16), (20_000, 1))
-    W[:100] = rng.dirichlet(np.ones(16) * 50, size=100)            # a few other rows, all worse or better: the oracle decides
+    head = rng.dirichlet(np.ones(16) * 50, size=100)
+    best = int(np.argmax(ref.evaluate(head, mu, sigma, 0.03, 0.30)["sharpes"]))
+    W = np.tile(head[best], (20_000, 1))                           # 19 900 copies of the best row: more exact ties than RC_CAP = 8192
+    W[:100] = head
     want = ref.evaluate(W, mu, sigma, 0.03, 0.30)
+    assert want["max_sharpe"]["index"] == best
     for src in ("host", "device"):
         if src == "device":
             import torch
