@@ -35,8 +35,10 @@ struct mcp_context {
     // [12..13] 1/sum(e) per portfolio of the tcgen05 sweep (per stream), [14] host-buffer collectives (mcp_comm_allgather /
     // allreduce), [15] merge block of a sharded call (records, counts, bins: send + gathered), [16] terminal values of
     // mcp_paths_stats when the caller does not want them, [17] first radix histogram filled by the path kernel,
-    // [18] mu / Sigma estimation (returns matrix, results), [19] historical recheck (candidate lists, FP64 rows)
-    mcp_scratch dev[20];
+    // [18] mu / Sigma estimation (returns matrix, results), [19] historical recheck (candidate lists, FP64 rows),
+    // [20] constants of the tiled SIMT sweep when it runs next to the tcgen05 sweep (bounded route), [21..22] deferred-row
+    // list of the bounded tcgen05 sweep (per pipeline stream)
+    mcp_scratch dev[24];
     // pinned host scratch: [0..1] HOST-space staging of pageable outputs (per pipeline slot), [2] inputs, [3] collectives,
     // [4] small results (records / stats) read back with one copy
     mcp_scratch pinned[6];

@@ -54,6 +54,13 @@ struct PfJob {
     uint64_t lg_table_epoch = 0;       // != 0: the SIMT large-sweep constants (S' / Sigma, mu, bounds) of THIS call sit in slot 6 under that epoch
     int lg_table_kind = -1;            // which kernel family / dtype they were laid out for (0 tiled FP32, 1 generic FP32, 2 generic FP64)
     int rounds = 10;                   // Philox4x32 rounds (10 default, 7 optional)
+    // list mode of the tiled SIMT sweep: evaluate the portfolios idx_list[0 .. *idx_count) (device memory) instead of a contiguous
+    // range; outputs go to row (index - first).  Used for the rows the bounded tensor-core sweep defers.
+    const uint64_t* idx_list = nullptr;
+    const unsigned long long* idx_count = nullptr;
+    const uint16_t* idx_attempt = nullptr;   // optional, per listed row: the attempt number of its first draw in this launch
+    bool lgl_uploaded = false;         // the list-mode / bounded-route copy of the tiled kernel's constants (slot 20) is in place
+    int tc_bounds_route = 0;           // != 0: this call's bounded sweep runs on the tcgen05 kernel with the tiled SIMT kernel beside it
 };
 
 // Replay of selected portfolios: regenerates (RNG mode) or re-reads (supplied mode, `rows`
@@ -97,9 +104,16 @@ int pf_small_launch(mcp_context* h, PfJob& job);
 int pf_small_replay(mcp_context* h, const PfJob& job, const PfReplay& rp);
 int pf_large_launch(mcp_context* h, PfJob& job);
 int pf_large_replay(mcp_context* h, const PfJob& job, const PfReplay& rp);
-// tcgen05 path of the large sweep (mcp_portfolio_large_tc.cu): FP32, 32 < N <= 256, no bounds (Philox or supplied weights)
+// tcgen05 path of the large sweep (mcp_portfolio_large_tc.cu): FP32, 32 < N <= 256; Philox rows with or without bounds, supplied
+// weights without bounds
 bool pf_large_tc_eligible(const PfJob& job);
 int pf_large_launch_tc(mcp_context* h, PfJob& job);
+// Bounds rejection on the tensor-core sweep (app.py:700-707): the tcgen05 kernel evaluates every portfolio's attempt 0 and accepts
+// the rows that are inside the bounds with a safety margin; the others (rejected, or too close to a bound to call in this kernel's
+// summation order) are appended to a device list and go through the tiled SIMT kernel (pf_large_launch_list), which redraws with
+// attempt + 1 exactly as before.  Accept / skip decisions and attempt numbers are therefore the SIMT kernel's.
+int pf_large_launch_tc_bounded(mcp_context* h, PfJob& job);
+int pf_large_launch_list(mcp_context* h, PfJob& job);            // tiled SIMT kernel over job.idx_list
 
 // implemented per (type, padded N) in mcp_portfolio_small_inst.cu
 template <typename T, int NP> int pf_small_launch_t(mcp_context* h, PfJob& job);

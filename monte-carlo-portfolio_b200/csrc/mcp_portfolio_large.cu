@@ -58,6 +58,11 @@ struct LargeArgs {
     PfCand* cands;
     unsigned long long* n_accepted;
     uint64_t first, P;
+    // list mode (the tensor-core sweep's deferred rows, mcp_portfolio_large_tc.cu): row p of this launch is the portfolio with
+    // global index list[p], *list_count rows in all (a device-side count: no host round trip between the two kernels)
+    const uint64_t* list;
+    const unsigned long long* list_count;
+    const uint16_t* list_att;        // optional: attempts row p has already used up (its first draw here is attempt list_att[p])
     int n, np, st_floats;
     int max_tries, keep_last, bounds;
     uint32_t k0, k1;
@@ -85,7 +90,8 @@ __global__ void __launch_bounds__(LG_THREADS, 1) large_sweep(const LargeArgs a) 
     float* sSum = sRedR + LG_WARPS * LG_TP;                          // [LG_TP] sum(e)
     float* sInv = sSum + LG_TP;                                      // [LG_TP] 1 / sum(e)
     int* sState = reinterpret_cast<int*>(sInv + LG_TP);              // [LG_TP]
-    int* sFlag = sState + LG_TP;                                     // [1] "some row must be redrawn"
+    int* sFlag = sState + LG_TP;                                     // [1] "some row must be redrawn" (4 ints reserved)
+    int* sStart = sFlag + 4;                                         // [LG_TP] attempt number of the row's first draw (list mode)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < a.st_floats; i += LG_THREADS) sSt[i] = a.st[i];
@@ -98,7 +104,9 @@ __global__ void __launch_bounds__(LG_THREADS, 1) large_sweep(const LargeArgs a) 
     const int gp = tid >> 2, gc = tid & 3;      // generation role: portfolio slot, block phase
     const bool supplied = a.w_in != nullptr;
 
-    const uint64_t n_tiles = (a.P + LG_TP - 1) / LG_TP;
+    const bool listed = a.list != nullptr;
+    const uint64_t P = listed ? (uint64_t)*a.list_count : a.P;
+    const uint64_t n_tiles = (P + LG_TP - 1) / LG_TP;
     float best_s = -Math<float>::inf(), best_d = -Math<float>::inf();
     uint64_t idx_s = MCP_NO_INDEX, idx_d = MCP_NO_INDEX;
     float rmin = Math<float>::inf(), rmax = -Math<float>::inf();
@@ -106,8 +114,11 @@ __global__ void __launch_bounds__(LG_THREADS, 1) large_sweep(const LargeArgs a) 
 
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t p0 = tile * LG_TP;
-        const int rows = (a.P - p0) < (uint64_t)LG_TP ? (int)(a.P - p0) : LG_TP;
-        if (tid < LG_TP) sState[tid] = tid < rows ? ST_PENDING : ST_INACTIVE;
+        const int rows = (P - p0) < (uint64_t)LG_TP ? (int)(P - p0) : LG_TP;
+        if (tid < LG_TP) {
+            sState[tid] = tid < rows ? ST_PENDING : ST_INACTIVE;
+            sStart[tid] = (listed && a.list_att != nullptr && tid < rows) ? (int)a.list_att[p0 + tid] : 0;
+        }
         __syncthreads();
         const int tries = (a.bounds && !supplied) ? a.max_tries : 1;
         for (int attempt = 0; attempt < tries; ++attempt) {
@@ -119,12 +130,12 @@ __global__ void __launch_bounds__(LG_THREADS, 1) large_sweep(const LargeArgs a) 
                     sW[i * LG_WSTRIDE + p] = (p < rows && i < a.n) ? src[(size_t)p * a.n + i] : 0.f;
                 }
             } else if (sState[gp] == ST_PENDING || (attempt == 0 && sState[gp] == ST_INACTIVE)) {
-                const uint64_t gidx = a.first + p0 + gp;
+                const uint64_t gidx = listed ? (gp < rows ? a.list[p0 + gp] : 0ull) : a.first + p0 + gp;
                 const uint32_t c0 = (uint32_t)gidx, c1 = (uint32_t)(gidx >> 32);
                 const bool live = sState[gp] == ST_PENDING;
                 for (int G = gc; G < a.np / 16; G += 4) {          // 16-asset group = 16 fields = Philox blocks 3G .. 3G+2
                     uint32_t f[16];
-                    philox_fields<16, ROUNDS>(c0, c1, (uint32_t)attempt, STREAM_WEIGHTS | (uint32_t)(3 * G), a.k0, a.k1, f);
+                    philox_fields<16, ROUNDS>(c0, c1, (uint32_t)(attempt + sStart[gp]), STREAM_WEIGHTS | (uint32_t)(3 * G), a.k0, a.k1, f);
 #pragma unroll
                     for (int k = 0; k < 16; ++k) {
                         const int i = 16 * G + k;
@@ -229,7 +240,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) large_sweep(const LargeArgs a) 
                 ok &= __shfl_xor_sync(0xffffffffu, ok, 2);
                 if (gc == 0 && sState[gp] == ST_PENDING) {
                     if (ok) sState[gp] = ST_ACCEPTED;
-                    else if (attempt + 1 < tries) sFlag[0] = 1;                   // benign race: all writers store 1
+                    else if (attempt + sStart[gp] + 1 < tries) sFlag[0] = 1;      // benign race: all writers store 1
                     else sState[gp] = a.keep_last ? ST_ACCEPTED : ST_SKIPPED;
                 }
             } else if (tid < LG_TP && sState[tid] == ST_PENDING) {
@@ -242,8 +253,8 @@ __global__ void __launch_bounds__(LG_THREADS, 1) large_sweep(const LargeArgs a) 
 
         // ---- 4c. metrics, selection, write-back ----
         if (tid < LG_TP) {
-            const uint64_t local = p0 + tid;
             const bool active = tid < rows;
+            const uint64_t local = listed ? (active ? a.list[p0 + tid] - a.first : 0ull) : p0 + tid;    // row in the output arrays
             const bool accepted = sState[tid] == ST_ACCEPTED;
             float q = 0.f, r = 0.f;
             for (int w = 0; w < LG_WARPS; ++w) { q += sRedQ[w * LG_TP + tid]; r += sRedR[w * LG_TP + tid]; }
@@ -252,9 +263,10 @@ __global__ void __launch_bounds__(LG_THREADS, 1) large_sweep(const LargeArgs a) 
             if (accepted) {
                 ++n_acc;
                 const uint64_t g = a.first + local;
-                if (sharpe > best_s) { best_s = sharpe; idx_s = g; }       // tiles ascend: first occurrence kept
+                // tiles ascend: the first occurrence is kept (a list is in arrival order, so ties compare indices there)
+                if (sharpe > best_s || (listed && sharpe == best_s && g < idx_s)) { best_s = sharpe; idx_s = g; }
                 const float d = -fabsf(risk - a.target);
-                if (d > best_d) { best_d = d; idx_d = g; }
+                if (d > best_d || (listed && d == best_d && g < idx_d)) { best_d = d; idx_d = g; }
                 rmin = fminf(rmin, risk);
                 rmax = fmaxf(rmax, risk);
             }
@@ -271,7 +283,8 @@ __global__ void __launch_bounds__(LG_THREADS, 1) large_sweep(const LargeArgs a) 
             const int total = rows * a.n;
             for (int f = tid; f < total; f += LG_THREADS) {
                 const int p = f / a.n, i = f - p * a.n;
-                dst[f] = sW[i * LG_WSTRIDE + p] * sInv[p];
+                if (listed) a.w_out[(a.list[p0 + p] - a.first) * (uint64_t)a.n + i] = sW[i * LG_WSTRIDE + p] * sInv[p];
+                else dst[f] = sW[i * LG_WSTRIDE + p] * sInv[p];
             }
         }
         __syncthreads();
@@ -504,14 +517,19 @@ static int large_launch_tiled(mcp_context* h, PfJob& job) {
         hhi[i] = (i < n && job.hi) ? (float)job.hi[i] : 1e30f;
     }
     float* dev = nullptr;
-    MCP_CHECK(mcp_dev_reserve(h, 6, host.size() * sizeof(float), (void**)&dev));
+    // next to the tcgen05 sweep (bounded route) this kernel's constants live in their own slot: slot 6 holds that kernel's table
+    const bool beside_tc = job.tc_bounds_route != 0 || job.idx_list != nullptr;
+    MCP_CHECK(mcp_dev_reserve(h, beside_tc ? 20 : 6, host.size() * sizeof(float), (void**)&dev));
     // once per mcp_portfolios call: later chunks (other pipeline streams included) and the replays reuse the table
-    if (job.lg_table_epoch == 0 || job.lg_table_epoch != h->const_epoch || job.lg_table_kind != 0) {
+    if (beside_tc ? !job.lgl_uploaded : (job.lg_table_epoch == 0 || job.lg_table_epoch != h->const_epoch || job.lg_table_kind != 0)) {
         MCP_CUDA(h, cudaDeviceSynchronize());                  // another pipeline stream may still read the previous table
         MCP_CUDA(h, cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, job.stream));
         MCP_CUDA(h, cudaStreamSynchronize(job.stream));        // `host` is pageable and dies at scope exit
-        job.lg_table_epoch = ++h->const_epoch;
-        job.lg_table_kind = 0;
+        if (beside_tc) job.lgl_uploaded = true;
+        else {
+            job.lg_table_epoch = ++h->const_epoch;
+            job.lg_table_kind = 0;
+        }
     }
 
     LargeArgs a;
@@ -520,12 +538,13 @@ static int large_launch_tiled(mcp_context* h, PfJob& job) {
     a.ret_out = (float*)job.ret_out; a.risk_out = (float*)job.risk_out; a.sharpe_out = (float*)job.sharpe_out;
     a.acc_out = job.acc_out; a.cands = job.cands; a.n_accepted = job.n_accepted;
     a.first = job.first; a.P = job.P; a.n = n; a.np = np; a.st_floats = st_floats;
+    a.list = job.idx_list; a.list_count = job.idx_count; a.list_att = job.idx_attempt;
     a.max_tries = job.max_tries; a.keep_last = job.keep_last; a.bounds = job.bounds ? 1 : 0;
     a.k0 = (uint32_t)job.seed; a.k1 = (uint32_t)(job.seed >> 32);
     a.rf = (float)job.rf; a.target = (float)job.target;
     (void)G;
     const size_t smem = ((size_t)st_floats + (size_t)np * LG_WSTRIDE + np + 3 * LG_WARPS * LG_TP + 2 * LG_TP) * sizeof(float) +
-                        (LG_TP + 4) * sizeof(int);
+                        (2 * LG_TP + 4) * sizeof(int);
     if (smem > h->prop.sharedMemPerBlockOptin)
         return mcp_fail(h, MCP_ERR_INVALID, "large_sweep: N=%d needs %zu B of shared memory (max %zu)", n, smem,
                         (size_t)h->prop.sharedMemPerBlockOptin);
@@ -589,8 +608,13 @@ static int large_launch_generic(mcp_context* h, PfJob& job) {
     return MCP_OK;
 }
 
+int pf_large_launch_list(mcp_context* h, PfJob& job) {
+    if (!use_tiled(job)) return mcp_fail(h, MCP_ERR_INVALID, "list mode needs the tiled FP32 sweep (n_assets <= %d)", LG_MAX_N);
+    return large_launch_tiled(h, job);
+}
+
 int pf_large_launch(mcp_context* h, PfJob& job) {
-    if (pf_large_tc_eligible(job)) return pf_large_launch_tc(h, job);
+    if (pf_large_tc_eligible(job)) return job.bounds ? pf_large_launch_tc_bounded(h, job) : pf_large_launch_tc(h, job);
     if (use_tiled(job)) return large_launch_tiled(h, job);
     return job.dtype == MCP_F64 ? large_launch_generic<double>(h, job) : large_launch_generic<float>(h, job);
 }

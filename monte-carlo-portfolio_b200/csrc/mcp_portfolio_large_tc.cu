@@ -60,6 +60,7 @@ constexpr int TC_KC = 32;                    // K (assets) per chunk
 constexpr int TC_MAX_N = 256;
 constexpr uint32_t TC_COL_A = 256;           // first TMEM column of the A stages (accumulator = columns 0..255)
 constexpr int TC_MAX_GROUPS = 4;
+constexpr uint64_t TC_BOUNDED_MIN_P = 1ull << 15, TC_BOUNDED_MAX_P = 1ull << 31;     // per launch; the deferred-row list is 8 B per row of a sub-range
 // Two operand splits share the kernel (template parameter F16):
 //   TF32 split (any FP32 input, so supplied weights use it): stage = hi 32 + lo 32 + bf16 16 = 80 columns, 3 stages / generator groups
 //   FP16 split (Philox rows: |lg2 U| <= 24 fits FP16):        stage = h1 16 + h2 16 + l 32 = 64 columns, 4 stages / generator groups
@@ -88,13 +89,45 @@ struct TcArgs {
     PhiloxKeys rk;
     float rf, target;
     float qscale;                            // FP16 split: S' is stored times a power of two, q comes back times that; this undoes it
+    // BOUNDS instances (Philox rows, app.py:700-707): the table carries three more float[np] arrays behind mu -- 1 / max_weight
+    // (0 where the bound cannot bite), 1 / min_weight and an additive term that takes unconstrained / padded assets out of the
+    // minimum.  One launch evaluates ONE attempt of its rows (the contiguous range, or in_list[0 .. *in_count) in the later
+    // rounds): rows inside the bounds with a margin are accepted; rows outside with a margin go to retry_list (next round,
+    // attempt + 1) or are skipped / kept when this was the last attempt; rows too close to a bound to call in this kernel's
+    // summation order go to simt_list with the attempt they are at, and the tiled SIMT kernel decides them.
+    const uint64_t* in_list;
+    const unsigned long long* in_count;
+    uint64_t* retry_list;
+    unsigned long long* retry_count;
+    uint64_t* simt_list;
+    uint16_t* simt_att;
+    unsigned long long* simt_count;
+    uint32_t attempt;
+    int max_tries, keep_last;
+    int has_lo;                              // some min_weight > 0
 };
+
+// warp-aggregated append of `v` to list[(*count)++] for the lanes with `take` (called by all 32 lanes)
+__device__ __forceinline__ unsigned long long warp_append(bool take, unsigned long long* count, int lane) {
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    if (m == 0u) return 0ull;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (unsigned)__popc(m & ((1u << lane) - 1u));
+}
+
+// min / max of three (sm_100: one FMNMX3)
+__device__ __forceinline__ float fmin3(float a, float b, float c) { float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+__device__ __forceinline__ float fmax3(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
 
 __host__ __device__ inline uint32_t tc_hi_off(int c) { return 2048u * (uint32_t)(c * (c + 1)); }     // bytes before chunk c
 __host__ __device__ inline uint32_t tc_lo_off(int c) { return 1024u * (uint32_t)(c * (c + 1)); }
 
-template <bool F16, int ROUNDS>
+template <bool F16, int ROUNDS, bool BOUNDS>
 __global__ void __launch_bounds__(TcCfg<F16>::THREADS, 1) large_sweep_tc(const TcArgs a) {
+    static_assert(!BOUNDS || F16, "bounds rejection runs on the Philox (FP16-split) instance");
     constexpr int TC_GROUPS = TcCfg<F16>::GROUPS, TC_EPI_WARP0 = TcCfg<F16>::EPI_WARP0, TC_MMA_WARP = TcCfg<F16>::MMA_WARP;
     constexpr uint32_t TC_STAGE_COLS = TcCfg<F16>::STAGE_COLS;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -104,7 +137,10 @@ __global__ void __launch_bounds__(TcCfg<F16>::THREADS, 1) large_sweep_tc(const T
     unsigned char* sHi = smem;
     unsigned char* sLo = smem + hi_bytes;
     float* sMu = reinterpret_cast<float*>(sLo + lo_bytes);                                       // [np]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sMu + a.np);
+    const float* sInvHi = sMu + a.np;                                                            // [np] each, BOUNDS only
+    const float* sInvLo = sInvHi + a.np;
+    const float* sBiasLo = sInvLo + a.np;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sMu + (BOUNDS ? 4 : 1) * a.np);
     uint64_t* a_full = bars;                           // [G]  128 arrivals: the stage's A operand is in TMEM
     uint64_t* d_done = bars + TC_MAX_GROUPS;           // [G]  tcgen05.commit: the stage's MMAs are complete
     uint64_t* a_free = bars + 2 * TC_MAX_GROUPS;       // [G]  128 arrivals: the epilogue has read the stage back
@@ -124,7 +160,7 @@ __global__ void __launch_bounds__(TcCfg<F16>::THREADS, 1) large_sweep_tc(const T
         mbar_init(drained, TC_ROWS);
         mbar_init(table_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t bytes = hi_bytes + lo_bytes + (uint32_t)a.np * 4u;
+        const uint32_t bytes = hi_bytes + lo_bytes + (uint32_t)a.np * (BOUNDS ? 16u : 4u);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(table_bar)), "r"(bytes) : "memory");
         for (uint32_t off = 0; off < bytes; off += 32768u) {
             const uint32_t part = bytes - off < 32768u ? bytes - off : 32768u;
@@ -142,7 +178,9 @@ __global__ void __launch_bounds__(TcCfg<F16>::THREADS, 1) large_sweep_tc(const T
     mbar_wait(table_bar, 0u);                                          // every consumer of S' / mu waits for the bytes to land
     const uint32_t tmem = *tmem_slot;
 
-    const uint64_t n_tiles = (a.P + TC_ROWS - 1) / TC_ROWS;
+    const bool listed = BOUNDS && a.in_list != nullptr;
+    const uint64_t P = listed ? (uint64_t)*a.in_count : a.P;
+    const uint64_t n_tiles = (P + TC_ROWS - 1) / TC_ROWS;
 
     if (warp < TC_EPI_WARP0) {
         // ================= generators: Philox -> lg2 -> split -> A stage =================
@@ -155,9 +193,10 @@ __global__ void __launch_bounds__(TcCfg<F16>::THREADS, 1) large_sweep_tc(const T
         uint32_t first_mod = 0;                          // (tl * C) mod G
         for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const uint64_t p0 = tile * TC_ROWS;
-            const uint64_t gidx = a.first + p0 + (uint64_t)row;
+            const bool live = p0 + (uint64_t)row < P;
+            const uint64_t gidx = listed ? (live ? a.in_list[p0 + (uint64_t)row] : 0ull) : a.first + p0 + (uint64_t)row;
+            const uint64_t out_row = BOUNDS ? gidx - a.first : p0 + (uint64_t)row;      // row in the output arrays
             const uint32_t c0 = (uint32_t)gidx, c1 = (uint32_t)(gidx >> 32);
-            const bool live = p0 + (uint64_t)row < a.P;
             for (int ci = (int)((g + (uint32_t)TC_GROUPS - first_mod) % (uint32_t)TC_GROUPS); ci < C; ci += TC_GROUPS, ++k) {
                 const int c = C - 1 - ci;
                 float l[TC_KC];
@@ -178,7 +217,7 @@ __global__ void __launch_bounds__(TcCfg<F16>::THREADS, 1) large_sweep_tc(const T
                 } else {
                     // ---- Philox: 24-bit fields 32c .. 32c+31 = blocks 6c .. 6c+5; l = lg2(U) = -e ----
                     uint32_t f[TC_KC];
-                    philox_fields<TC_KC, ROUNDS>(c0, c1, 0u, STREAM_WEIGHTS | (uint32_t)(6 * c), a.rk, f);
+                    philox_fields<TC_KC, ROUNDS>(c0, c1, BOUNDS ? a.attempt : 0u, STREAM_WEIGHTS | (uint32_t)(6 * c), a.rk, f);
 #pragma unroll
                     for (int j = 0; j < TC_KC; j += 2) {          // U = 2 - f in (0, 1], two per FFMA2 (same values as unit_open0)
                         const float2 m2 = make_float2(__uint_as_float(mant_or(f[j], one_bits)), __uint_as_float(mant_or(f[j + 1], one_bits)));
@@ -194,7 +233,7 @@ __global__ void __launch_bounds__(TcCfg<F16>::THREADS, 1) large_sweep_tc(const T
                 }
                 if (a.w_out != nullptr && live) {         // raw values (e = -l, or the supplied weight); tc_scale_rows normalises them
                     const float sg = a.w_in != nullptr ? 1.f : -1.f;
-                    float* dst = a.w_out + (p0 + (uint64_t)row) * (uint64_t)a.n + (uint64_t)i0;
+                    float* dst = a.w_out + out_row * (uint64_t)a.n + (uint64_t)i0;
                     if ((a.n & 3) == 0) {
 #pragma unroll
                         for (int m = 0; m < 8; ++m)
@@ -334,6 +373,9 @@ __global__ void __launch_bounds__(TcCfg<F16>::THREADS, 1) large_sweep_tc(const T
         uint32_t g = 0, cyc = 0;
         for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             float2 q2 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f), r2 = make_float2(0.f, 0.f);     // .x: even assets, .y: odd assets
+            // BOUNDS: w_i <= hi_i  <=>  e_i / hi_i <= s and w_i >= lo_i  <=>  e_i / lo_i >= s, on l = -e: running min of l / hi and
+            // running max of l / lo (+ a term that removes unconstrained assets) -- one FFMA2 + one three-input min / max per pair
+            float mn_hi = 0.f, mx_lo = -Math<float>::inf();
             for (int ci = 0; ci < C; ++ci) {
                 const int c = C - 1 - ci;
                 const uint32_t st = lane_base + TC_COL_A + TC_STAGE_COLS * g;
@@ -376,22 +418,67 @@ __global__ void __launch_bounds__(TcCfg<F16>::THREADS, 1) large_sweep_tc(const T
                         s2 = fma2(lb, bcast2(1.0f), s2);
                         r2 = fma2(la, make_float2(u.x, u.y), r2);
                         r2 = fma2(lb, make_float2(u.z, u.w), r2);
+                        if constexpr (BOUNDS) {
+                            const float4 ih = reinterpret_cast<const float4*>(sInvHi + TC_KC * c + 16 * h)[m];
+                            const float2 ta = fma2(la, make_float2(ih.x, ih.y), bcast2(0.f)), tb = fma2(lb, make_float2(ih.z, ih.w), bcast2(0.f));
+                            mn_hi = fmin3(mn_hi, ta.x, ta.y);
+                            mn_hi = fmin3(mn_hi, tb.x, tb.y);
+                            if (a.has_lo) {
+                                const float4 il = reinterpret_cast<const float4*>(sInvLo + TC_KC * c + 16 * h)[m];
+                                const float4 bl = reinterpret_cast<const float4*>(sBiasLo + TC_KC * c + 16 * h)[m];
+                                const float2 va = fma2(la, make_float2(il.x, il.y), make_float2(bl.x, bl.y));
+                                const float2 vb = fma2(lb, make_float2(il.z, il.w), make_float2(bl.z, bl.w));
+                                mx_lo = fmax3(mx_lo, va.x, va.y);
+                                mx_lo = fmax3(mx_lo, vb.x, vb.y);
+                            }
+                        }
                     }
                 }
                 if (++g == TC_GROUPS) { g = 0; ++cyc; }
             }
-            const uint64_t local = tile * TC_ROWS + (uint64_t)row;
-            if (local < a.P) {
+            const uint64_t lrow = tile * TC_ROWS + (uint64_t)row;                // row of this launch
+            const bool live = lrow < P;
+            const uint64_t gi = (BOUNDS && listed) ? (live ? a.in_list[lrow] : 0ull) : a.first + lrow;
+            const uint64_t local = BOUNDS ? gi - a.first : lrow;                   // row in the output arrays
+            bool take = live;
+            if constexpr (BOUNDS) {
+                // w_i <= hi_i for all i  <=>  max e_i / hi_i <= sum(e), and the mirror image for the lower bounds.  This kernel's
+                // sum(e) differs from the SIMT kernel's in the last bits, so only verdicts with a margin far above that (1e-5
+                // relative against ~1e-7) are taken here; the rest is decided by the SIMT kernel, whose accept / skip decisions
+                // and attempt numbers therefore hold for every row.
+                const float s = -(s2.x + s2.y), up = s * (1.f + 1e-5f), dn = s * (1.f - 1e-5f);
+                const float mx = -mn_hi, mn = -mx_lo;
+                const bool inside = mx <= dn && (!a.has_lo || mn >= up);
+                const bool outside = mx > up || (a.has_lo && mn < dn);
+                const bool last = (int)a.attempt + 1 >= a.max_tries;
+                const bool retry = live && outside && !last;
+                const bool unsure = live && !inside && !outside;
+                take = live && (inside || (outside && last && a.keep_last != 0));
+                const bool skip = live && outside && last && a.keep_last == 0;     // app.py:706-707
+                const unsigned long long rpos = warp_append(retry, a.retry_count, lane);
+                if (retry) a.retry_list[rpos] = gi;
+                const unsigned long long spos = warp_append(unsure, a.simt_count, lane);
+                if (unsure) { a.simt_list[spos] = gi; a.simt_att[spos] = (uint16_t)a.attempt; }
+                if (live && !take && a.inv_out) a.inv_out[local] = 0.f;            // not this row's final draw
+                if (skip) {
+                    const float nanv = Math<float>::nan();
+                    if (a.ret_out) a.ret_out[local] = nanv;
+                    if (a.risk_out) a.risk_out[local] = nanv;
+                    if (a.sharpe_out) a.sharpe_out[local] = nanv;
+                    if (a.acc_out) a.acc_out[local] = 0;
+                }
+            }
+            if (take) {
                 const bool supplied = a.w_in != nullptr;
                 const float q = F16 ? (q2.x + q2.y) * a.qscale : q2.x + q2.y;
                 const float s = supplied ? 1.f : -(s2.x + s2.y), r = supplied ? (r2.x + r2.y) : -(r2.x + r2.y);         // Philox rows hold l = -e
                 float ret, risk, sharpe;
                 metrics_from<float>(q, r, s, a.rf, supplied, ret, risk, sharpe);
                 ++n_acc;
-                const uint64_t gi = a.first + local;
-                if (sharpe > best_s) { best_s = sharpe; idx_s = gi; }          // tiles ascend per thread: first occurrence kept
+                // tiles ascend per thread: the first occurrence is kept (a list is in arrival order: ties compare indices there)
+                if (sharpe > best_s || (BOUNDS && sharpe == best_s && gi < idx_s)) { best_s = sharpe; idx_s = gi; }
                 const float d = -fabsf(risk - a.target);
-                if (d > best_d) { best_d = d; idx_d = gi; }
+                if (d > best_d || (BOUNDS && d == best_d && gi < idx_d)) { best_d = d; idx_d = gi; }
                 rmin = fminf(rmin, risk);
                 rmax = fmaxf(rmax, risk);
                 if (a.ret_out) a.ret_out[local] = ret;
@@ -437,6 +524,16 @@ __global__ void __launch_bounds__(256) tc_scale_rows(float* w, const float* inv,
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) w[i] *= inv[i / (uint64_t)n];
 }
 
+// the same for the rows of one retry round: row = list[r] - first
+__global__ void __launch_bounds__(256) tc_scale_rows_list(float* w, const float* inv, const uint64_t* list, const unsigned long long* count,
+                                                           uint64_t first, int n) {
+    const uint64_t total = (uint64_t)*count * (uint64_t)n;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t row = list[i / (uint64_t)n] - first;
+        w[row * (uint64_t)n + i % (uint64_t)n] *= inv[row];
+    }
+}
+
 // ---- host side -------------------------------------------------------------------------------
 
 static inline float tf32_round(float x) {          // round-to-nearest-even onto 10 explicit mantissa bits
@@ -458,7 +555,12 @@ static inline uint16_t bf16_round(float x) {
 bool pf_large_tc_eligible(const PfJob& job) {
     const char* v = getenv("MCP_LARGE_TC");               // "0" forces the SIMT kernel (A/B tests, benchmarks)
     if (v && v[0] == '0') return false;
-    return job.dtype == MCP_F32 && job.n > PF_SMALL_MAX_N && job.n <= TC_MAX_N && !job.bounds;
+    if (!(job.dtype == MCP_F32 && job.n > PF_SMALL_MAX_N && job.n <= TC_MAX_N)) return false;
+    if (!job.bounds) return true;
+    // bounds: Philox rows only, and only launches big enough to be worth two kernels (a replay is one portfolio: SIMT)
+    const char* b = getenv("MCP_LARGE_TC_BOUNDS");        // "0": bounded sweeps stay on the SIMT kernel (A/B tests)
+    if (b && b[0] == '0') return false;
+    return job.w_in == nullptr && job.idx_list == nullptr && job.P >= TC_BOUNDED_MIN_P && job.P <= TC_BOUNDED_MAX_P;
 }
 
 // FP16 split: Philox rows only (|lg2 U| <= 24 is inside FP16's range; supplied weights may be any FP32 value), MCP_LARGE_TC_F16=0 disables
@@ -468,9 +570,9 @@ static bool tc_use_f16(const PfJob& job) {
     return job.w_in == nullptr;
 }
 
-template <bool F16>
+template <bool F16, bool BOUNDS = false>
 static int tc_launch(mcp_context* h, PfJob& job, const TcArgs& a, size_t table_bytes) {
-    auto kern = job.rounds == 7 ? large_sweep_tc<F16, 7> : large_sweep_tc<F16, 10>;
+    auto kern = job.rounds == 7 ? large_sweep_tc<F16, 7, BOUNDS> : large_sweep_tc<F16, 10, BOUNDS>;
     const size_t smem = table_bytes + (3 * TC_MAX_GROUPS + 3) * sizeof(uint64_t) + 4 * sizeof(PfCand) + 4 * sizeof(unsigned int) + 8 * sizeof(uint4) + 32;
     if (smem > h->prop.sharedMemPerBlockOptin)
         return mcp_fail(h, MCP_ERR_INVALID, "large_sweep_tc: N=%d needs %zu B of shared memory (max %zu)", job.n, smem, (size_t)h->prop.sharedMemPerBlockOptin);
@@ -485,11 +587,30 @@ static int tc_launch(mcp_context* h, PfJob& job, const TcArgs& a, size_t table_b
     return MCP_OK;
 }
 
-int pf_large_launch_tc(mcp_context* h, PfJob& job) {
+// Lists of one bounded round (device memory): input rows (null = the contiguous range), rows to redraw, rows for the SIMT kernel
+struct TcRound {
+    const uint64_t* in_list = nullptr;
+    const unsigned long long* in_count = nullptr;
+    uint64_t* retry_list = nullptr;
+    unsigned long long* retry_count = nullptr;
+    uint64_t* simt_list = nullptr;
+    uint16_t* simt_att = nullptr;
+    unsigned long long* simt_count = nullptr;
+    int attempt = 0;
+    float* inv_out = nullptr;          // 1 / sum(e) scratch of the whole sub-range (allocated by the first round)
+};
+
+// One tcgen05 sweep over job's range.  round != null: the BOUNDS instance (FP16 split, Philox rows), one attempt of the round's rows.
+static int tc_launch_range(mcp_context* h, PfJob& job, TcRound* round) {
+    const bool bounded = round != nullptr;
     const int n = job.n, np = std::max(64, (n + TC_KC - 1) / TC_KC * TC_KC), C = np / TC_KC;
-    const bool f16 = tc_use_f16(job);
+    const bool f16 = bounded || tc_use_f16(job);
+    const int table_kind = bounded ? 2 : (f16 ? 1 : 0);
     const uint32_t lo_bytes = tc_lo_off(C), hi_bytes = f16 ? lo_bytes : tc_hi_off(C);
-    const size_t table_bytes = (size_t)hi_bytes + lo_bytes + (size_t)np * 4;
+    const size_t table_bytes = (size_t)hi_bytes + lo_bytes + (size_t)np * (bounded ? 16 : 4);
+    bool has_lo = false;
+    if (bounded && job.lo)
+        for (int i = 0; i < n; ++i) has_lo = has_lo || job.lo[i] > 0.0;
     // S'[k][j], j <= k: Sigma_kk on the diagonal, Sigma_kj + Sigma_jk below it (w' Sigma w = sum_k sum_{j<=k} w_k S'_kj w_j)
     auto s_prime = [&](int k, int j) { return j == k ? job.sigma[(size_t)k * n + k] : job.sigma[(size_t)k * n + j] + job.sigma[(size_t)j * n + k]; };
     // FP16 split: S' is stored times 2^e with the largest entry in [2^13, 2^14) (FP16 keeps 11 significant bits down to
@@ -510,7 +631,7 @@ int pf_large_launch_tc(mcp_context* h, PfJob& job) {
     unsigned char* dev = nullptr;
     MCP_CHECK(mcp_dev_reserve(h, 6, table_bytes, (void**)&dev));
     // once per mcp_portfolios call and operand split: later chunks and the replays reuse it
-    if (job.tc_table_epoch == 0 || job.tc_table_epoch != h->const_epoch || job.tc_table_f16 != (f16 ? 1 : 0)) {
+    if (job.tc_table_epoch == 0 || job.tc_table_epoch != h->const_epoch || job.tc_table_f16 != table_kind) {
         std::vector<unsigned char> host(table_bytes, 0);
         // Canonical K-major no-swizzle layout per chunk: [K core (4 tf32 / 8 16-bit)][N group of 8][8 rows x 16 bytes].
         for (int k = 0; k < n; ++k) {
@@ -535,10 +656,23 @@ int pf_large_launch_tc(mcp_context* h, PfJob& job) {
         }
         float* hmu = reinterpret_cast<float*>(host.data() + hi_bytes + lo_bytes);
         for (int i = 0; i < n; ++i) hmu[i] = (float)job.mu[i];
+        if (bounded) {
+            // w_i <= hi_i <=> e_i / hi_i <= sum(e);  w_i >= lo_i <=> e_i / lo_i >= sum(e).  A bound that cannot bite (hi >= 1, lo <= 0)
+            // and the padded assets drop out: factor 0 for the maximum, factor 0 with a -1e30 term for the minimum.
+            float* inv_hi = hmu + np;
+            float* inv_lo = inv_hi + np;
+            float* bias_lo = inv_lo + np;
+            for (int i = 0; i < np; ++i) {
+                inv_hi[i] = 0.f; inv_lo[i] = 0.f; bias_lo[i] = -1e30f;
+                if (i >= n) continue;
+                if (job.hi && job.hi[i] < 1.0) inv_hi[i] = job.hi[i] > 1e-30 ? (float)(1.0 / job.hi[i]) : 1e30f;
+                if (job.lo && job.lo[i] > 0.0) { inv_lo[i] = (float)std::min(1.0 / job.lo[i], 1e30); bias_lo[i] = 0.f; }
+            }
+        }
         MCP_CUDA(h, cudaMemcpyAsync(dev, host.data(), table_bytes, cudaMemcpyHostToDevice, job.stream));
         MCP_CUDA(h, cudaStreamSynchronize(job.stream));        // `host` is pageable and dies at scope exit; other streams may read next
         job.tc_table_epoch = ++h->const_epoch;
-        job.tc_table_f16 = f16 ? 1 : 0;
+        job.tc_table_f16 = table_kind;
     }
 
     TcArgs a;
@@ -546,8 +680,10 @@ int pf_large_launch_tc(mcp_context* h, PfJob& job) {
     a.w_in = (const float*)job.w_in;
     a.w_out = (float*)job.w_out;
     a.inv_out = nullptr;
-    if (a.w_out)      // two sweeps can be in flight in the HOST-space pipeline (one per side stream): one scratch each
+    if (a.w_out) {    // two sweeps can be in flight in the HOST-space pipeline (one per side stream): one scratch each
         MCP_CHECK(mcp_dev_reserve(h, job.stream == h->side_stream[1] ? 13 : 12, (size_t)job.P * sizeof(float), (void**)&a.inv_out));
+        if (bounded) round->inv_out = a.inv_out;
+    }
     a.ret_out = (float*)job.ret_out; a.risk_out = (float*)job.risk_out; a.sharpe_out = (float*)job.sharpe_out;
     a.acc_out = job.acc_out; a.cands = job.cands; a.n_accepted = job.n_accepted;
     a.first = job.first; a.P = job.P; a.n = n; a.np = np;
@@ -555,8 +691,24 @@ int pf_large_launch_tc(mcp_context* h, PfJob& job) {
     philox_keys_fill(a.rk, job.seed);
     a.rf = (float)job.rf; a.target = (float)job.target;
     a.qscale = (float)qscale;
-    MCP_CHECK(f16 ? tc_launch<true>(h, job, a, table_bytes) : tc_launch<false>(h, job, a, table_bytes));
-    if (a.w_out) {
+    a.in_list = nullptr; a.in_count = nullptr; a.retry_list = nullptr; a.retry_count = nullptr;
+    a.simt_list = nullptr; a.simt_att = nullptr; a.simt_count = nullptr;
+    a.attempt = 0; a.max_tries = job.max_tries; a.keep_last = job.keep_last;
+    a.has_lo = has_lo ? 1 : 0;
+    if (bounded) {
+        a.in_list = round->in_list; a.in_count = round->in_count;
+        a.retry_list = round->retry_list; a.retry_count = round->retry_count;
+        a.simt_list = round->simt_list; a.simt_att = round->simt_att; a.simt_count = round->simt_count;
+        a.attempt = (uint32_t)round->attempt;
+        MCP_CHECK((tc_launch<true, true>(h, job, a, table_bytes)));
+    } else {
+        MCP_CHECK(f16 ? tc_launch<true>(h, job, a, table_bytes) : tc_launch<false>(h, job, a, table_bytes));
+    }
+    if (a.w_out && bounded && round->in_list) {
+        tc_scale_rows_list<<<(unsigned)h->prop.multiProcessorCount * 4, 256, 0, job.stream>>>(a.w_out, a.inv_out, round->in_list, round->in_count, job.first, n);
+        MCP_CUDA(h, cudaGetLastError());
+        h->launches++;
+    } else if (a.w_out) {
         const uint64_t total = job.P * (uint64_t)n;
         const unsigned blocks = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)h->prop.multiProcessorCount * 8);
         tc_scale_rows<<<blocks, 256, 0, job.stream>>>(a.w_out, a.inv_out, job.P, n);
@@ -564,6 +716,83 @@ int pf_large_launch_tc(mcp_context* h, PfJob& job) {
         h->launches++;
     }
     return MCP_OK;
+}
+
+int pf_large_launch_tc(mcp_context* h, PfJob& job) { return tc_launch_range(h, job, nullptr); }
+
+// Bounds rejection (app.py:700-707) with the quadratic forms on the tensor cores.  Per sub-range of the launch, in rounds: round k
+// evaluates attempt k of the rows still pending (round 0: the contiguous range, later: the previous round's retry list) on the
+// BOUNDS instance, which accepts, skips (last attempt) or queues each row for the next round -- and hands the rows it cannot
+// call (within 1e-5 of a bound) to the tiled SIMT kernel together with the attempt they are at.  Which kernel evaluates a row
+// depends on that row's draws only -- never on how the range is chunked or sharded -- so results are reproducible across chunk
+// sizes and GPU counts.  One 8-byte read-back per round (the retry count) ends the rounds when nothing is pending.
+int pf_large_launch_tc_bounded(mcp_context* h, PfJob& job) {
+    const uint64_t P = job.P, first = job.first;
+    const size_t es = 4;
+    constexpr uint64_t SUB = 1ull << 26;                  // rows per sub-range: three index lists of at most 512 MB each
+    constexpr int MAX_SUBS = 40;
+    const int side = job.stream == h->side_stream[1] ? 1 : 0;
+    const uint64_t cap = std::min<uint64_t>(P, SUB);
+    unsigned char* lbuf = nullptr;
+    MCP_CHECK(mcp_dev_reserve(h, 21 + side, 256 + cap * (3 * 8 + 2) + 64, (void**)&lbuf));
+    unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(lbuf);      // [0], [1]: ping-pong retry counts, [2]: SIMT rows
+    uint64_t* d_retry[2] = {reinterpret_cast<uint64_t*>(lbuf + 256), reinterpret_cast<uint64_t*>(lbuf + 256) + cap};
+    uint64_t* d_simt = d_retry[1] + cap;
+    uint16_t* d_simt_att = reinterpret_cast<uint16_t*>(d_simt + cap);
+    PfCand* const cands0 = job.cands;
+    const int max_blocks0 = job.max_blocks;
+    if (max_blocks0 < MAX_SUBS + h->prop.multiProcessorCount) return mcp_fail(h, MCP_ERR_INVALID, "bounded tcgen05 sweep: candidate scratch too small");
+    if ((P + SUB - 1) / SUB > (uint64_t)MAX_SUBS) return mcp_fail(h, MCP_ERR_INVALID, "bounded tcgen05 sweep: %llu rows in one launch", (unsigned long long)P);
+    void* const w0 = job.w_out; void* const r0p = job.ret_out; void* const k0p = job.risk_out; void* const s0p = job.sharpe_out;
+    uint8_t* const a0 = job.acc_out;
+    auto at = [&](void* q, uint64_t off, size_t row_bytes) -> void* { return q ? (unsigned char*)q + off * row_bytes : nullptr; };
+    job.tc_bounds_route = 1;
+    int n_sub = 0;
+    int rc = MCP_OK;
+    PfCand* const region = cands0 + MAX_SUBS;
+    for (uint64_t off = 0; off < P && rc == MCP_OK; off += SUB, ++n_sub) {
+        const uint64_t rows = std::min<uint64_t>(SUB, P - off);
+        job.first = first + off;
+        job.P = rows;
+        job.w_out = at(w0, off, (size_t)job.n * es); job.ret_out = at(r0p, off, es); job.risk_out = at(k0p, off, es); job.sharpe_out = at(s0p, off, es);
+        job.acc_out = (uint8_t*)at(a0, off, 1);
+        job.cands = region;
+        job.max_blocks = h->prop.multiProcessorCount;
+        MCP_CUDA(h, cudaMemsetAsync(d_counts, 0, 24, job.stream));
+        TcRound rd;
+        rd.simt_list = d_simt; rd.simt_att = d_simt_att; rd.simt_count = d_counts + 2;
+        unsigned long long pending = rows;
+        int folded = 0;
+        for (int attempt = 0; attempt < job.max_tries && pending > 0 && rc == MCP_OK; ++attempt) {
+            const int cur = attempt & 1, nxt = cur ^ 1;
+            rd.attempt = attempt;
+            rd.in_list = attempt == 0 ? nullptr : d_retry[cur];
+            rd.in_count = attempt == 0 ? nullptr : d_counts + cur;
+            rd.retry_list = d_retry[nxt];
+            rd.retry_count = d_counts + nxt;
+            MCP_CUDA(h, cudaMemsetAsync(d_counts + nxt, 0, 8, job.stream));
+            rc = tc_launch_range(h, job, &rd);
+            if (rc != MCP_OK) break;
+            rc = pf_reduce_launch(h, region, job.blocks_used, cands0 + n_sub, folded, job.stream);
+            folded = 1;
+            if (rc != MCP_OK) break;
+            MCP_CUDA(h, cudaMemcpyAsync(&pending, d_counts + nxt, 8, cudaMemcpyDeviceToHost, job.stream));
+            MCP_CUDA(h, cudaStreamSynchronize(job.stream));
+        }
+        if (rc != MCP_OK) break;
+        job.idx_list = d_simt;
+        job.idx_count = d_counts + 2;
+        job.idx_attempt = d_simt_att;
+        rc = pf_large_launch_list(h, job);
+        job.idx_list = nullptr; job.idx_count = nullptr; job.idx_attempt = nullptr;
+        if (rc != MCP_OK) break;
+        rc = pf_reduce_launch(h, region, job.blocks_used, cands0 + n_sub, folded, job.stream);
+    }
+    job.first = first; job.P = P;
+    job.w_out = w0; job.ret_out = r0p; job.risk_out = k0p; job.sharpe_out = s0p; job.acc_out = a0;
+    job.cands = cands0; job.max_blocks = max_blocks0;
+    job.blocks_used = n_sub;
+    return rc;
 }
 
 }  // namespace mcp

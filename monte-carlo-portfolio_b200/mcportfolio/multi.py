@@ -75,6 +75,13 @@ def device_group(devices) -> DeviceGroup:
         return g
 
 
+def close_all():
+    """Dissolve every device group of this process (their engines leave the groups' communicators)."""
+    with _groups_lock:
+        for k in list(_groups):
+            _groups.pop(k).close()
+
+
 def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, devices, weights=None, return_arrays=True, first_index=0,
                         dtype="float32", **kw):
     """`api.simulate_portfolios` over several GPUs of this process; same result object.  Arrays (host only) are one

@@ -35,9 +35,13 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     have_ref = os.path.isfile("/root/reference/app.py")
     skip_ref = pytest.mark.skip(reason="/root/reference not present on this box")
+    have_timeout = config.pluginmanager.hasplugin("timeout")
     for item in items:
         if "needs_reference" in item.keywords and not have_ref:
             item.add_marker(skip_ref)
+        if have_timeout and "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+            # a collective that one rank never joins blocks inside a C call: kill the run instead of hanging the GPU box
+            item.add_marker(pytest.mark.timeout(420, method="thread"))
 
 
 def load_golden(name):

@@ -253,7 +253,7 @@ def test_pinned_pool_recycles_blocks(mcp):
     gc.collect()
     b = mcp.pinned_empty((1 << 20,), np.float32)
     assert b.ctypes.data == addr                    # same block, no new cudaHostAlloc
-    assert not api._pinned_pool.free.get(4 << 20)   # ... and it left the idle list of its size class
+    assert addr not in api._pinned_pool.free.get(4 << 20, [])   # ... and it left the idle list of its size class
     del b
 
 
@@ -314,6 +314,8 @@ def test_recheck_overflow_falls_back_to_a_full_fp64_pass(mcp):
 # ---- the in-library communicator (one rank here; 2 ranks: test_multi_gpu.py / bench) ----------------------------------
 
 def test_comm_world_of_one_merges_to_the_same_results(mcp):
+    from mcportfolio import multi
+    multi.close_all()                                # a devices=[...] call of an earlier test left engine 0 in a wider communicator
     eng = mcp.Engine(0)                              # a private handle: the shared engine's state stays untouched
     try:
         eng.comm_init(mcp.comm_unique_id(), 0, 1)
@@ -349,3 +351,71 @@ def test_comm_world_of_one_merges_to_the_same_results(mcp):
     with pytest.raises(mcp.McpError, match="communicator"):
         mcp.simulate_portfolios(mu, sigma, 10, comm_merge=True)
     del api
+
+
+# ---- bounds rejection with the quadratic forms on the tensor cores (32 < N <= 256) ------------------------------------------
+
+@pytest.mark.parametrize("n,lo,hi,tries", [(64, None, 0.07, 3), (64, 1e-4, None, 5), (256, None, 0.022, 4), (100, 2e-5, 0.06, 100),
+                                           (64, None, 0.045, 2)])
+def test_bounded_sweep_on_tensor_cores_equals_the_simt_sweep(mcp, n, lo, hi, tries):
+    """app.py:700-707 at N > 32: the tcgen05 kernel accepts what is safely inside the bounds at attempt 0 and hands the rest to
+    the tiled SIMT kernel.  Accept / skip decisions, attempts and therefore the weights are the SIMT-only sweep's; the metrics
+    carry the tensor-core kernel's FP16-split arithmetic (1e-4 against FP64).  Rejected rows are redrawn in further tensor-core
+    rounds (attempt + 1); the last case rejects almost everything, so most rows end skipped after two attempts."""
+    mu, sigma = synthetic_inputs(n)
+    P, seed = 70_001, 11
+    kw = dict(min_weights=None if lo is None else np.full(n, lo), max_weights=None if hi is None else np.full(n, hi), seed=seed,
+              max_tries=tries, risk_free=0.03)
+    a = mcp.simulate_portfolios(mu, sigma, P, **kw)
+    with _env(MCP_LARGE_TC_BOUNDS="0"):
+        b = mcp.simulate_portfolios(mu, sigma, P, **kw)
+    assert 0 < b.n_accepted < P and a.n_accepted == b.n_accepted
+    assert np.array_equal(a.accepted, b.accepted)
+    assert np.allclose(a.weights, b.weights, rtol=0, atol=3e-7)
+    want = ref.evaluate(np.asarray(a.weights, dtype=np.float64), mu, sigma, 0.03, 0.30)
+    assert np.allclose(a.risks, want["risks"], rtol=1e-4) and np.allclose(a.returns, want["returns"], rtol=1e-4)
+    assert np.allclose(a.sharpes, want["sharpes"], rtol=1e-4, atol=1e-4)
+    if lo is not None:
+        assert a.weights.min() >= np.float32(lo) * (1 - 1e-6)
+    if hi is not None:
+        assert a.weights.max() <= np.float32(hi) * (1 + 1e-6)
+    assert a.max_sharpe["index"] == int(np.argmax(a.sharpes)) and a.target_risk["index"] == int(np.argmin(np.abs(a.risks - np.float32(0.30))))
+    # value by value against the generator restatement with the reference's rejection loop (a sample)
+    W, valid = philox_np.dirichlet_weights(0, 3000, n, seed, "float32", kw["min_weights"], kw["max_weights"], max_tries=tries)
+    acc = a.accepted[:3000].astype(bool)
+    edge = np.full(3000, np.inf)
+    if hi is not None:
+        edge = np.minimum(edge, np.abs(W - hi).min(1))
+    if lo is not None:
+        edge = np.minimum(edge, np.abs(W - lo).min(1))
+    differ = acc != valid
+    assert differ.sum() <= 3 and np.all(edge[differ] < 1e-6)
+    both = acc & valid
+    assert np.allclose(a.weights[np.cumsum(acc)[both] - 1], W[both], atol=1e-6)
+    # selections only (no arrays), and device-resident arrays, take the same route
+    s = mcp.simulate_portfolios(mu, sigma, P, return_arrays=False, **kw)
+    assert s.n_accepted == a.n_accepted and s.max_sharpe["global_index"] == a.max_sharpe["global_index"]
+    assert s.target_risk["global_index"] == a.target_risk["global_index"]
+    d = mcp.simulate_portfolios(mu, sigma, P, return_arrays="device", **kw)
+    assert d.n_accepted == a.n_accepted and np.array_equal(d.sharpes.cpu().numpy(), a.sharpes)
+
+
+def test_bounded_tensor_core_sweep_sharding_and_host_pipeline(mcp):
+    """The bounded route inside the HOST-space chunk pipeline (two streams, several chunks) and across index shards."""
+    n = 64
+    mu, sigma = synthetic_inputs(n)
+    hi = np.full(n, 0.08)
+    P = 700_001                                           # 183 MB of weights: several pipeline chunks
+    whole = mcp.simulate_portfolios(mu, sigma, P, max_weights=hi, seed=2, max_tries=4, risk_free=0.03)
+    assert 0 < whole.n_accepted < P
+    sel = mcp.simulate_portfolios(mu, sigma, P, max_weights=hi, seed=2, max_tries=4, risk_free=0.03, return_arrays=False)
+    assert sel.n_accepted == whole.n_accepted and sel.max_sharpe["global_index"] == whole.max_sharpe["global_index"]
+    cuts = [0, 40_000, 300_001, P]
+    parts = [mcp.simulate_portfolios(mu, sigma, b - a, max_weights=hi, seed=2, max_tries=4, risk_free=0.03, first_index=a, return_arrays=False)
+             for a, b in zip(cuts[:-1], cuts[1:])]
+    assert sum(p.n_accepted for p in parts) == whole.n_accepted
+    best = max(parts, key=lambda r: (r.max_sharpe["key"], -r.max_sharpe["global_index"]))
+    assert best.max_sharpe["global_index"] == whole.max_sharpe["global_index"]
+    with _env(MCP_LARGE_TC_BOUNDS="0"):
+        simt = mcp.simulate_portfolios(mu, sigma, P, max_weights=hi, seed=2, max_tries=4, risk_free=0.03, return_arrays=False)
+    assert simt.n_accepted == whole.n_accepted
