@@ -60,7 +60,8 @@ struct PfJob {
     const unsigned long long* idx_count = nullptr;
     const uint16_t* idx_attempt = nullptr;   // optional, per listed row: the attempt number of its first draw in this launch
     bool lgl_uploaded = false;         // the list-mode / bounded-route copy of the tiled kernel's constants (slot 20) is in place
-    int tc_bounds_route = 0;           // != 0: this call's bounded sweep runs on the tcgen05 kernel with the tiled SIMT kernel beside it
+    int tc_bounds_route = 0;           // bounded sweep at 32 < N <= 256: 1 once the tcgen05 route ran (the tiled SIMT kernel then keeps its
+                                       // constants beside that kernel's table), 2 = the SIMT kernel only (replays)
 };
 
 // Replay of selected portfolios: regenerates (RNG mode) or re-reads (supplied mode, `rows`

@@ -642,6 +642,7 @@ int pf_large_replay(mcp_context* h, const PfJob& job, const PfReplay& rp) {
         j.cands = (PfCand*)(scratch + 2 * per);
         j.n_accepted = (unsigned long long*)(scratch + 2 * per + 4 * sizeof(PfCand));
         j.max_blocks = 1;
+        if (j.bounds) j.tc_bounds_route = 2;      // one row: the tiled SIMT kernel replays the rejection loop (its decisions are the sweep's)
         if (rp.idx[k] == MCP_NO_INDEX) {
             std::vector<double> nanrec(PF_REC_HEADER + n, NAN);
             uint64_t none = MCP_NO_INDEX;

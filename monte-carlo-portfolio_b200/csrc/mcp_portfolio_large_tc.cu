@@ -60,7 +60,7 @@ constexpr int TC_KC = 32;                    // K (assets) per chunk
 constexpr int TC_MAX_N = 256;
 constexpr uint32_t TC_COL_A = 256;           // first TMEM column of the A stages (accumulator = columns 0..255)
 constexpr int TC_MAX_GROUPS = 4;
-constexpr uint64_t TC_BOUNDED_MIN_P = 1ull << 15, TC_BOUNDED_MAX_P = 1ull << 31;     // per launch; the deferred-row list is 8 B per row of a sub-range
+constexpr uint64_t TC_BOUNDED_MAX_P = 1ull << 31;     // rows per launch of the bounded route (the index lists are 8 B per row of a 2^26-row sub-range)
 // Two operand splits share the kernel (template parameter F16):
 //   TF32 split (any FP32 input, so supplied weights use it): stage = hi 32 + lo 32 + bf16 16 = 80 columns, 3 stages / generator groups
 //   FP16 split (Philox rows: |lg2 U| <= 24 fits FP16):        stage = h1 16 + h2 16 + l 32 = 64 columns, 4 stages / generator groups
@@ -557,10 +557,12 @@ bool pf_large_tc_eligible(const PfJob& job) {
     if (v && v[0] == '0') return false;
     if (!(job.dtype == MCP_F32 && job.n > PF_SMALL_MAX_N && job.n <= TC_MAX_N)) return false;
     if (!job.bounds) return true;
-    // bounds: Philox rows only, and only launches big enough to be worth two kernels (a replay is one portfolio: SIMT)
+    // bounds: Philox rows only.  The choice must not depend on the size of the launch: a call is cut into chunks and shards, and
+    // which kernel evaluates a row has to be a property of the row (the two kernels agree to ~1e-7, not to the bit).  Replays of the
+    // selected rows ask for the SIMT kernel explicitly (tc_bounds_route == 2).
     const char* b = getenv("MCP_LARGE_TC_BOUNDS");        // "0": bounded sweeps stay on the SIMT kernel (A/B tests)
     if (b && b[0] == '0') return false;
-    return job.w_in == nullptr && job.idx_list == nullptr && job.P >= TC_BOUNDED_MIN_P && job.P <= TC_BOUNDED_MAX_P;
+    return job.w_in == nullptr && job.idx_list == nullptr && job.tc_bounds_route != 2 && job.P <= TC_BOUNDED_MAX_P;
 }
 
 // FP16 split: Philox rows only (|lg2 U| <= 24 is inside FP16's range; supplied weights may be any FP32 value), MCP_LARGE_TC_F16=0 disables

@@ -369,7 +369,7 @@ def test_bounded_sweep_on_tensor_cores_equals_the_simt_sweep(mcp, n, lo, hi, tri
     a = mcp.simulate_portfolios(mu, sigma, P, **kw)
     with _env(MCP_LARGE_TC_BOUNDS="0"):
         b = mcp.simulate_portfolios(mu, sigma, P, **kw)
-    assert 0 < b.n_accepted < P and a.n_accepted == b.n_accepted
+    assert 0 < b.n_accepted and (b.n_accepted < P or tries == 100) and a.n_accepted == b.n_accepted     # 100 tries: everything lands
     assert np.array_equal(a.accepted, b.accepted)
     assert np.allclose(a.weights, b.weights, rtol=0, atol=3e-7)
     want = ref.evaluate(np.asarray(a.weights, dtype=np.float64), mu, sigma, 0.03, 0.30)

@@ -1,6 +1,6 @@
 """ncu target (one GPU): the four headline kernels at the launch sizes bench.py uses, two launches each.
 
-    PROFILE_ONLY=sweep|paths|tc|hist  restricts the run to one kernel family (default: all four).
+    PROFILE_ONLY=sweep|paths|tc|tcb|hist  restricts the run to one kernel family (default: all five).
 """
 import os
 import sys
@@ -31,6 +31,12 @@ if only in ("", "tc"):
     for _ in range(2):
         r256 = mcp.simulate_portfolios(mu256, sigma256, P256, risk_free=0.03, seed=0, return_arrays=False)
     print(f"sweep N=256 P={P256:.0e}: {P256 / r256.kernel_ms * 1e3:.4g} pf/s kernel_ms={r256.kernel_ms:.3f}")
+if only in ("", "tcb"):
+    mu256, sigma256 = synthetic_inputs(256)
+    Pb = int(float(os.environ.get("PROFILE_P256B", 2e7)))
+    for _ in range(2):
+        rb = mcp.simulate_portfolios(mu256, sigma256, Pb, risk_free=0.03, seed=0, return_arrays=False, max_weights=np.full(256, 0.03))
+    print(f"bounded sweep N=256 hi=0.03 P={Pb:.0e}: {Pb / rb.kernel_ms * 1e3:.4g} pf/s kernel_ms={rb.kernel_ms:.3f} accepted={rb.n_accepted}")
 if only in ("", "hist"):
     rng = np.random.default_rng(0)
     T, n, Ph = 365, 16, 1_000_000
