@@ -109,12 +109,13 @@ def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, devices, weig
                                        out=out, comm_merge=True, **kw)
 
     parts = grp.run(work)
+    accepted_per_part = [p.n_accepted for p in parts]      # before parts[0] becomes the merged result
     r = parts[0]
     r.n_requested = P
-    r.n_accepted = sum(p.n_accepted for p in parts)
-    r.kernel_ms = max(p.kernel_ms for p in parts)
-    r.extra["devices"] = list(grp.devices)
+    r.n_accepted = sum(accepted_per_part)
     r.extra["kernel_ms_per_device"] = [p.kernel_ms for p in parts]
+    r.kernel_ms = max(r.extra["kernel_ms_per_device"])
+    r.extra["devices"] = list(grp.devices)
     if full is not None:
         skipped = r.n_accepted < P
         if skipped:      # app.py:706-707: the reference's arrays simply do not contain skipped portfolios
@@ -124,7 +125,7 @@ def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, devices, weig
         else:
             r.weights, r.returns, r.risks, r.sharpes, r.accepted = (full[k] for k in ("weights", "returns", "risks", "sharpes", "accepted"))
         # `index` = position in the returned arrays (app.py:747): the owning device knows the local position
-        offsets = np.concatenate([[0], np.cumsum([p.n_accepted for p in parts])])
+        offsets = np.concatenate([[0], np.cumsum(accepted_per_part)])
         for pick in ("max_sharpe", "target_risk"):
             rec = getattr(r, pick)
             if rec is None:
