@@ -325,6 +325,20 @@ int mcp_comm_nccl_version(int* version);
 int mcp_comm_allgather(mcp_handle h, const void* send_host, size_t bytes, void* recv_host);
 int mcp_comm_allreduce(mcp_handle h, void* inout_host, size_t count, int kind);
 
+/* ---- one call, n GPUs of this process (the reference is ONE Streamlit process, Procfile:1) -------------------------------------
+ * `handles`: n handles, one per GPU, joined by mcp_comm_init_all (handle r = rank r).  The job described by `params` -- the global
+ * index range [first_index, first_index + n_portfolios) or n_paths -- is cut into n contiguous blocks (block r holds
+ * total / n + (r < total % n) units) and every handle runs the ordinary entry point on its block from its own host thread inside
+ * the library, with comm_merge set: `out` / `stats` receive the whole job's results, identical to a one-GPU run of the same job.
+ * mcp_portfolios_multi: arrays (weights_in, weights_recheck, every array of `out`) must be HOST space and describe the WHOLE job;
+ * each device reads / fills its slice.  out->n_accepted is the whole job's count, out->kernel_ms the slowest device's;
+ * kernel_ms_per_device (n doubles) may be NULL.  mcp_paths_stats_multi: Philox paths only, terminal values stay on the devices.
+ * On failure the message of the failing device is available through mcp_last_error(handles[0]).                                 */
+int mcp_portfolios_multi(mcp_handle* handles, int n, const mcp_portfolio_params* params,
+                         const double* mu_host, const double* sigma_host, mcp_portfolio_out* out, double* kernel_ms_per_device);
+int mcp_paths_stats_multi(mcp_handle* handles, int n, const mcp_path_params* params,
+                          const double* mu_host, const double* sigma_host, const double* weights_host, mcp_path_stats* stats);
+
 /* ---- microbenchmarks used as roofline denominators (bench.py) ------------------------- */
 int mcp_measure_fma_peak(mcp_handle h, int dtype /* MCP_F32 | MCP_F64 | 2 = packed FP32x2 (FFMA2) */, double* tflops);
 

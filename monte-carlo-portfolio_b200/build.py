@@ -33,6 +33,7 @@ def translation_units():
     """(object name, source, extra defines)"""
     tus = [("mcp_context", "mcp_context.cu", []),
            ("mcp_comm", "mcp_comm.cu", []),
+           ("mcp_multi", "mcp_multi.cu", []),
            ("mcp_portfolio", "mcp_portfolio.cu", []),
            ("mcp_portfolio_large", "mcp_portfolio_large.cu", []),
            ("mcp_portfolio_large_tc", "mcp_portfolio_large_tc.cu", []),
@@ -94,7 +95,7 @@ def _build_locked(force: bool, verbose: bool) -> str:
     tus = translation_units()
     with cf.ThreadPoolExecutor(max_workers=min(len(tus), os.cpu_count() or 4)) as ex:
         objs = list(ex.map(lambda t: _compile(t, verbose), tus))
-    cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-ldl", "-Xlinker", "--no-undefined"]
+    cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-ldl", "-lpthread", "-Xlinker", "--no-undefined"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

@@ -102,6 +102,7 @@ int mcp_destroy(mcp_handle h) {
     if (!h) return MCP_OK;
     mcp_device_guard guard(h->device);
     cudaDeviceSynchronize();
+    mcp_worker_release(h);
     mcp_comm_release(h);
     for (auto& s : h->dev) if (s.p) cudaFree(s.p);
     for (auto& s : h->pinned) if (s.p) cudaFreeHost(s.p);

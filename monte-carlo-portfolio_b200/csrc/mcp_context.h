@@ -45,6 +45,8 @@ struct mcp_context {
     // multi-GPU (mcp_comm.cu): NCCL communicator of this handle, null until mcp_comm_init
     struct mcp_comm_state* comm = nullptr;
     int comm_rank = 0, comm_size = 0;
+    // host thread of this handle in the one-call multi-GPU entry points (mcp_multi.cu), null until first used
+    struct mcp_worker* worker = nullptr;
 };
 
 // reduction kinds of mcp_comm_allreduce(_dev) -- values are part of the C ABI (include/mcp.h MCP_REDUCE_*)
@@ -52,6 +54,7 @@ int mcp_comm_allgather_dev(mcp_context* h, const void* send_dev, void* recv_dev,
 int mcp_comm_allreduce_dev(mcp_context* h, void* buf_dev, size_t count, int kind, cudaStream_t st);
 int mcp_comm_check(mcp_context* h);
 void mcp_comm_release(mcp_context* h);
+void mcp_worker_release(mcp_context* h);
 
 // select + tail passes on device-resident values (mcp_quantile.cu); hist0_dev: optional pre-filled histogram of the first radix
 // digit (2048 uint64 counts of this shard, FP32 keys only)

@@ -137,6 +137,10 @@ SYMBOLS = {
     "mcp_comm_nccl_version": (C.c_int, [C.POINTER(C.c_int)]),
     "mcp_comm_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mcp_comm_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "mcp_portfolios_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(PortfolioParams), C.c_void_p, C.c_void_p,
+                                       C.POINTER(PortfolioOut), C.c_void_p]),
+    "mcp_paths_stats_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(PathParams), C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.POINTER(PathStats)]),
 }
 
 _lib = None

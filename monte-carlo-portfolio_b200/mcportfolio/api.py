@@ -299,7 +299,7 @@ def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, risk_free=0.0
                         min_weights=None, max_weights=None, weights=None, seed=0, dtype="float32",
                         return_arrays=True, first_index=0, keep_last=False, max_tries=100,
                         device=None, out=None, n_bins=0, risk_range=None, devices=None, comm_merge=False,
-                        philox_rounds=10) -> PortfolioResult:
+                        philox_rounds=10, _group=None) -> PortfolioResult:
     """Random-weight portfolio sweep: the loop of app.py:699-722 in one call.
 
     weights=None      flat-Dirichlet weights generated in-kernel (Philox4x32-10, counter =
@@ -337,7 +337,7 @@ def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, risk_free=0.0
                                          risk_target=risk_target, min_weights=min_weights, max_weights=max_weights,
                                          weights=weights, seed=seed, dtype=dtype, return_arrays=return_arrays,
                                          first_index=first_index, keep_last=keep_last, max_tries=max_tries, n_bins=n_bins,
-                                         risk_range=risk_range, philox_rounds=philox_rounds)
+                                         risk_range=risk_range, philox_rounds=philox_rounds, out=out)
     if devices is not None and len(devices) == 1:
         device = devices[0]
     mu, sigma, n = _mu_sigma(mean_returns, cov_matrix)
@@ -354,7 +354,9 @@ def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, risk_free=0.0
             raise ValueError(f"weights must have shape (P, {n}), got {wshape}")
         if wshape[0] != P:
             raise ValueError(f"weights has {wshape[0]} rows but n_portfolios={P}")
-    eng = get_engine(device)
+    eng = get_engine(device) if _group is None else _group.engines[0]
+    if _group is not None and (_is_device_tensor(weights) or return_arrays not in (True, False) or comm_merge):
+        raise ValueError("devices=[...] takes host weights and returns host arrays or picks only (return_arrays True / False)")
     if weights is not None and not _is_device_tensor(weights) and return_arrays in ("device", "device-metrics"):
         # host weights with device-resident results: the call runs in DEVICE space, so the rows go up first
         import torch
@@ -433,7 +435,17 @@ def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, risk_free=0.0
     if params.space == MCP_DEVICE:
         import torch
         eng.set_stream(torch.cuda.current_stream(eng.device).cuda_stream)
-    check(eng.handle, lib().mcp_portfolios(eng.handle, C.byref(params), mu.ctypes.data, sigma.ctypes.data, C.byref(res)))
+    per_device_ms = None
+    if _group is not None:
+        # ONE library call drives every GPU of the group: libmcp cuts the index range, runs a host thread per handle and merges
+        # the results over its communicator (mcp_multi.cu); arrays are the whole job's, each device fills its slice
+        for e in _group.engines:
+            e.set_stream(None)
+        per_device_ms = np.zeros(_group.world)
+        check(eng.handle, lib().mcp_portfolios_multi(_group.handles, _group.world, C.byref(params), mu.ctypes.data, sigma.ctypes.data,
+                                                     C.byref(res), per_device_ms.ctypes.data))
+    else:
+        check(eng.handle, lib().mcp_portfolios(eng.handle, C.byref(params), mu.ctypes.data, sigma.ctypes.data, C.byref(res)))
     if comm_merge:
         extra_merge = {"n_accepted_global": int(res.n_accepted_global)}
     else:
@@ -459,6 +471,10 @@ def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, risk_free=0.0
     elif return_arrays:
         positions = _Identity()
     extra = dict(extra_merge)
+    if _group is not None:
+        extra["devices"] = list(_group.devices)
+        extra["kernel_ms_per_device"] = per_device_ms.tolist()
+        extra["n_accepted_global"] = int(res.n_accepted_global)
     if n_bins:
         idx = bin_idx.astype(np.int64)
         idx[bin_idx == np.uint64(MCP_NO_INDEX)] = -1
@@ -582,7 +598,7 @@ def envelope_from_arrays(risks, returns, n_bins, risk_range, *, first_index=0, d
 def simulate_paths(mean_returns, cov_matrix, weights, n_paths, n_steps=252, *, dt=1.0 / 252,
                    alphas=(0.95, 0.99), normals=None, seed=0, dtype="float32", first_index=0,
                    return_terminal=None, device=None, allreduce=None, n_total=None, devices=None, comm_merge=False,
-                   philox_rounds=10):
+                   philox_rounds=10, _group=None):
     """Correlated-return paths (Cholesky of Sigma, per-asset cumulative product) -> VaR / CVaR.
 
     Not in the reference: r = mu dt + sqrt(dt) L z, V *= 1 + r (the
@@ -613,7 +629,11 @@ def simulate_paths(mean_returns, cov_matrix, weights, n_paths, n_steps=252, *, d
     alphas = tuple(float(a) for a in alphas)
     if not (1 <= len(alphas) <= _lib.MCP_MAX_ALPHAS):
         raise ValueError(f"between 1 and {_lib.MCP_MAX_ALPHAS} alphas are supported")
-    eng = get_engine(device)
+    eng = get_engine(device) if _group is None else _group.engines[0]
+    if _group is not None:
+        if normals is not None or allreduce is not None or comm_merge:
+            raise ValueError("devices=[...] simulates Philox paths (no supplied normals, no caller-side merge)")
+        return_terminal = False                  # terminal values stay on the devices
     if return_terminal is None:
         return_terminal = M <= (1 << 22)
     z_dev = terminal = None
@@ -654,8 +674,14 @@ def simulate_paths(mean_returns, cov_matrix, weights, n_paths, n_steps=252, *, d
         st.n_total = int(n_total) if n_total is not None else M
         for i, a in enumerate(alphas):
             st.alphas[i] = a
-        check(eng.handle, lib().mcp_paths_stats(eng.handle, C.byref(p), mu.ctypes.data, sigma.ctypes.data, w.ctypes.data,
-                                                terminal.data_ptr() if terminal is not None else None, C.byref(st)))
+        if _group is not None:
+            for e in _group.engines:
+                e.set_stream(None)
+            check(eng.handle, lib().mcp_paths_stats_multi(_group.handles, _group.world, C.byref(p), mu.ctypes.data, sigma.ctypes.data,
+                                                          w.ctypes.data, C.byref(st)))
+        else:
+            check(eng.handle, lib().mcp_paths_stats(eng.handle, C.byref(p), mu.ctypes.data, sigma.ctypes.data, w.ctypes.data,
+                                                    terminal.data_ptr() if terminal is not None else None, C.byref(st)))
         stats = {a: (float(st.var[i]), float(st.cvar[i])) for i, a in enumerate(alphas)}
         kernel_ms, quantile_ms = st.kernel_ms, st.quantile_ms
     return {"stats": stats, "terminal": terminal.cpu().numpy() if (return_terminal and terminal is not None) else None,

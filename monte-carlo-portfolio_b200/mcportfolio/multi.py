@@ -33,8 +33,8 @@ class DeviceGroup:
         for e in self.engines:
             if e.comm_info()[1]:
                 e.comm_destroy()                       # the engine leaves whatever communicator it was in
-        handles = (C.c_void_p * len(self.engines))(*[e.handle for e in self.engines])
-        check(self.engines[0].handle, lib().mcp_comm_init_all(handles, len(self.engines)))
+        self.handles = (C.c_void_p * len(self.engines))(*[e.handle for e in self.engines])        # rank r = devices[r]
+        check(self.engines[0].handle, lib().mcp_comm_init_all(self.handles, len(self.engines)))
         self.pool = cf.ThreadPoolExecutor(max_workers=len(self.engines), thread_name_prefix="mcp-gpu")
         self.lock = threading.Lock()                   # one job at a time: handles are not re-entrant
 
@@ -82,79 +82,21 @@ def close_all():
             _groups.pop(k).close()
 
 
-def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, devices, weights=None, return_arrays=True, first_index=0,
-                        dtype="float32", **kw):
-    """`api.simulate_portfolios` over several GPUs of this process; same result object.  Arrays (host only) are one
-    allocation that every device fills its slice of."""
-    if return_arrays not in (True, False):
-        raise ValueError("devices=[...] returns host arrays or picks only (return_arrays True / False)")
+def simulate_portfolios(mean_returns, cov_matrix, n_portfolios, *, devices, **kw):
+    """`api.simulate_portfolios` over several GPUs of this process; same result object.  ONE library call
+    (`mcp_portfolios_multi`): libmcp cuts the index range, drives every handle from its own host thread and merges picks, counts,
+    risk range and envelope bins over its communicator.  Arrays (host only) are one allocation; every device fills its slice."""
     grp = device_group(devices)
-    P, first_index = int(n_portfolios), int(first_index)
-    n = len(np.asarray(mean_returns))
-    _, npdt = api._dtype(dtype)
-    if weights is not None:
-        weights = np.asarray(weights)
-        if weights.ndim != 2 or weights.shape != (P, n):
-            raise ValueError(f"weights must have shape ({P}, {n}), got {weights.shape}")
-    full = None
-    if return_arrays:
-        full = {"weights": api._result_empty((P, n), npdt), "returns": api._result_empty((P,), npdt), "risks": api._result_empty((P,), npdt),
-                "sharpes": api._result_empty((P,), npdt), "accepted": api._result_empty((P,), np.uint8)}
-
-    def work(rank, eng):
-        lo, cnt = shard_range(P, rank, grp.world)
-        out = None if full is None else {k: v[lo:lo + cnt] for k, v in full.items()}
-        return api.simulate_portfolios(mean_returns, cov_matrix, cnt, weights=None if weights is None else weights[lo:lo + cnt],
-                                       return_arrays=return_arrays, first_index=first_index + lo, dtype=dtype, device=eng.device,
-                                       out=out, comm_merge=True, **kw)
-
-    parts = grp.run(work)
-    accepted_per_part = [p.n_accepted for p in parts]      # before parts[0] becomes the merged result
-    r = parts[0]
-    r.n_requested = P
-    r.n_accepted = sum(accepted_per_part)
-    r.extra["kernel_ms_per_device"] = [p.kernel_ms for p in parts]
-    r.kernel_ms = max(r.extra["kernel_ms_per_device"])
-    r.extra["devices"] = list(grp.devices)
-    if full is not None:
-        skipped = r.n_accepted < P
-        if skipped:      # app.py:706-707: the reference's arrays simply do not contain skipped portfolios
-            for name in ("weights", "returns", "risks", "sharpes"):
-                setattr(r, name, np.concatenate([getattr(p, name) for p in parts]))
-            r.accepted = full["accepted"]
-        else:
-            r.weights, r.returns, r.risks, r.sharpes, r.accepted = (full[k] for k in ("weights", "returns", "risks", "sharpes", "accepted"))
-        # `index` = position in the returned arrays (app.py:747): the owning device knows the local position
-        offsets = np.concatenate([[0], np.cumsum(accepted_per_part)])
-        for pick in ("max_sharpe", "target_risk"):
-            rec = getattr(r, pick)
-            if rec is None:
-                continue
-            g = rec["global_index"] - first_index
-            for rank, p in enumerate(parts):
-                lo, cnt = shard_range(P, rank, grp.world)
-                if lo <= g < lo + cnt:
-                    rec = dict(rec, index=int(offsets[rank]) + int(getattr(p, pick)["index"]))
-            setattr(r, pick, rec)
-    return r
+    with grp.lock:
+        return api.simulate_portfolios(mean_returns, cov_matrix, n_portfolios, _group=grp, **kw)
 
 
-def simulate_paths(mean_returns, cov_matrix, weights, n_paths, n_steps=252, *, devices, first_index=0, **kw):
-    """`api.simulate_paths` over several GPUs of this process: paths sharded by index, exact VaR / CVaR of the whole job
-    (radix-select histograms and tail sums all-reduced inside libmcp)."""
+def simulate_paths(mean_returns, cov_matrix, weights, n_paths, n_steps=252, *, devices, **kw):
+    """`api.simulate_paths` over several GPUs of this process (`mcp_paths_stats_multi`): paths sharded by index, exact VaR / CVaR of
+    the whole job (radix-select histograms and tail sums all-reduced inside libmcp)."""
     grp = device_group(devices)
-    M, first_index = int(n_paths), int(first_index)
-
-    def work(rank, eng):
-        lo, cnt = shard_range(M, rank, grp.world)
-        return api.simulate_paths(mean_returns, cov_matrix, weights, cnt, n_steps, first_index=first_index + lo, device=eng.device,
-                                  comm_merge=True, n_total=M, return_terminal=False, **kw)
-
-    parts = grp.run(work)
-    assert all(p["stats"] == parts[0]["stats"] for p in parts), "devices disagree on the merged quantiles"
-    out = dict(parts[0])
-    out["kernel_ms"] = max(p["kernel_ms"] for p in parts)
-    out["quantile_ms"] = max(p["quantile_ms"] for p in parts)
+    with grp.lock:
+        out = api.simulate_paths(mean_returns, cov_matrix, weights, n_paths, n_steps, _group=grp, **kw)
     out["devices"] = list(grp.devices)
     return out
 

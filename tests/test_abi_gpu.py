@@ -154,3 +154,84 @@ def test_empty_range_and_quantile_edge_cases_through_the_raw_abi(abi):
     assert L.mcp_abi_version() >= 1
     info = _lib.DeviceInfo()
     assert L.mcp_device_info(h, C.byref(info)) == 0 and info.cc_major == 10 and info.sm_count > 0
+
+
+def _multi_job(L, _lib, handles, n_dev, mu, sigma, P, want_arrays):
+    n = len(mu)
+    arr = (C.c_void_p * n_dev)(*handles)
+    p = make_params(_lib, n, P, seed=5)
+    out = _lib.PortfolioOut()
+    ws, wt = np.empty(n), np.empty(n)
+    out.max_sharpe.weights, out.target_risk.weights = ptr(ws), ptr(wt)
+    bufs = {}
+    if want_arrays:
+        bufs = {"weights": np.empty((P, n), np.float32), "returns": np.empty(P, np.float32), "risks": np.empty(P, np.float32),
+                "sharpes": np.empty(P, np.float32), "accepted": np.zeros(P, np.uint8)}
+        for k, v in bufs.items():
+            setattr(out, k, ptr(v))
+    ms = np.zeros(n_dev)
+    rc = L.mcp_portfolios_multi(arr, n_dev, C.byref(p), ptr(mu), ptr(sigma), C.byref(out), ptr(ms))
+    assert rc == 0, last_error(L, handles[0])
+    return out, ws, wt, bufs, ms
+
+
+def test_multi_entry_points_with_one_handle_equal_the_plain_calls(abi):
+    """mcp_portfolios_multi / mcp_paths_stats_multi with n = 1 (what a one-GPU box can run): same results as the plain entry points."""
+    L, h, _lib = abi
+    n = 16
+    mu, sigma = synthetic_inputs(n, seed=0)
+    P = 200_001
+    out, ws, wt, bufs, ms = _multi_job(L, _lib, [h], 1, mu, sigma, P, True)
+    p = make_params(_lib, n, P, seed=5)
+    ref_out = _lib.PortfolioOut()
+    assert L.mcp_portfolios(h, C.byref(p), ptr(mu), ptr(sigma), C.byref(ref_out)) == 0
+    assert out.max_sharpe.index == ref_out.max_sharpe.index and out.target_risk.index == ref_out.target_risk.index
+    assert out.n_accepted == P and bufs["accepted"].all() and ms[0] > 0
+    assert int(np.argmax(bufs["sharpes"])) == out.max_sharpe.index and np.allclose(bufs["weights"].sum(1), 1, atol=1e-5)
+    pp = _lib.PathParams()
+    pp.n_assets, pp.dtype, pp.n_paths, pp.first_index, pp.seed, pp.n_steps, pp.space, pp.dt = n, _lib.MCP_F32, 50_001, 0, 3, 20, _lib.MCP_DEVICE, 1 / 252
+    w = np.full(n, 1 / n)
+    st1, st2 = _lib.PathStats(), _lib.PathStats()
+    for st in (st1, st2):
+        st.n_alphas = 2
+        st.alphas[0], st.alphas[1] = 0.95, 0.99
+    arr = (C.c_void_p * 1)(h)
+    assert L.mcp_paths_stats_multi(arr, 1, C.byref(pp), ptr(mu), ptr(sigma), ptr(w), C.byref(st1)) == 0, last_error(L, h)
+    assert L.mcp_paths_stats(h, C.byref(pp), ptr(mu), ptr(sigma), ptr(w), None, C.byref(st2)) == 0
+    assert list(st1.var)[:2] == list(st2.var)[:2] and list(st1.cvar)[:2] == list(st2.cvar)[:2]
+    # error behaviour: NULL group, a group without a communicator
+    assert L.mcp_portfolios_multi(None, 1, C.byref(p), ptr(mu), ptr(sigma), C.byref(ref_out), None) == _lib.MCP_ERR_INVALID
+    two = (C.c_void_p * 2)(h, h)
+    assert L.mcp_portfolios_multi(two, 2, C.byref(p), ptr(mu), ptr(sigma), C.byref(ref_out), None) == _lib.MCP_ERR_COMM
+    assert "communicator" in last_error(L, h)
+
+
+def test_two_communicators_merge_through_the_raw_abi(abi):
+    """Two handles on two GPUs, mcp_comm_init_all, one mcp_portfolios_multi call: the picks and arrays of the one-GPU run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    L, h, _lib = abi
+    n = 16
+    mu, sigma = synthetic_inputs(n, seed=0)
+    P = 400_003
+    hs = [C.c_void_p(), C.c_void_p()]
+    for d, hd in enumerate(hs):
+        assert L.mcp_create(d, C.byref(hd)) == 0
+    try:
+        arr = (C.c_void_p * 2)(*hs)
+        assert L.mcp_comm_init_all(arr, 2) == 0, last_error(L, hs[0])
+        rank, world = C.c_int(), C.c_int()
+        assert L.mcp_comm_info(hs[1], C.byref(rank), C.byref(world)) == 0 and (rank.value, world.value) == (1, 2)
+        one, ws1, wt1, b1, _ = _multi_job(L, _lib, [h], 1, mu, sigma, P, True)
+        two, ws2, wt2, b2, ms = _multi_job(L, _lib, hs, 2, mu, sigma, P, True)
+        assert two.max_sharpe.index == one.max_sharpe.index and two.target_risk.index == one.target_risk.index
+        assert two.max_sharpe.sharpe == one.max_sharpe.sharpe and np.array_equal(ws1, ws2) and np.array_equal(wt1, wt2)
+        assert two.n_accepted == one.n_accepted == P and two.n_accepted_global == P and (ms > 0).all()
+        for k in b1:
+            assert np.array_equal(b1[k], b2[k]), k
+        for hd in hs:
+            assert L.mcp_comm_destroy(hd) == 0
+    finally:
+        for hd in hs:
+            L.mcp_destroy(hd)
