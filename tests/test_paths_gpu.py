@@ -45,21 +45,22 @@ def test_rng_paths_match_generator_restatement(mcp, dtype, tol):
     assert np.allclose(out["terminal"] + 1, want + 1, rtol=tol)
 
 
-def test_rng_paths_statistics(mcp):
+@pytest.mark.parametrize("rounds", [10, 7])      # 7: the optional Philox4x32-7 stream must pass the same statistical tier
+def test_rng_paths_statistics(mcp, rounds):
     """Mean of the terminal value is analytic: E[V_T,i] = (1 + mu_i dt)^S; sharding invariance."""
     n, S, M = 16, 252, 400_000
     mu, sigma = synthetic_inputs(n)
     w = np.random.default_rng(1).dirichlet(np.ones(n))
-    out = mcp.simulate_paths(mu, sigma, w, M, S, seed=1, return_terminal=True)
+    out = mcp.simulate_paths(mu, sigma, w, M, S, seed=1, return_terminal=True, philox_rounds=rounds)
     x = out["terminal"].astype(np.float64)
     want = w @ ((1 + mu / 252) ** S) - 1
     assert abs(x.mean() - want) < 4.5 * x.std() / np.sqrt(M)
     # variance of log terminal value of a single asset ~ sigma_ii (weights on one asset)
     e0 = np.zeros(n); e0[0] = 1
-    x0 = mcp.simulate_paths(mu, sigma, e0, 200_000, S, seed=2, return_terminal=True)["terminal"].astype(np.float64)
+    x0 = mcp.simulate_paths(mu, sigma, e0, 200_000, S, seed=2, return_terminal=True, philox_rounds=rounds)["terminal"].astype(np.float64)
     assert np.isclose(np.log1p(x0).var(), sigma[0, 0], rtol=0.03)
     # a shard [a, b) of the same seed reproduces the same terminal values bit for bit
-    part = mcp.simulate_paths(mu, sigma, w, 1000, S, seed=1, first_index=5000, return_terminal=True)["terminal"]
+    part = mcp.simulate_paths(mu, sigma, w, 1000, S, seed=1, first_index=5000, return_terminal=True, philox_rounds=rounds)["terminal"]
     assert np.array_equal(part, out["terminal"][5000:6000])
     for a, (v, c) in out["stats"].items():
         assert v == ref.var(x, a) and np.isclose(c, ref.cvar(x, a), rtol=1e-12)
@@ -111,7 +112,8 @@ def test_cholesky_failure_is_reported(mcp):
         mcp.simulate_paths(mu, bad, np.array([0.5, 0.5]), 10, 5)
 
 
-def test_rng_normals_distribution(mcp):
+@pytest.mark.parametrize("rounds", [10, 7])      # 7: the optional Philox4x32-7 stream must pass the same statistical tier
+def test_rng_normals_distribution(mcp, rounds):
     """Statistical tier for the in-kernel Box-Muller normals: with L = I, one step and dt = 1 the
     terminal value of asset i is z_i, so the kernel's normals can be tested directly: moments,
     independence across assets and a KS test of the marginal against the exact normal CDF."""
@@ -122,7 +124,7 @@ def test_rng_normals_distribution(mcp):
     cols = []
     for i in (0, 1, 7, 15):
         w = np.zeros(n); w[i] = 1.0
-        x = mcp.simulate_paths(mu, sigma, w, M, 1, dt=1.0, seed=11, return_terminal=True)["terminal"].astype(np.float64)
+        x = mcp.simulate_paths(mu, sigma, w, M, 1, dt=1.0, seed=11, return_terminal=True, philox_rounds=rounds)["terminal"].astype(np.float64)
         cols.append(x)
         assert abs(x.mean()) < 4.5 / np.sqrt(M) and abs(x.var() - 1) < 5 * np.sqrt(2 / M)
         assert abs(((x - x.mean()) ** 3).mean()) < 0.02 and abs(((x - x.mean()) ** 4).mean() - 3) < 0.05
@@ -134,5 +136,5 @@ def test_rng_normals_distribution(mcp):
     assert np.abs(c - np.eye(4)).max() < 5 / np.sqrt(M)          # (z0, z1) share a Box-Muller pair: still uncorrelated
     # consecutive steps are independent: two-step compounding variance of log(1 + r) adds up
     w = np.zeros(n); w[3] = 1.0
-    x2 = mcp.simulate_paths(mu, 1e-4 * sigma, w, M, 2, dt=1.0, seed=12, return_terminal=True)["terminal"].astype(np.float64)
+    x2 = mcp.simulate_paths(mu, 1e-4 * sigma, w, M, 2, dt=1.0, seed=12, return_terminal=True, philox_rounds=rounds)["terminal"].astype(np.float64)
     assert np.isclose(x2.var(), 2e-4, rtol=0.01)

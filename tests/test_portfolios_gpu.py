@@ -185,11 +185,12 @@ def test_sharding_invariance(mcp, synth16):
     assert whole.target_risk["global_index"] == int(np.argmin(np.abs(full.risks - 0.30)))
 
 
-def test_rng_statistics_against_numpy_dirichlet(mcp, synth16):
+@pytest.mark.parametrize("rounds", [10, 7])      # 7: the optional Philox4x32-7 stream must pass the same statistical tier
+def test_rng_statistics_against_numpy_dirichlet(mcp, synth16, rounds):
     """Flat Dirichlet: mean 1/N, var (N-1)/(N^2 (N+1)); (risk, return) envelope vs numpy's sampler."""
     mu, sigma = synth16
     N, P = 16, 2_000_000
-    r = mcp.simulate_portfolios(mu, sigma, P, risk_free=0.03, seed=99)
+    r = mcp.simulate_portfolios(mu, sigma, P, risk_free=0.03, seed=99, philox_rounds=rounds)
     W = r.weights
     assert np.allclose(W.sum(1), 1.0, atol=1e-5)
     v = (N - 1) / (N * N * (N + 1))
@@ -446,13 +447,14 @@ def test_default_app_bounds_cost_nothing(mcp, synth16):
     assert r.n_accepted == 1 and len(r.risks) == 1
 
 
-def test_rng_weight_histogram_chi_square(mcp):
+@pytest.mark.parametrize("rounds", [10, 7])      # 7: the optional Philox4x32-7 stream must pass the same statistical tier
+def test_rng_weight_histogram_chi_square(mcp, rounds):
     """A single coordinate of a flat Dirichlet(N) is Beta(1, N-1): chi-square over 64 equal-mass bins,
     for N = 4 and N = 16, and pairwise sums (w_i + w_j ~ Beta(2, N-2)) to catch cross-asset correlation."""
     for N in (4, 16):
         mu, sigma = synthetic_inputs(N)
         P = 4_000_000
-        W = mcp.simulate_portfolios(mu, sigma, P, seed=21).weights.astype(np.float64)
+        W = mcp.simulate_portfolios(mu, sigma, P, seed=21, philox_rounds=rounds).weights.astype(np.float64)
         edges = 1 - (1 - np.linspace(0, 1, 65)) ** (1 / (N - 1))                   # Beta(1, N-1) quantiles
         for col in (0, N - 1):
             counts = np.histogram(W[:, col], bins=edges)[0]
