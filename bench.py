@@ -460,7 +460,7 @@ def run_ours(args):
     del xq
     p_achieved = my_paths * N_STEPS * flops_per_path_step(n) / paths_kernel_s / 1e12
     tc_paths = os.environ.get("MCP_PATHS_TC", "1") != "0"
-    paths_ncu = ncu_figures("path_kernel_tc" if tc_paths else "path_kernel_packed<16>")
+    paths_ncu = ncu_figures("path_kernel_tc<16, 4, 1, 1, 10>" if tc_paths else "path_kernel_packed<16, 10>") or ncu_figures("path_kernel_packed<16>")
     paths_roofline = {"bound": "fp32-simt",
                       "kernel": ("path_kernel_tc<16> (Philox + Box-Muller on SIMT warps, L.z on tcgen05: FP16-split normals from TMEM x L' images in "
                                  "shared memory, FP32 accumulate; histogram of the terminal values in the epilogue)") if tc_paths else

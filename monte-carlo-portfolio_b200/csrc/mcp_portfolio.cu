@@ -275,10 +275,16 @@ static int portfolios_impl(mcp_handle h, const mcp_portfolio_params* p, const do
         // at full PCIe rate while the host memcpy of chunk c-1 into (or chunk c+1 out of) the caller's pages overlaps it.  Smaller
         // chunks then, so that there is something to overlap with.  Page-locked buffers (mcp_host_alloc) are copied directly.
         const bool stage_in = in_row && !host_is_pinned(p->weights_in);
-        const bool stage_out = out_row && !(host_is_pinned(out->weights) && host_is_pinned(out->returns) && host_is_pinned(out->risks) &&
-                                            host_is_pinned(out->sharpes) && host_is_pinned(out->accepted));
+        // per output array: only the pageable ones are staged (a small pageable array -- the accepted flags, say -- must not pull the
+        // page-locked 64 MB of weights through the staging buffers with it)
+        const bool stg[5] = {out->weights && !host_is_pinned(out->weights), out->returns && !host_is_pinned(out->returns),
+                             out->risks && !host_is_pinned(out->risks), out->sharpes && !host_is_pinned(out->sharpes),
+                             out->accepted && !host_is_pinned(out->accepted)};
+        const size_t staged_row = (stg[0] ? (size_t)N * es : 0) + (stg[1] ? es : 0) + (stg[2] ? es : 0) + (stg[3] ? es : 0) + (stg[4] ? 1 : 0);
+        const bool stage_out = staged_row != 0;
         uint64_t chunk = P;
-        const size_t budget = (stage_in || stage_out) ? (size_t)16 << 20 : (size_t)96 << 20;            // bytes per slot and direction
+        // small chunks only when a substantial part of the traffic is staged (there must be something for the host memcpy to overlap)
+        const size_t budget = (stage_in || staged_row * 8 > out_row) ? (size_t)16 << 20 : (size_t)96 << 20;   // bytes per slot and direction
         if (in_row) chunk = std::min<uint64_t>(chunk, std::max<size_t>(budget / in_row, 1024));
         if (out_row) chunk = std::min<uint64_t>(chunk, std::max<size_t>(budget / out_row, 1024));
         chunk = (chunk + PF_BLOCK - 1) / PF_BLOCK * PF_BLOCK;
@@ -367,7 +373,7 @@ static int portfolios_impl(mcp_handle h, const mcp_portfolio_params* p, const do
             auto back = [&](unsigned char* dsrc, void* user, size_t row_bytes, int which, unsigned char*& staged) {
                 staged = nullptr;
                 if (!dsrc || !user) return cudaSuccess;
-                if (stage_out) {
+                if (stg[which]) {
                     staged = p_out + offs[which];
                     return cudaMemcpyAsync(staged, dsrc, rows * row_bytes, cudaMemcpyDeviceToHost, ss);
                 }

@@ -213,7 +213,7 @@ def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
     return np.frombuffer(buf, dtype=dt, count=count).reshape(shape)
 
 
-_PINNED_MIN_BYTES = 1 << 20      # smaller results are not worth a pinned block
+_PINNED_MIN_BYTES = 1 << 16      # smaller results are not worth a pinned block
 
 
 def _result_empty(shape, dtype):

@@ -88,6 +88,41 @@ def test_tensor_core_sweep_any_shape(mcp, n, P, seed, first, supplied):
 
 
 @settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(n=st.integers(33, 256), P=st.integers(1, 3000), seed=st.integers(0, 2**40), first=st.integers(0, 2**45),
+       hi_scale=st.floats(1.5, 6.0), lo_scale=st.sampled_from([0.0, 0.0, 0.02, 0.2]), tries=st.integers(1, 6), keep_last=st.booleans())
+def test_bounded_tensor_core_sweep_any_shape(mcp, n, P, seed, first, hi_scale, lo_scale, tries, keep_last):
+    """Bounds rejection at 32 < N <= 256 (app.py:700-707): the tcgen05 rounds + SIMT list route against the SIMT-only sweep
+    (same accept / skip decisions, same attempts) and against the generator restatement with the reference's rejection loop."""
+    import os
+    mu, sigma = synthetic_inputs(n, seed=n + 5)
+    hi = np.full(n, hi_scale / n)                        # the largest of n flat-Dirichlet weights is ~ (ln n + 0.58) / n
+    lo = np.full(n, lo_scale / (n * n)) if lo_scale else None      # the smallest is ~ 1 / n^2
+    kw = dict(min_weights=lo, max_weights=hi, seed=seed, first_index=first, max_tries=tries, keep_last=keep_last, risk_free=0.03)
+    a = mcp.simulate_portfolios(mu, sigma, P, **kw)
+    os.environ["MCP_LARGE_TC_BOUNDS"] = "0"
+    try:
+        b = mcp.simulate_portfolios(mu, sigma, P, **kw)
+    finally:
+        os.environ.pop("MCP_LARGE_TC_BOUNDS")
+    assert a.n_accepted == b.n_accepted and np.array_equal(a.accepted, b.accepted)
+    if keep_last:
+        assert a.n_accepted == P
+    if a.n_accepted:
+        assert np.allclose(a.weights, b.weights, rtol=0, atol=3e-7)
+        assert np.allclose(a.risks, b.risks, rtol=2e-5) and np.allclose(a.sharpes, b.sharpes, rtol=2e-5, atol=2e-5)
+        assert a.max_sharpe["index"] == int(np.argmax(a.sharpes))
+        W, valid = philox_np.dirichlet_weights(first, P, n, seed, "float32", lo, hi, max_tries=tries, keep_last=keep_last)
+        acc = a.accepted.astype(bool)
+        edge = np.abs(W - hi).min(1) if lo is None else np.minimum(np.abs(W - hi).min(1), np.abs(W - lo).min(1))
+        differ = acc != valid
+        assert differ.sum() <= 2 and np.all(edge[differ] < 1e-6)
+        both = acc & valid
+        assert np.allclose(a.weights[np.cumsum(acc)[both] - 1], W[both], atol=2e-6)
+    else:
+        assert a.max_sharpe is None
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
 @given(T=st.integers(2, 520), n=st.integers(1, 24), P=st.integers(1, 300), alpha=st.sampled_from([0.9, 0.95, 0.99, 0.5]),
        decimals=st.sampled_from([2, 3, 8]), dtype=st.sampled_from(["float32", "float64"]), seed=st.integers(0, 10**6))
 def test_historical_var_cvar_any_shape(mcp, T, n, P, alpha, decimals, dtype, seed):
