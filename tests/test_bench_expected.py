@@ -48,3 +48,25 @@ def test_ncu_figures_come_from_the_committed_file():
     assert f is not None and 0 < f["fp32_pipe_busy_pct"] < 100 and f["source"].startswith("profiles/")
     assert isinstance(f["digest_matches_build"], bool)
     assert bench.ncu_figures("no such kernel") is None
+
+
+def test_expected_c3_picks_are_what_the_generator_restatement_gives():
+    """The two golden indices of the 1e10-portfolio job, re-derived on the CPU: the numpy restatement of the generator draws the
+    weights of those global indices, the FP64 oracle evaluates them -- the Sharpe ratio / risk the GPU reported (FP32, 1e-4) -- and
+    inside a 4e5-index neighbourhood of each no other portfolio beats them (the whole range cannot be swept on a CPU)."""
+    import numpy as np
+    from conftest import synthetic_inputs
+    from oracle import philox_np, reference_np as ref
+    with open(os.path.join(ROOT, "tests", "golden", "c3c4c5_expected.json")) as fh:
+        want = json.load(fh)["c3"]
+    mu, sigma = synthetic_inputs(bench.N_ASSETS)
+    assert np.array_equal(mu, bench.synthetic_inputs(bench.N_ASSETS)[0])
+    half = 200_000
+    i = want["max_sharpe_index"]
+    W, _ = philox_np.dirichlet_weights(i - half, 2 * half, bench.N_ASSETS, seed=bench.SEED)
+    e = ref.evaluate(W, mu, sigma, bench.RISK_FREE, bench.RISK_TARGET)
+    assert int(np.argmax(e["sharpes"])) == half and np.isclose(e["sharpes"][half], want["max_sharpe"], rtol=1e-4)
+    j = want["target_risk_index"]
+    W, _ = philox_np.dirichlet_weights(j - half, 2 * half, bench.N_ASSETS, seed=bench.SEED)
+    e = ref.evaluate(W, mu, sigma, bench.RISK_FREE, bench.RISK_TARGET)
+    assert int(np.argmin(np.abs(e["risks"] - bench.RISK_TARGET))) == half and np.isclose(e["risks"][half], want["target_risk"], rtol=1e-4)
