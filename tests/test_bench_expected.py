@@ -70,3 +70,11 @@ def test_expected_c3_picks_are_what_the_generator_restatement_gives():
     W, _ = philox_np.dirichlet_weights(j - half, 2 * half, bench.N_ASSETS, seed=bench.SEED)
     e = ref.evaluate(W, mu, sigma, bench.RISK_FREE, bench.RISK_TARGET)
     assert int(np.argmin(np.abs(e["risks"] - bench.RISK_TARGET))) == half and np.isclose(e["risks"][half], want["target_risk"], rtol=1e-4)
+    # C5 (256 assets): the nearest-to-30 % pick is the riskiest portfolio of the job; same check on a 4e4-index neighbourhood
+    with open(os.path.join(ROOT, "tests", "golden", "c3c4c5_expected.json")) as fh:
+        c5 = json.load(fh)["c5"]
+    mu, sigma = synthetic_inputs(bench.N_LARGE)
+    k, half = c5["target_risk_index"], 20_000
+    W, _ = philox_np.dirichlet_weights(k - half, 2 * half, bench.N_LARGE, seed=bench.SEED)
+    e = ref.evaluate(W, mu, sigma, bench.RISK_FREE, bench.RISK_TARGET)
+    assert int(np.argmin(np.abs(e["risks"] - bench.RISK_TARGET))) == half and np.isclose(e["risks"][half], c5["target_risk"], rtol=1e-4)
