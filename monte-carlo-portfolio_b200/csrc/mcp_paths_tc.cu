@@ -45,7 +45,7 @@ constexpr int PTC_MAX_MMA_WARPS = 4;
 // MMAs of step s - 2, which finished long ago -- the issue latency of the MMA warp (~0.5 us per tile-step) leaves the
 // critical path.  STAGES = 1 fits more tiles (more resident generator warps) but exposes that latency.
 template <int NP, int STAGES> struct PtcCfg {
-    static_assert(NP == 16 || NP == 32, "padded asset counts of the tensor-core path kernel");
+    static_assert(NP == 16 || NP == 32 || NP == 64 || NP == 128, "padded asset counts of the tensor-core path kernels");
     static_assert(STAGES == 1 || STAGES == 2, "one or two A / D stages per tile");
     static constexpr int KB = NP + 8;                        // K extent of the hi image: NP normals + the constant block (drift)
     static constexpr uint32_t STAGE_COLS = 3 * NP, COL_D = 0, COL_Z = NP, COL_ZLO = 2 * NP, COL_ONE = STAGES * STAGE_COLS;
@@ -335,6 +335,183 @@ __global__ void __launch_bounds__(WG* PTC_ROWS + 32 * PTC_MAX_MMA_WARPS, 1) path
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// 32 < N <= 128: the same scheme with the step's normals produced and stored 16 at a time.  A thread still owns one path (its
+// compounded values V are N registers), but a whole step's normals and their remainders would not fit next to them, so chunk c
+// (normals 16c .. 16c+15 = Philox blocks 3c .. 3c+2 of the step's stream, as in every other path kernel) goes from the registers
+// straight into its 16 + 16 tensor-memory columns before the next chunk is drawn.  One A / D stage per tile (3 N + 8 columns:
+// two tiles at N = 64, one at N = 128); the first chunk of step s + 1 is drawn before the thread waits for the MMAs of step s.
+// The MMA warp issues the 3 N / 8 + 1 tcgen05.mma of a tile-step in a loop (49 at N = 128): at these widths the generator's
+// work per step, which grows with N like the MMA count, keeps the issue off the critical path.
+// ---------------------------------------------------------------------------------------------------------------------------
+template <int NP, int WG, int ROUNDS>
+__global__ void __launch_bounds__(WG* PTC_ROWS + 32 * WG, 1) path_kernel_tc_wide(const __grid_constant__ PtcArgs<NP> a) {
+    using Cfg = PtcCfg<NP, 1>;
+    constexpr int TILES = WG, GEN_WARPS = 4 * WG, NCH = NP / 16;
+    constexpr int NBINS = 1 << MCP_SEL_BITS;
+    static_assert(TILES * Cfg::TILE_COLS <= 512, "tiles x columns exceed tensor memory");
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* sHi = smem;
+    unsigned char* sLo = smem + Cfg::HI_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sLo + Cfg::LO_BYTES);
+    uint64_t* full = bars;                               // [TILES] 128 arrivals: the step's A operand is in tensor memory
+    uint64_t* done = bars + PTC_MAX_TILES;               // [TILES] tcgen05.commit: the step's MMAs are complete
+    uint64_t* table_bar = bars + 2 * PTC_MAX_TILES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * PTC_MAX_TILES + 1);
+    unsigned int* sHist = reinterpret_cast<unsigned int*>(bars + 2 * PTC_MAX_TILES + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nthreads = (int)blockDim.x;
+    if (tid == 0) {
+        for (int t = 0; t < TILES; ++t) { mbar_init(&full[t], PTC_ROWS); mbar_init(&done[t], 1); }
+        mbar_init(table_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t bytes = Cfg::HI_BYTES + Cfg::LO_BYTES;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(table_bar)), "r"(bytes) : "memory");
+        for (uint32_t off = 0; off < bytes; off += 32768u) {
+            const uint32_t part = bytes - off < 32768u ? bytes - off : 32768u;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(smem + off)), "l"(a.table + off), "r"(part), "r"(smem_u32(table_bar)) : "memory");
+        }
+    }
+    if (warp == GEN_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (a.hist0 != nullptr)
+        for (int i = tid; i < NBINS; i += nthreads) sHist[i] = 0u;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    mbar_wait(table_bar, 0u);
+    const uint32_t tmem = *tmem_slot;
+
+    const uint64_t n_tiles = (a.M + PTC_ROWS - 1) / PTC_ROWS;
+    const uint64_t slots = (uint64_t)gridDim.x * TILES;
+    const uint32_t S = (uint32_t)a.n_steps;
+
+    if (warp < GEN_WARPS) {
+        const int t0 = warp >> 2, row = tid & (PTC_ROWS - 1);
+        const uint32_t tile_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + Cfg::TILE_COLS * (uint32_t)t0;
+        const float kPi = 3.14159265358979323846f;
+        const uint32_t one_bits = opaque_u32(0x3f800000u), two_bits = opaque_u32(0x40000000u);
+        {
+            const uint32_t ones[8] = {0x3f800000u, 0x3f800000u, 0x3f800000u, 0u, 0u, 0u, 0u, 0u};
+            tmem_st8(tile_base + Cfg::COL_ONE, ones);
+        }
+        uint32_t ph = 0;
+        for (uint64_t tile = (uint64_t)blockIdx.x * TILES + t0; tile < n_tiles; tile += slots) {
+            const uint64_t m = tile * PTC_ROWS + (uint64_t)row;
+            const uint64_t gidx = a.first + m;
+            const uint32_t c0 = (uint32_t)gidx, c1 = (uint32_t)(gidx >> 32);
+            float2 V[NP / 2];
+#pragma unroll
+            for (int i = 0; i < NP / 2; ++i) V[i] = make_float2(1.f, 1.f);
+            // normals 16c .. 16c+15 of step s and their TF32 remainders (register order z[4q], z[4q+2], z[4q+1], z[4q+3], see ptc_normal_of_col)
+            auto draw = [&](uint32_t s, int c, uint32_t (&z)[16], uint32_t (&zlo)[16]) {
+                uint32_t f[16];
+                philox_fields<16, ROUNDS>(c0, c1, s, STREAM_NORMALS + (uint32_t)(3 * c), a.rk, f);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 f1 = make_float2(__uint_as_float(mant_or(f[4 * q], one_bits)), __uint_as_float(mant_or(f[4 * q + 2], one_bits)));
+                    const float2 u1 = fma2(f1, bcast2(-1.0f), bcast2(2.0f));
+                    const float2 r = make_float2(Math<float>::sqrt(-Math<float>::lg2(u1.x)), Math<float>::sqrt(-Math<float>::lg2(u1.y)));
+                    const float2 f2 = make_float2(__uint_as_float(mant_or(f[4 * q + 1], two_bits)), __uint_as_float(mant_or(f[4 * q + 3], two_bits)));
+                    const float2 th = fma2(f2, bcast2(kPi), bcast2(-3.0f * kPi));
+                    const float2 cs = make_float2(Math<float>::cosf_(th.x), Math<float>::cosf_(th.y));
+                    const float2 sn = make_float2(Math<float>::sinf_(th.x), Math<float>::sinf_(th.y));
+                    const float2 zc = fma2(r, cs, bcast2(0.0f)), zs = fma2(r, sn, bcast2(0.0f));
+                    const float2 hc = make_float2(__uint_as_float(__float_as_uint(zc.x) & 0xffffe000u), __uint_as_float(__float_as_uint(zc.y) & 0xffffe000u));
+                    const float2 hs = make_float2(__uint_as_float(__float_as_uint(zs.x) & 0xffffe000u), __uint_as_float(__float_as_uint(zs.y) & 0xffffe000u));
+                    const float2 lc = fma2(hc, bcast2(-1.0f), zc), ls = fma2(hs, bcast2(-1.0f), zs);
+                    z[4 * q] = __float_as_uint(zc.x); z[4 * q + 1] = __float_as_uint(zc.y);
+                    z[4 * q + 2] = __float_as_uint(zs.x); z[4 * q + 3] = __float_as_uint(zs.y);
+                    zlo[4 * q] = __float_as_uint(lc.x); zlo[4 * q + 1] = __float_as_uint(lc.y);
+                    zlo[4 * q + 2] = __float_as_uint(ls.x); zlo[4 * q + 3] = __float_as_uint(ls.y);
+                }
+            };
+            auto compound = [&](uint32_t g) {            // R row of published step g: wait for its MMAs, V *= 1 + r
+                mbar_wait(&done[t0], g & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int b = 0; b < NP / 32; ++b) {
+                    uint32_t d[32];
+                    tmem_ld32(tile_base + Cfg::COL_D + 32u * (uint32_t)b, d);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        V[16 * b + i] = fma2(V[16 * b + i], make_float2(__uint_as_float(d[2 * i]), __uint_as_float(d[2 * i + 1])), V[16 * b + i]);
+                }
+            };
+            for (uint32_t s = 0; s < S; ++s) {
+                uint32_t z[16], zlo[16];
+                draw(s, 0, z, zlo);                      // overlaps the MMAs of step s - 1
+                if (s > 0) compound(ph - 1u);            // ... whose result frees the tile's one stage
+                tmem_st16(tile_base + Cfg::COL_Z, z);
+                tmem_st16(tile_base + Cfg::COL_ZLO, zlo);
+#pragma unroll
+                for (int c = 1; c < NCH; ++c) {
+                    draw(s, c, z, zlo);
+                    tmem_st16(tile_base + Cfg::COL_Z + 16u * (uint32_t)c, z);
+                    tmem_st16(tile_base + Cfg::COL_ZLO + 16u * (uint32_t)c, zlo);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                mbar_arrive(&full[t0]);
+                ++ph;
+            }
+            compound(ph - 1u);
+            float2 x2 = make_float2(-1.0f, 0.0f);
+#pragma unroll
+            for (int i = 0; i < NP / 2; ++i) x2 = fma2(make_float2(a.w[2 * i], a.w[2 * i + 1]), V[i], x2);
+            const float x = x2.x + x2.y;
+            if (m < a.M) {
+                a.terminal[m] = x;
+                if (a.hist0 != nullptr) {
+                    const unsigned digit = f32_to_key(__float_as_uint(x)) >> (32 - MCP_SEL_BITS);
+                    const unsigned act = __activemask();
+                    const unsigned peers = __match_any_sync(act, digit);
+                    if (lane == __ffs(peers) - 1) atomicAdd(&sHist[digit], (unsigned)__popc(peers));
+                }
+            }
+        }
+    } else {
+        // MMA issue warp of tile t = warp - GEN_WARPS: R = z Lhi (overwrites) + zlo Lhi + z Llo + [1 1 1 0 ..] drift, K = 8 per tcgen05.mma
+        const int t = warp - GEN_WARPS;
+        const uint32_t idesc = tc_idesc(2u, (uint32_t)NP);
+        const uint64_t bhi0 = tc_sdesc(smem_u32(sHi), Cfg::LBO, Cfg::SBO), blo0 = tc_sdesc(smem_u32(sLo), Cfg::LBO, Cfg::SBO);
+        const uint32_t base = tmem + Cfg::TILE_COLS * (uint32_t)t;
+        uint32_t ph = 0;
+        for (uint64_t tile = (uint64_t)blockIdx.x * TILES + (uint64_t)t; tile < n_tiles; tile += slots) {
+            for (uint32_t s = 0; s < S; ++s, ++ph) {
+                mbar_wait_idle(&full[t], ph & 1u);
+                tc_fence_after();
+#pragma unroll 1
+                for (uint32_t k = 0; k < (uint32_t)(NP / 8); ++k)
+                    mma_tf32_ts_elect(base + Cfg::COL_D, base + Cfg::COL_Z + 8u * k, bhi0 + (uint64_t)(k * Cfg::DESC_STEP), idesc, k > 0 ? 1u : 0u);
+#pragma unroll 1
+                for (uint32_t k = 0; k < (uint32_t)(NP / 8); ++k)
+                    mma_tf32_ts_elect(base + Cfg::COL_D, base + Cfg::COL_ZLO + 8u * k, bhi0 + (uint64_t)(k * Cfg::DESC_STEP), idesc, 1u);
+#pragma unroll 1
+                for (uint32_t k = 0; k < (uint32_t)(NP / 8); ++k)
+                    mma_tf32_ts_elect(base + Cfg::COL_D, base + Cfg::COL_Z + 8u * k, blo0 + (uint64_t)(k * Cfg::DESC_STEP), idesc, 1u);
+                mma_tf32_ts_elect(base + Cfg::COL_D, base + Cfg::COL_ONE, bhi0 + (uint64_t)((NP / 8) * Cfg::DESC_STEP), idesc, 1u);
+                tc_commit_elect(&done[t]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == GEN_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    if (a.hist0 != nullptr) {
+        for (int i = tid; i < NBINS; i += nthreads) {
+            const unsigned c = sHist[i];
+            if (c) atomicAdd(&a.hist0[i], (unsigned long long)c);
+        }
+    }
+}
+
 // ---- host side -------------------------------------------------------------------------------
 
 static inline float ptc_tf32_round(float x) {          // round-to-nearest-even onto 10 explicit mantissa bits
@@ -350,7 +527,7 @@ static inline float ptc_tf32_round(float x) {          // round-to-nearest-even 
 bool path_tc_eligible(const PathJob& job) {
     const char* v = getenv("MCP_PATHS_TC");               // "0" forces the SIMT kernels (A/B tests, benchmarks)
     if (v && v[0] == '0') return false;
-    return job.dtype == MCP_F32 && job.z_in == nullptr && job.n <= 32;
+    return job.dtype == MCP_F32 && job.z_in == nullptr && job.n <= 128;
 }
 
 static int ptc_env(const char* name, int lo, int hi) {   // tuning knobs: 0 = default
@@ -371,6 +548,21 @@ static int ptc_launch_t(mcp_context* h, PathJob& job, const PtcArgs<NP>& a, int 
     if (grid < 1) grid = 1;
     nmma = std::max(1, std::min(nmma, std::min(TILES, PTC_MAX_MMA_WARPS)));
     kern<<<(unsigned)grid, WG * PTC_ROWS + 32 * nmma, smem, job.stream>>>(a);
+    MCP_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return MCP_OK;
+}
+
+template <int NP, int WG, int ROUNDS>
+static int ptc_launch_wide_t(mcp_context* h, PathJob& job, const PtcArgs<NP>& a) {
+    using Cfg = PtcCfg<NP, 1>;
+    auto kern = path_kernel_tc_wide<NP, WG, ROUNDS>;
+    const size_t smem = Cfg::HI_BYTES + Cfg::LO_BYTES + (2 * PTC_MAX_TILES + 2) * sizeof(uint64_t) + (job.hist0 ? sizeof(unsigned int) << MCP_SEL_BITS : 0) + 128;
+    MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t n_tiles = (job.M + PTC_ROWS - 1) / PTC_ROWS;
+    uint64_t grid = std::min<uint64_t>((uint64_t)h->prop.multiProcessorCount, (n_tiles + WG - 1) / WG);
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, WG * PTC_ROWS + 32 * WG, smem, job.stream>>>(a);
     MCP_CUDA(h, cudaGetLastError());
     h->launches++;
     return MCP_OK;
@@ -424,6 +616,12 @@ static int ptc_launch(mcp_context* h, PathJob& job) {
     static const int wg_env = ptc_env("MCP_PATHS_TC_WG", 1, PTC_MAX_TILES), ppt_env = ptc_env("MCP_PATHS_TC_PPT", 1, 2),
                      stages_env = ptc_env("MCP_PATHS_TC_STAGES", 1, 2), nmma_env = ptc_env("MCP_PATHS_TC_MMA", 1, PTC_MAX_MMA_WARPS);
     const int nmma = nmma_env ? nmma_env : 4;
+    if constexpr (NP > 32) {
+        // one stage per tile, 3 NP + 8 columns: two tiles at NP = 64, one at NP = 128
+        constexpr int WGW = NP == 64 ? 2 : 1;
+        (void)wg_env; (void)ppt_env; (void)stages_env; (void)nmma;
+        return job.rounds == 7 ? ptc_launch_wide_t<NP, WGW, 7>(h, job, a) : ptc_launch_wide_t<NP, WGW, 10>(h, job, a);
+    } else {
 #define MCP_PTC(W, P, ST)                                                                                  \
     return job.rounds == 7 ? ptc_launch_t<NP, W, P, ST, 7>(h, job, a, nmma) : ptc_launch_t<NP, W, P, ST, 10>(h, job, a, nmma);
     if constexpr (NP == 16) {
@@ -467,10 +665,13 @@ static int ptc_launch(mcp_context* h, PathJob& job) {
         }
     }
 #undef MCP_PTC
+    }
 }
 
 int path_launch_tc(mcp_context* h, PathJob& job) {
-    return job.n <= 16 ? ptc_launch<16>(h, job) : ptc_launch<32>(h, job);
+    if (job.n <= 16) return ptc_launch<16>(h, job);
+    if (job.n <= 32) return ptc_launch<32>(h, job);
+    return job.n <= 64 ? ptc_launch<64>(h, job) : ptc_launch<128>(h, job);
 }
 
 }  // namespace mcp

@@ -419,3 +419,30 @@ def test_bounded_tensor_core_sweep_sharding_and_host_pipeline(mcp):
     with _env(MCP_LARGE_TC_BOUNDS="0"):
         simt = mcp.simulate_portfolios(mu, sigma, P, max_weights=hi, seed=2, max_tries=4, risk_free=0.03, return_arrays=False)
     assert simt.n_accepted == whole.n_accepted
+
+
+# ---- tcgen05 path kernel for 32 < N <= 128 (normals drawn and stored 16 at a time) --------------------------------------------
+
+@pytest.mark.parametrize("n,steps,M", [(33, 9, 300), (64, 30, 700), (100, 12, 1000), (128, 20, 500), (70, 252, 260)])
+def test_wide_tc_paths_match_the_generator_restatement_and_the_simt_kernel(mcp, n, steps, M):
+    mu, sigma = synthetic_inputs(n, seed=6)
+    w = np.random.default_rng(n).dirichlet(np.ones(n))
+    first, seed = 3_000_000_000, 41
+    a = mcp.simulate_paths(mu, sigma, w, M, steps, seed=seed, first_index=first, return_terminal=True)
+    with _env(MCP_PATHS_TC="0"):
+        b = mcp.simulate_paths(mu, sigma, w, M, steps, seed=seed, first_index=first, return_terminal=True)
+    Z = philox_np.normals(first, M, steps, n, seed, "float32")
+    want = paths_np.terminal_returns(mu, sigma, w, Z)
+    assert np.allclose(a["terminal"] + 1.0, want + 1.0, rtol=1e-4)            # north star, FP32
+    assert np.allclose(b["terminal"] + 1.0, want + 1.0, rtol=1e-4)
+    assert np.allclose(a["terminal"] + 1.0, b["terminal"] + 1.0, rtol=3e-5)
+    x = a["terminal"].astype(np.float64)
+    for alpha, (v, c) in a["stats"].items():                                  # the kernel-filled first histogram feeds the exact select
+        assert v == ref.var(x, alpha) and np.isclose(c, ref.cvar(x, alpha), rtol=1e-12)
+    # shards of the same seed reproduce the same paths bit for bit; 7 rounds is another stream
+    part = mcp.simulate_paths(mu, sigma, w, 130, steps, seed=seed, first_index=first + 129, return_terminal=True)["terminal"]
+    assert np.array_equal(part, a["terminal"][129:259])
+    if steps <= 30:
+        Z7 = philox_np.normals(first, 200, steps, n, seed, "float32", rounds=7)
+        p7 = mcp.simulate_paths(mu, sigma, w, 200, steps, seed=seed, first_index=first, return_terminal=True, philox_rounds=7)
+        assert np.allclose(p7["terminal"] + 1.0, paths_np.terminal_returns(mu, sigma, w, Z7) + 1.0, rtol=1e-4)
