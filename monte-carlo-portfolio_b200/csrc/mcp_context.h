@@ -37,7 +37,8 @@ struct mcp_context {
     // mcp_paths_stats when the caller does not want them, [17] first radix histogram filled by the path kernel,
     // [18] mu / Sigma estimation (returns matrix, results), [19] historical recheck (candidate lists, FP64 rows),
     // [20] constants of the tiled SIMT sweep when it runs next to the tcgen05 sweep (bounded route), [21..22] deferred-row
-    // list of the bounded tcgen05 sweep (per pipeline stream)
+    // list of the bounded tcgen05 sweep (per pipeline stream), [23] per-block partial terminal sums of the tcgen05 path kernel
+    // for 128 < N <= 256
     mcp_scratch dev[24];
     // pinned host scratch: [0..1] HOST-space staging of pageable outputs (per pipeline slot), [2] inputs, [3] collectives,
     // [4] small results (records / stats) read back with one copy

@@ -64,7 +64,11 @@ struct PtcArgs {
     unsigned long long* hist0;           // [1 << MCP_SEL_BITS] or null
     uint64_t first, M;
     int n_steps;
-    int ablate;                          // measurement only (MCP_PATHS_TC_ABLATE): 1 = commit without MMAs
+    // path_kernel_tc_wide only: the tile's outputs are one BLOCK of NP assets of a wider universe whose K extent (the normals
+    // 0 .. k_rounds NP - 1 its rows of L reach) is worked off in k_rounds rounds of NP normals; x0 = the constant of the
+    // terminal sum (-1 for a whole universe, 0 for a block's partial sum)
+    int k_rounds;
+    float x0;
     PhiloxKeys rk;
 };
 
@@ -317,8 +321,7 @@ __global__ void __launch_bounds__(WG* PTC_ROWS + 32 * PTC_MAX_MMA_WARPS, 1) path
                     const uint32_t base = tmem + Cfg::TILE_COLS * (uint32_t)t, sb = base + st * Cfg::STAGE_COLS;
                     mbar_wait_idle(&full[2 * t + st], use & 1u);
                     tc_fence_after();
-                    if (a.ablate & 1) tc_commit_elect(&done[2 * t + st]);
-                    else ptc_issue<NP>(sb + Cfg::COL_D, sb + Cfg::COL_Z, sb + Cfg::COL_ZLO, base + Cfg::COL_ONE, bhi0, blo0, idesc, smem_u32(&done[2 * t + st]));
+                    ptc_issue<NP>(sb + Cfg::COL_D, sb + Cfg::COL_Z, sb + Cfg::COL_ZLO, base + Cfg::COL_ONE, bhi0, blo0, idesc, smem_u32(&done[2 * t + st]));
                 }
             }
         }
@@ -351,11 +354,11 @@ __global__ void __launch_bounds__(WG* PTC_ROWS + 32 * WG, 1) path_kernel_tc_wide
     constexpr int NBINS = 1 << MCP_SEL_BITS;
     static_assert(TILES * Cfg::TILE_COLS <= 512, "tiles x columns exceed tensor memory");
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* sHi = smem;
-    unsigned char* sLo = smem + Cfg::HI_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sLo + Cfg::LO_BYTES);
-    uint64_t* full = bars;                               // [TILES] 128 arrivals: the step's A operand is in tensor memory
-    uint64_t* done = bars + PTC_MAX_TILES;               // [TILES] tcgen05.commit: the step's MMAs are complete
+    constexpr uint32_t IMG_BYTES = Cfg::HI_BYTES + Cfg::LO_BYTES;       // one K round: Bhi image | Blo image
+    const int KR = a.k_rounds;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)KR * IMG_BYTES);
+    uint64_t* full = bars;                               // [TILES] 128 arrivals: the round's A operand is in tensor memory
+    uint64_t* done = bars + PTC_MAX_TILES;               // [TILES] tcgen05.commit: the round's MMAs are complete
     uint64_t* table_bar = bars + 2 * PTC_MAX_TILES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * PTC_MAX_TILES + 1);
     unsigned int* sHist = reinterpret_cast<unsigned int*>(bars + 2 * PTC_MAX_TILES + 2);
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(WG* PTC_ROWS + 32 * WG, 1) path_kernel_tc_wide
         for (int t = 0; t < TILES; ++t) { mbar_init(&full[t], PTC_ROWS); mbar_init(&done[t], 1); }
         mbar_init(table_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t bytes = Cfg::HI_BYTES + Cfg::LO_BYTES;
+        const uint32_t bytes = (uint32_t)KR * IMG_BYTES;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(table_bar)), "r"(bytes) : "memory");
         for (uint32_t off = 0; off < bytes; off += 32768u) {
             const uint32_t part = bytes - off < 32768u ? bytes - off : 32768u;
@@ -430,9 +433,7 @@ __global__ void __launch_bounds__(WG* PTC_ROWS + 32 * WG, 1) path_kernel_tc_wide
                     zlo[4 * q + 2] = __float_as_uint(ls.x); zlo[4 * q + 3] = __float_as_uint(ls.y);
                 }
             };
-            auto compound = [&](uint32_t g) {            // R row of published step g: wait for its MMAs, V *= 1 + r
-                mbar_wait(&done[t0], g & 1u);
-                tc_fence_after();
+            auto compound = [&]() {                      // R row of the finished step: V *= 1 + r
 #pragma unroll
                 for (int b = 0; b < NP / 32; ++b) {
                     uint32_t d[32];
@@ -444,24 +445,32 @@ __global__ void __launch_bounds__(WG* PTC_ROWS + 32 * WG, 1) path_kernel_tc_wide
                 }
             };
             for (uint32_t s = 0; s < S; ++s) {
-                uint32_t z[16], zlo[16];
-                draw(s, 0, z, zlo);                      // overlaps the MMAs of step s - 1
-                if (s > 0) compound(ph - 1u);            // ... whose result frees the tile's one stage
-                tmem_st16(tile_base + Cfg::COL_Z, z);
-                tmem_st16(tile_base + Cfg::COL_ZLO, zlo);
+                for (int r = 0; r < KR; ++r) {           // K rounds: normals r NP .. r NP + NP - 1 against round r's images of B
+                    uint32_t z[16], zlo[16];
+                    draw(s, r * NCH, z, zlo);            // overlaps the MMAs of the previous round
+                    if (s > 0 || r > 0) {                // ... which must be complete before the tile's one A stage is overwritten
+                        mbar_wait(&done[t0], (ph - 1u) & 1u);
+                        tc_fence_after();
+                        if (r == 0) compound();          // a new step: the finished one's R row is read first (frees the accumulator)
+                    }
+                    tmem_st16(tile_base + Cfg::COL_Z, z);
+                    tmem_st16(tile_base + Cfg::COL_ZLO, zlo);
 #pragma unroll
-                for (int c = 1; c < NCH; ++c) {
-                    draw(s, c, z, zlo);
-                    tmem_st16(tile_base + Cfg::COL_Z + 16u * (uint32_t)c, z);
-                    tmem_st16(tile_base + Cfg::COL_ZLO + 16u * (uint32_t)c, zlo);
+                    for (int c = 1; c < NCH; ++c) {
+                        draw(s, r * NCH + c, z, zlo);
+                        tmem_st16(tile_base + Cfg::COL_Z + 16u * (uint32_t)c, z);
+                        tmem_st16(tile_base + Cfg::COL_ZLO + 16u * (uint32_t)c, zlo);
+                    }
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    mbar_arrive(&full[t0]);
+                    ++ph;
                 }
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                tc_fence_before();
-                mbar_arrive(&full[t0]);
-                ++ph;
             }
-            compound(ph - 1u);
-            float2 x2 = make_float2(-1.0f, 0.0f);
+            mbar_wait(&done[t0], (ph - 1u) & 1u);
+            tc_fence_after();
+            compound();
+            float2 x2 = make_float2(a.x0, 0.0f);
 #pragma unroll
             for (int i = 0; i < NP / 2; ++i) x2 = fma2(make_float2(a.w[2 * i], a.w[2 * i + 1]), V[i], x2);
             const float x = x2.x + x2.y;
@@ -479,24 +488,28 @@ __global__ void __launch_bounds__(WG* PTC_ROWS + 32 * WG, 1) path_kernel_tc_wide
         // MMA issue warp of tile t = warp - GEN_WARPS: R = z Lhi (overwrites) + zlo Lhi + z Llo + [1 1 1 0 ..] drift, K = 8 per tcgen05.mma
         const int t = warp - GEN_WARPS;
         const uint32_t idesc = tc_idesc(2u, (uint32_t)NP);
-        const uint64_t bhi0 = tc_sdesc(smem_u32(sHi), Cfg::LBO, Cfg::SBO), blo0 = tc_sdesc(smem_u32(sLo), Cfg::LBO, Cfg::SBO);
         const uint32_t base = tmem + Cfg::TILE_COLS * (uint32_t)t;
         uint32_t ph = 0;
         for (uint64_t tile = (uint64_t)blockIdx.x * TILES + (uint64_t)t; tile < n_tiles; tile += slots) {
-            for (uint32_t s = 0; s < S; ++s, ++ph) {
-                mbar_wait_idle(&full[t], ph & 1u);
-                tc_fence_after();
+            for (uint32_t s = 0; s < S; ++s) {
+                for (int r = 0; r < KR; ++r, ++ph) {
+                    const uint32_t img = smem_u32(smem) + (uint32_t)r * IMG_BYTES;
+                    const uint64_t bhi0 = tc_sdesc(img, Cfg::LBO, Cfg::SBO), blo0 = tc_sdesc(img + Cfg::HI_BYTES, Cfg::LBO, Cfg::SBO);
+                    mbar_wait_idle(&full[t], ph & 1u);
+                    tc_fence_after();
 #pragma unroll 1
-                for (uint32_t k = 0; k < (uint32_t)(NP / 8); ++k)
-                    mma_tf32_ts_elect(base + Cfg::COL_D, base + Cfg::COL_Z + 8u * k, bhi0 + (uint64_t)(k * Cfg::DESC_STEP), idesc, k > 0 ? 1u : 0u);
+                    for (uint32_t k = 0; k < (uint32_t)(NP / 8); ++k)      // round 0 overwrites the accumulator, later rounds add to it
+                        mma_tf32_ts_elect(base + Cfg::COL_D, base + Cfg::COL_Z + 8u * k, bhi0 + (uint64_t)(k * Cfg::DESC_STEP), idesc, (k > 0 || r > 0) ? 1u : 0u);
 #pragma unroll 1
-                for (uint32_t k = 0; k < (uint32_t)(NP / 8); ++k)
-                    mma_tf32_ts_elect(base + Cfg::COL_D, base + Cfg::COL_ZLO + 8u * k, bhi0 + (uint64_t)(k * Cfg::DESC_STEP), idesc, 1u);
+                    for (uint32_t k = 0; k < (uint32_t)(NP / 8); ++k)
+                        mma_tf32_ts_elect(base + Cfg::COL_D, base + Cfg::COL_ZLO + 8u * k, bhi0 + (uint64_t)(k * Cfg::DESC_STEP), idesc, 1u);
 #pragma unroll 1
-                for (uint32_t k = 0; k < (uint32_t)(NP / 8); ++k)
-                    mma_tf32_ts_elect(base + Cfg::COL_D, base + Cfg::COL_Z + 8u * k, blo0 + (uint64_t)(k * Cfg::DESC_STEP), idesc, 1u);
-                mma_tf32_ts_elect(base + Cfg::COL_D, base + Cfg::COL_ONE, bhi0 + (uint64_t)((NP / 8) * Cfg::DESC_STEP), idesc, 1u);
-                tc_commit_elect(&done[t]);
+                    for (uint32_t k = 0; k < (uint32_t)(NP / 8); ++k)
+                        mma_tf32_ts_elect(base + Cfg::COL_D, base + Cfg::COL_Z + 8u * k, blo0 + (uint64_t)(k * Cfg::DESC_STEP), idesc, 1u);
+                    if (r == 0)                                            // the drift rows ride in round 0's image
+                        mma_tf32_ts_elect(base + Cfg::COL_D, base + Cfg::COL_ONE, bhi0 + (uint64_t)((NP / 8) * Cfg::DESC_STEP), idesc, 1u);
+                    tc_commit_elect(&done[t]);
+                }
             }
         }
     }
@@ -527,7 +540,7 @@ static inline float ptc_tf32_round(float x) {          // round-to-nearest-even 
 bool path_tc_eligible(const PathJob& job) {
     const char* v = getenv("MCP_PATHS_TC");               // "0" forces the SIMT kernels (A/B tests, benchmarks)
     if (v && v[0] == '0') return false;
-    return job.dtype == MCP_F32 && job.z_in == nullptr && job.n <= 128;
+    return job.dtype == MCP_F32 && job.z_in == nullptr && job.n <= 256;
 }
 
 static int ptc_env(const char* name, int lo, int hi) {   // tuning knobs: 0 = default
@@ -557,7 +570,10 @@ template <int NP, int WG, int ROUNDS>
 static int ptc_launch_wide_t(mcp_context* h, PathJob& job, const PtcArgs<NP>& a) {
     using Cfg = PtcCfg<NP, 1>;
     auto kern = path_kernel_tc_wide<NP, WG, ROUNDS>;
-    const size_t smem = Cfg::HI_BYTES + Cfg::LO_BYTES + (2 * PTC_MAX_TILES + 2) * sizeof(uint64_t) + (job.hist0 ? sizeof(unsigned int) << MCP_SEL_BITS : 0) + 128;
+    const size_t smem = (size_t)a.k_rounds * (Cfg::HI_BYTES + Cfg::LO_BYTES) + (2 * PTC_MAX_TILES + 2) * sizeof(uint64_t) +
+                        (a.hist0 ? sizeof(unsigned int) << MCP_SEL_BITS : 0) + 128;
+    if (smem > h->prop.sharedMemPerBlockOptin)
+        return mcp_fail(h, MCP_ERR_INVALID, "path_kernel_tc_wide: %d K rounds need %zu B of shared memory (max %zu)", a.k_rounds, smem, (size_t)h->prop.sharedMemPerBlockOptin);
     MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t n_tiles = (job.M + PTC_ROWS - 1) / PTC_ROWS;
     uint64_t grid = std::min<uint64_t>((uint64_t)h->prop.multiProcessorCount, (n_tiles + WG - 1) / WG);
@@ -610,7 +626,8 @@ static int ptc_launch(mcp_context* h, PathJob& job) {
     a.first = job.first;
     a.M = job.M;
     a.n_steps = job.n_steps;
-    a.ablate = ptc_env("MCP_PATHS_TC_ABLATE", 1, 1);
+    a.k_rounds = 1;
+    a.x0 = -1.0f;
     philox_keys_fill(a.rk, job.seed);
     job.hist0_filled = job.hist0 != nullptr;
     static const int wg_env = ptc_env("MCP_PATHS_TC_WG", 1, PTC_MAX_TILES), ppt_env = ptc_env("MCP_PATHS_TC_PPT", 1, 2),
@@ -668,10 +685,93 @@ static int ptc_launch(mcp_context* h, PathJob& job) {
     }
 }
 
+// terminal[m] = sum_b partial[b][m] - 1, blocks added in ascending order (deterministic)
+__global__ void __launch_bounds__(256) ptc_combine_blocks(const float* __restrict__ partial, int n_blocks, uint64_t M, float* __restrict__ terminal) {
+    for (uint64_t m = (uint64_t)blockIdx.x * 256 + threadIdx.x; m < M; m += (uint64_t)gridDim.x * 256) {
+        float x = -1.0f;
+        for (int b = 0; b < n_blocks; ++b) x += partial[(size_t)b * M + m];
+        terminal[m] = x;
+    }
+}
+
+// 128 < N <= 256: the universe is cut into blocks of 64 assets.  L is lower triangular, so block b (assets 64 b .. 64 b + 63) only
+// reaches the normals 0 .. 64 (b + 1) - 1: one launch of the N = 64 kernel per block, with b + 1 K rounds of 64 normals each
+// accumulating in the tile's tensor-memory accumulator (b + 1 image pairs of B in shared memory: 139 KB for the last block of a
+// 256-asset universe).  A launch compounds its 64 assets and writes the block's part of w . V_T; a small kernel adds the parts.
+// The normals of the earlier blocks are drawn again by the later ones (the Philox counter makes them the same numbers): 2.5x the
+// draws of a single pass at N = 256 -- still an order of magnitude above the SIMT warp-per-path kernel, whose N^2 FMAs per step it
+// moves to the tensor cores.  (A thread cannot own more assets: V is one register per asset.)
+static int ptc_launch_blocks(mcp_context* h, PathJob& job) {
+    using Cfg = PtcCfg<64, 1>;
+    constexpr size_t IMG = Cfg::HI_BYTES + Cfg::LO_BYTES;
+    const int n = job.n, B = (n + 63) / 64;
+    const std::vector<double>& L = *job.L;
+    const double sdt = std::sqrt(job.dt), c = std::sqrt(2.0 * std::log(2.0));
+    std::vector<size_t> off(B + 1, 0);
+    for (int b = 0; b < B; ++b) off[b + 1] = off[b] + (size_t)(b + 1) * IMG;
+    std::vector<unsigned char> host(off[B], 0);
+    auto at = [&](size_t image, int i, int kc) -> float* {
+        return reinterpret_cast<float*>(host.data() + image + ((size_t)(kc / 4) * (64 / 8) + i / 8) * 128 + (i % 8) * 16 + (kc % 4) * 4);
+    };
+    for (int b = 0; b < B; ++b) {
+        for (int r = 0; r <= b; ++r) {
+            const size_t img = off[b] + (size_t)r * IMG;
+            for (int i = 0; i < 64; ++i) {
+                const int gi = 64 * b + i;
+                if (gi >= n) continue;
+                for (int kc = 0; kc < 64; ++kc) {
+                    const int j = 64 * r + ptc_normal_of_col(kc);
+                    if (j > gi || j >= n) continue;
+                    const double v = L[(size_t)gi * n + j] * sdt * c;
+                    const float hi = ptc_tf32_round((float)v);
+                    *at(img, i, kc) = hi;
+                    *at(img + Cfg::HI_BYTES, i, kc) = ptc_tf32_round((float)(v - (double)hi));
+                }
+                if (r == 0) {
+                    const double dr = job.mu[gi] * job.dt;
+                    const float d0 = ptc_tf32_round((float)dr), d1 = ptc_tf32_round((float)(dr - (double)d0));
+                    const float d2 = ptc_tf32_round((float)(dr - (double)d0 - (double)d1));
+                    *at(img, i, 64) = d0;
+                    *at(img, i, 65) = d1;
+                    *at(img, i, 66) = d2;
+                }
+            }
+        }
+    }
+    unsigned char* dev = nullptr;
+    MCP_CHECK(mcp_dev_reserve(h, 6, host.size(), (void**)&dev));
+    ++h->const_epoch;
+    MCP_CUDA(h, cudaMemcpyAsync(dev, host.data(), host.size(), cudaMemcpyHostToDevice, job.stream));
+    MCP_CUDA(h, cudaStreamSynchronize(job.stream));        // `host` is pageable and dies at scope exit
+    float* partial = nullptr;
+    MCP_CHECK(mcp_dev_reserve(h, 23, (size_t)B * job.M * sizeof(float), (void**)&partial));
+    for (int b = 0; b < B; ++b) {
+        PtcArgs<64> a;
+        a.table = dev + off[b];
+        for (int i = 0; i < 64; ++i) a.w[i] = 64 * b + i < n ? (float)job.w[64 * b + i] : 0.f;
+        a.terminal = partial + (size_t)b * job.M;
+        a.hist0 = nullptr;
+        a.first = job.first;
+        a.M = job.M;
+        a.n_steps = job.n_steps;
+        a.k_rounds = b + 1;
+        a.x0 = 0.0f;
+        philox_keys_fill(a.rk, job.seed);
+        MCP_CHECK(job.rounds == 7 ? (ptc_launch_wide_t<64, 2, 7>(h, job, a)) : (ptc_launch_wide_t<64, 2, 10>(h, job, a)));
+    }
+    const unsigned blocks = (unsigned)std::min<uint64_t>((job.M + 255) / 256, (uint64_t)h->prop.multiProcessorCount * 8);
+    ptc_combine_blocks<<<blocks, 256, 0, job.stream>>>(partial, B, job.M, (float*)job.terminal);
+    MCP_CUDA(h, cudaGetLastError());
+    h->launches++;
+    job.hist0_filled = false;              // the terminal values exist only after the combination: the select starts at pass 0
+    return MCP_OK;
+}
+
 int path_launch_tc(mcp_context* h, PathJob& job) {
     if (job.n <= 16) return ptc_launch<16>(h, job);
     if (job.n <= 32) return ptc_launch<32>(h, job);
-    return job.n <= 64 ? ptc_launch<64>(h, job) : ptc_launch<128>(h, job);
+    if (job.n <= 64) return ptc_launch<64>(h, job);
+    return job.n <= 128 ? ptc_launch<128>(h, job) : ptc_launch_blocks(h, job);
 }
 
 }  // namespace mcp

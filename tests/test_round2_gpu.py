@@ -421,9 +421,10 @@ def test_bounded_tensor_core_sweep_sharding_and_host_pipeline(mcp):
     assert simt.n_accepted == whole.n_accepted
 
 
-# ---- tcgen05 path kernel for 32 < N <= 128 (normals drawn and stored 16 at a time) --------------------------------------------
+# ---- tcgen05 path kernel for 32 < N <= 128 (normals drawn and stored 16 at a time) and, in blocks of 64 assets, up to 256 -----
 
-@pytest.mark.parametrize("n,steps,M", [(33, 9, 300), (64, 30, 700), (100, 12, 1000), (128, 20, 500), (70, 252, 260)])
+@pytest.mark.parametrize("n,steps,M", [(33, 9, 300), (64, 30, 700), (100, 12, 1000), (128, 20, 500), (70, 252, 260),
+                                       (129, 8, 300), (200, 15, 400), (256, 20, 300), (192, 252, 140)])
 def test_wide_tc_paths_match_the_generator_restatement_and_the_simt_kernel(mcp, n, steps, M):
     mu, sigma = synthetic_inputs(n, seed=6)
     w = np.random.default_rng(n).dirichlet(np.ones(n))
@@ -440,8 +441,9 @@ def test_wide_tc_paths_match_the_generator_restatement_and_the_simt_kernel(mcp, 
     for alpha, (v, c) in a["stats"].items():                                  # the kernel-filled first histogram feeds the exact select
         assert v == ref.var(x, alpha) and np.isclose(c, ref.cvar(x, alpha), rtol=1e-12)
     # shards of the same seed reproduce the same paths bit for bit; 7 rounds is another stream
-    part = mcp.simulate_paths(mu, sigma, w, 130, steps, seed=seed, first_index=first + 129, return_terminal=True)["terminal"]
-    assert np.array_equal(part, a["terminal"][129:259])
+    k = min(130, M - 129)
+    part = mcp.simulate_paths(mu, sigma, w, k, steps, seed=seed, first_index=first + 129, return_terminal=True)["terminal"]
+    assert np.array_equal(part, a["terminal"][129:129 + k])
     if steps <= 30:
         Z7 = philox_np.normals(first, 200, steps, n, seed, "float32", rounds=7)
         p7 = mcp.simulate_paths(mu, sigma, w, 200, steps, seed=seed, first_index=first, return_terminal=True, philox_rounds=7)

@@ -10,7 +10,7 @@ import mcportfolio as mcp
 from bench import synthetic_inputs
 
 for n, M, tc in ((16, 4_000_000, "1"), (32, 2_000_000, "1"), (64, 1_000_000, "1"), (64, 200_000, "0"), (128, 400_000, "1"), (128, 100_000, "0"),
-                 (256, 100_000, "1")):
+                 (192, 400_000, "1"), (256, 400_000, "1"), (256, 100_000, "0")):
     os.environ["MCP_PATHS_TC"] = tc
     mu, sigma = synthetic_inputs(n)
     w = np.full(n, 1 / n)
