@@ -462,8 +462,8 @@ def run_ours(args):
     tc_paths = os.environ.get("MCP_PATHS_TC", "1") != "0"
     paths_ncu = ncu_figures("path_kernel_tc<16, 4, 1, 1, 10>" if tc_paths else "path_kernel_packed<16, 10>") or ncu_figures("path_kernel_packed<16>")
     paths_roofline = {"bound": "fp32-simt",
-                      "kernel": ("path_kernel_tc<16> (Philox + Box-Muller on SIMT warps, L.z on tcgen05: FP16-split normals from TMEM x L' images in "
-                                 "shared memory, FP32 accumulate; histogram of the terminal values in the epilogue)") if tc_paths else
+                      "kernel": ("path_kernel_tc<16> (Philox + Box-Muller on SIMT warps, L.z + drift on tcgen05: TF32-split normals z, z - trunc(z) from "
+                                 "TMEM x Lhi / Llo images in shared memory, FP32 accumulate; first radix histogram of the terminal values in the epilogue)") if tc_paths else
                                 "path_kernel_packed<16> (Philox, FFMA2)",
                       "achieved": p_achieved, "peak": fma_peak,
                       "unit": "TFLOP/s", "frac": p_achieved / fma_peak, "traffic": paths_ncu["dram_bytes"] if paths_ncu else None,
