@@ -169,10 +169,11 @@ typedef struct {
 } mcp_path_params;
 
 /* Kernel selection (internal): FP32 Philox paths with N <= 256 run on the tensor cores (tcgen05: the step's normals go to
- * tensor memory as the A operand, L' sqrt(dt) is the B operand in shared memory, TF32 operand split with FP32
- * accumulation; for N > 32 the normals are drawn and stored 16 at a time, for N > 128 the universe is worked off in blocks
- * of 64 assets; MCP_PATHS_TC=0 forces the SIMT kernels for A/B measurements); supplied normals, FP64 and wider universes
- * use the thread-per-path register kernels (N <= 32) or the warp-per-path kernel (N <= 1024).                          */
+ * tensor memory as the A operand, L' sqrt(dt) is the B operand in shared memory, split operands with FP32 accumulation:
+ * TF32 for N <= 32; for N > 32 two stages of FP16 pairs, the normals drawn and stored 16 at a time, and for N > 128 two
+ * blocks of 128 assets; MCP_PATHS_TC=0 forces the SIMT kernels, MCP_PATHS_TC_WIDE16=0 the one-stage TF32 kernel above
+ * N = 32, for A/B measurements); supplied normals, FP64 and wider universes use the thread-per-path register kernels
+ * (N <= 32) or the warp-per-path kernel (N <= 1024).                                                                   */
 int mcp_paths(mcp_handle h, const mcp_path_params* params,
               const double* mu_host, const double* sigma_host, const double* weights_host,
               void* terminal_out, double* kernel_ms);

@@ -41,6 +41,7 @@ def translation_units():
            ("mcp_recheck", "mcp_recheck.cu", []),
            ("mcp_paths", "mcp_paths.cu", []),
            ("mcp_paths_tc", "mcp_paths_tc.cu", []),
+           ("mcp_paths_tc16", "mcp_paths_tc16.cu", []),
            ("mcp_quantile", "mcp_quantile.cu", []),
            ("mcp_historical", "mcp_historical.cu", []),
            ("mcp_stats", "mcp_stats.cu", [])]

@@ -24,6 +24,9 @@ struct PathJob {
 // tcgen05 path kernel (mcp_paths_tc.cu): FP32, Philox normals, N <= 32
 bool path_tc_eligible(const PathJob& job);
 int path_launch_tc(mcp_context* h, PathJob& job);
+// two-stage tcgen05 kernel with 16-bit split operands for 32 < N <= 256 (mcp_paths_tc16.cu); MCP_PATHS_TC_WIDE16=0 disables it
+bool path_tc16_enabled();
+int path_launch_tc16(mcp_context* h, PathJob& job);
 
 // warp-per-path kernel for wide universes (mcp_paths.cu): 32 < N <= PATH_WIDE_MAX_N, FP32 / FP64, Philox or supplied normals
 constexpr int PATH_WIDE_MAX_N = 1024;

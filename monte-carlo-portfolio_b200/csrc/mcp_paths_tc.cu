@@ -770,6 +770,7 @@ static int ptc_launch_blocks(mcp_context* h, PathJob& job) {
 int path_launch_tc(mcp_context* h, PathJob& job) {
     if (job.n <= 16) return ptc_launch<16>(h, job);
     if (job.n <= 32) return ptc_launch<32>(h, job);
+    if (path_tc16_enabled()) return path_launch_tc16(h, job);
     if (job.n <= 64) return ptc_launch<64>(h, job);
     return job.n <= 128 ? ptc_launch<128>(h, job) : ptc_launch_blocks(h, job);
 }

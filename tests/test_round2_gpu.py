@@ -437,6 +437,9 @@ def test_wide_tc_paths_match_the_generator_restatement_and_the_simt_kernel(mcp, 
     assert np.allclose(a["terminal"] + 1.0, want + 1.0, rtol=1e-4)            # north star, FP32
     assert np.allclose(b["terminal"] + 1.0, want + 1.0, rtol=1e-4)
     assert np.allclose(a["terminal"] + 1.0, b["terminal"] + 1.0, rtol=3e-5)
+    with _env(MCP_PATHS_TC_WIDE16="0"):                                       # the one-stage TF32-split kernel: a third witness
+        t32 = mcp.simulate_paths(mu, sigma, w, M, steps, seed=seed, first_index=first, return_terminal=True)
+    assert np.allclose(t32["terminal"] + 1.0, want + 1.0, rtol=1e-4) and np.allclose(a["terminal"] + 1.0, t32["terminal"] + 1.0, rtol=3e-5)
     x = a["terminal"].astype(np.float64)
     for alpha, (v, c) in a["stats"].items():                                  # the kernel-filled first histogram feeds the exact select
         assert v == ref.var(x, alpha) and np.isclose(c, ref.cvar(x, alpha), rtol=1e-12)

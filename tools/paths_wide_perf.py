@@ -9,9 +9,11 @@ import numpy as np
 import mcportfolio as mcp
 from bench import synthetic_inputs
 
-for n, M, tc in ((16, 4_000_000, "1"), (32, 2_000_000, "1"), (64, 1_000_000, "1"), (64, 200_000, "0"), (128, 400_000, "1"), (128, 100_000, "0"),
-                 (192, 400_000, "1"), (256, 400_000, "1"), (256, 100_000, "0")):
-    os.environ["MCP_PATHS_TC"] = tc
+for n, M, tc in ((16, 4_000_000, "1"), (32, 2_000_000, "1"), (64, 1_000_000, "1"), (64, 1_000_000, "32"), (64, 200_000, "0"),
+                 (128, 400_000, "1"), (128, 400_000, "32"), (128, 100_000, "0"), (192, 400_000, "1"), (192, 400_000, "32"),
+                 (256, 400_000, "1"), (256, 400_000, "32"), (256, 100_000, "0")):
+    os.environ["MCP_PATHS_TC"] = "0" if tc == "0" else "1"                  # tc: 1 = tcgen05 (16-bit split, two stages above N = 32),
+    os.environ["MCP_PATHS_TC_WIDE16"] = "0" if tc == "32" else "1"          # 32 = the one-stage TF32-split wide kernel, 0 = SIMT
     mu, sigma = synthetic_inputs(n)
     w = np.full(n, 1 / n)
     for _ in range(2):

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "monte-carlo-portfolio_b200", "lib", "libmcp.so")
 OPS = ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "ELECT", "SYNCS", "FFMA2", "FFMA", "IMAD.WIDE", "LOP3", "MUFU", "FMNMX3", "REDUX", "DFMA")
 WANT = ("small_sweep_packedILi16ELi4ELb0ELi10", "small_sweep_packedILi16ELi4ELb0ELi7", "small_sweepIdLi16ELi2ELi0ELb0ELi10", "large_sweep_tcILb1ELi10ELb0", "large_sweep_tcILb1ELi10ELb1",
-        "large_sweep_tcILb0ELi10ELb0", "path_kernel_tcILi16ELi4ELi1ELi1ELi10", "path_kernel_tcILi16ELi4ELi1ELi1ELi7", "path_kernel_tcILi32ELi3ELi1ELi1ELi10", "path_kernel_tc_wideILi64ELi2ELi10", "path_kernel_tc_wideILi128ELi1ELi10",
+        "large_sweep_tcILb0ELi10ELb0", "path_kernel_tcILi16ELi4ELi1ELi1ELi10", "path_kernel_tcILi16ELi4ELi1ELi1ELi7", "path_kernel_tcILi32ELi3ELi1ELi1ELi10", "path_kernel_tc_wideILi64ELi2ELi10", "path_kernel_tc_wideILi128ELi1ELi10", "path_kernel_tc16ILi64ELi2ELi10", "path_kernel_tc16ILi128ELi4ELi10",
         "hist_var_fastILi12", "path_kernel_packedILi16ELi10", "large_sweepILi10", "path_kernel_wideIfLi", "moments_cov")
 
 
