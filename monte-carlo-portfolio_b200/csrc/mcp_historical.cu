@@ -100,10 +100,14 @@ __global__ void __launch_bounds__(HV_BLOCK) hist_var_kernel(const HistArgs<T> a)
             const bool valid = lane + 32 * v < a.T_;
             key[v] = valid ? HKey<T>::to_key(x[v]) : ~(K)0;      // padding sorts last
         }
-        T v_lo, v_hi;
+        T var, cvar;
         if (a.k_hi < HV_EXTRACT_MAX) {
             // ---- lower-tail ranks (the reference's alpha = 0.95: k = 18 of T = 365): sort each lane's
-            // values once, then pop the warp-wide minimum k_hi + 1 times (5 shuffles + a register shift each)
+            // values once, then pop the warp-wide minimum k_lo + 1 times (5 shuffles + a register shift each).
+            // The tail mean comes out of the same pops: the set {x <= VaR} is exactly what has been popped when the
+            // next minimum exceeds VaR (the loop below pops on while it does not: ties at the rank, gamma = 0).  Each
+            // lane adds ITS popped values in ascending order, the lanes' sums meet in the butterfly -- hist_var_fast
+            // reaches the same set by another route and adds in the same order (bit-identical results).
             K y[VPL];
 #pragma unroll
             for (int v = 0; v < VPL; ++v) y[v] = key[v];
@@ -115,23 +119,34 @@ __global__ void __launch_bounds__(HV_BLOCK) hist_var_kernel(const HistArgs<T> a)
                     y[v] = lo; y[v + 1] = hi;
                 }
             }
-            K k_at_lo = 0, k_at_hi = 0;
-#pragma unroll 1
-            for (int r = 0; r <= a.k_hi; ++r) {
+            T acc = (T)0;
+            auto warp_min_key = [&]() {
                 K m = y[0];
 #pragma unroll
                 for (int d = 16; d >= 1; d >>= 1) { const K o = shfl_xor_key<K>(m, d); m = o < m ? o : m; }
-                if (r == a.k_lo) k_at_lo = m;
-                k_at_hi = m;
+                return m;
+            };
+            auto pop = [&](K m) {                                // the lowest lane holding m gives it up
                 const unsigned owners = __ballot_sync(0xffffffffu, y[0] == m);
                 if (lane == __ffs(owners) - 1) {
+                    acc += HKey<T>::from_key(m);
 #pragma unroll
                     for (int v = 0; v + 1 < VPL; ++v) y[v] = y[v + 1];
                     y[VPL - 1] = ~(K)0;
                 }
-            }
-            v_lo = HKey<T>::from_key(k_at_lo);
-            v_hi = HKey<T>::from_key(k_at_hi);
+            };
+            K k_at_lo = 0;
+#pragma unroll 1
+            for (int r = 0; r <= a.k_lo; ++r) { k_at_lo = warp_min_key(); pop(k_at_lo); }
+            K peek = warp_min_key();
+            const T v_lo = HKey<T>::from_key(k_at_lo), v_hi = a.k_hi > a.k_lo ? HKey<T>::from_key(peek) : v_lo;
+            const T diff = v_hi - v_lo;                          // numpy _lerp
+            var = v_lo + diff * a.gamma;
+            if (a.gamma >= (T)0.5) var = v_hi - diff * ((T)1 - a.gamma);
+            int total = a.k_lo + 1;
+#pragma unroll 1
+            while (total < a.T_ && HKey<T>::from_key(peek) <= var) { pop(peek); ++total; peek = warp_min_key(); }
+            cvar = warp_sum<T>(acc) / (T)total;
         } else {
             // ---- any rank: MSB-first radix select, count keys with the candidate prefix and bit 0 ----
             K prefix = 0;
@@ -145,7 +160,7 @@ __global__ void __launch_bounds__(HV_BLOCK) hist_var_kernel(const HistArgs<T> a)
                 c = __reduce_add_sync(0xffffffffu, c);
                 if (rank >= c) { rank -= c; prefix |= (K)1 << b; }
             }
-            v_lo = HKey<T>::from_key(prefix);
+            const T v_lo = HKey<T>::from_key(prefix);
             // (k_lo+1)-th: v_lo again if it is repeated far enough, else the smallest value above it
             int le = 0;
             T above = Math<T>::inf();
@@ -157,24 +172,23 @@ __global__ void __launch_bounds__(HV_BLOCK) hist_var_kernel(const HistArgs<T> a)
             }
             le = __reduce_add_sync(0xffffffffu, le);
             above = warp_min<T>(above);
-            v_hi = (a.k_hi == a.k_lo || le >= a.k_hi + 1) ? v_lo : above;
-        }
-        // numpy _lerp
-        const T diff = v_hi - v_lo;
-        T var = v_lo + diff * a.gamma;
-        if (a.gamma >= (T)0.5) var = v_hi - diff * ((T)1 - a.gamma);
-        // ---- CVaR = mean(x[x <= VaR]) (VaR if empty), app.py:261-263 ----
-        T s = (T)0;
-        int cnt = 0;
+            const T v_hi = (a.k_hi == a.k_lo || le >= a.k_hi + 1) ? v_lo : above;
+            const T diff = v_hi - v_lo;                          // numpy _lerp
+            var = v_lo + diff * a.gamma;
+            if (a.gamma >= (T)0.5) var = v_hi - diff * ((T)1 - a.gamma);
+            // ---- CVaR = mean(x[x <= VaR]) (VaR if empty), app.py:261-263 ----
+            T s = (T)0;
+            int cnt = 0;
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-            const bool in = (lane + 32 * v < a.T_) && x[v] <= var;
-            s += in ? x[v] : (T)0;
-            cnt += in ? 1 : 0;
+            for (int v = 0; v < VPL; ++v) {
+                const bool in = (lane + 32 * v < a.T_) && x[v] <= var;
+                s += in ? x[v] : (T)0;
+                cnt += in ? 1 : 0;
+            }
+            s = warp_sum<T>(s);
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            cvar = cnt > 0 ? s / (T)cnt : var;
         }
-        s = warp_sum<T>(s);
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        const T cvar = cnt > 0 ? s / (T)cnt : var;
         if (lane == 0) {
             if (a.var_out) a.var_out[p] = a.out_sign * var;
             if (a.cvar_out) a.cvar_out[p] = a.out_sign * cvar;
@@ -200,18 +214,37 @@ __global__ void __launch_bounds__(HV_BLOCK) hist_var_kernel(const HistArgs<T> a)
 // ---------------------------------------------------------------------------------------------
 // FP32 fast path for lower-tail ranks (the reference's alpha = 0.95 on T <= 512 periods): a warp works on
 // FOUR consecutive portfolios at once.
-//   * series: every R element read from shared memory feeds four portfolios (two packed FFMA2), so the
-//     LDS count per portfolio drops 4x; the FMA order per (period, portfolio) is the plain kernel's.
-//   * selection: each lane sorts its VPL keys with a sorting network (39 compare-exchanges for 12), parks
-//     positions 1.. in shared memory and keeps only the head in a register; k+1 rounds of
-//     REDUX.UMIN (one instruction for the warp-wide minimum) + ballot pop the order statistics; the
-//     owning lane advances its head with one LDS.  The four portfolios' chains interleave (ILP 4).
-// Results are bit-identical to hist_var_kernel<float, VPL> (tests compare the two).
+//   * series: lane l owns the periods l, l + 32, ... as in the plain kernel.  R sits in shared memory as PAIRS of a lane's
+//     consecutive periods (one LDS.64 = two periods), the weights as (w, w) pairs (one broadcast LDS.128 = two portfolios),
+//     so a packed FFMA2 advances two periods of one portfolio: per asset 6 + 2 loads feed 24 FFMA2 (VPL = 12), no
+//     register moves; the FMA order per (period, portfolio) is the plain kernel's.
+//   * selection, on the FP32 values themselves (FMNMX, CREDUX.MIN/MAX.F32 -- no integer keys): each lane sorts its VPL
+//     values with a sorting network and parks them in shared memory.  With tau = the warp-wide minimum of the lanes'
+//     (ROW+1)-th smallest values, everything <= tau in the lanes' first ROW positions is a set S of the |S| smallest values
+//     of the series (nothing outside S is below tau), found with ONE reduction; for ROW = 2 and 32 lanes |S| is 16 +- 4,
+//     next to the 19 values the reference's alpha = 0.95 needs at T = 365.  From there |k_lo + 1 - |S|| single steps
+//     finish: warp-min pops from below when S is too small, warp-max removals from S when it is too big (one CREDUX +
+//     ballot each; the owning lane moves to its next parked value).  ROW is chosen from k_lo on the host (0: pops only).
+//   * tail mean: the set {x <= VaR} is what has been taken when the next minimum exceeds VaR (else the pops go on: ties);
+//     each lane adds ITS taken values in ascending order and the lanes' sums meet in the butterfly, as in the plain kernel.
+// VaR / CVaR are bit-identical to hist_var_kernel<float, VPL> up to the sign of a zero (tests compare the two).
 // ---------------------------------------------------------------------------------------------
 constexpr int HF_PPW = 4;
+constexpr int HF_PAD = 2;                 // sentinels on either side of a lane's parked values
 
-template <int VPL> __device__ __forceinline__ void lane_sort(uint32_t (&y)[VPL]) {
-#define MCP_CE(i, j) { const uint32_t lo_ = min(y[i], y[j]), hi_ = max(y[i], y[j]); y[i] = lo_; y[j] = hi_; }
+__device__ __forceinline__ float redux_min_f32(float v) {
+    float m;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+    return m;
+}
+__device__ __forceinline__ float redux_max_f32(float v) {
+    float m;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+    return m;
+}
+
+template <int VPL> __device__ __forceinline__ void lane_sort(float (&y)[VPL]) {
+#define MCP_CE(i, j) { const float lo_ = fminf(y[i], y[j]), hi_ = fmaxf(y[i], y[j]); y[i] = lo_; y[j] = hi_; }
     if constexpr (VPL == 12) {          // 39-comparator network (verified with the 0/1 principle)
         MCP_CE(0, 1) MCP_CE(2, 3) MCP_CE(4, 5) MCP_CE(6, 7) MCP_CE(8, 9) MCP_CE(10, 11)
         MCP_CE(1, 3) MCP_CE(5, 7) MCP_CE(9, 11) MCP_CE(0, 2) MCP_CE(4, 6) MCP_CE(8, 10)
@@ -232,134 +265,175 @@ template <int VPL> __device__ __forceinline__ void lane_sort(uint32_t (&y)[VPL])
 #undef MCP_CE
 }
 
-template <int VPL>
-__global__ void __launch_bounds__(HV_BLOCK) hist_var_fast(const HistArgs<float> a) {
+template <int VPL, int ROW>
+__global__ void __launch_bounds__(HV_BLOCK, 2) hist_var_fast(const HistArgs<float> a) {
+    static_assert(VPL % 2 == 0 && ROW < VPL, "period pairs");
+    constexpr int VP2 = VPL / 2, KSTRIDE = VPL + 2 * HF_PAD;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* sR = reinterpret_cast<float*>(smem_raw);                                 // [n][t_pad], t_pad = 32 VPL
-    float* sW = sR + (size_t)a.n * a.t_pad;                                         // [HV_WARPS][n][4]
-    uint32_t* sK = reinterpret_cast<uint32_t*>(sW + (size_t)HV_WARPS * a.n * HF_PPW);   // [HV_WARPS][4][VPL + 1][32], last = sentinel
-    for (int i = threadIdx.x; i < a.n * a.t_pad; i += HV_BLOCK) sR[i] = a.r_t[i];
-    __syncthreads();
+    float* sR = reinterpret_cast<float*>(smem_raw);                                 // [n][VP2][32][2], t_pad = 32 VPL
+    float* sW = sR + (size_t)a.n * a.t_pad;                                         // [HV_WARPS][n][4][2]
+    float* sK = sW + (size_t)HV_WARPS * a.n * HF_PPW * 2;                           // [HV_WARPS][KSTRIDE][32]
+    for (int d = threadIdx.x; d < a.n * a.t_pad; d += HV_BLOCK) {
+        const int i = d / a.t_pad, rem = d - i * a.t_pad, j = rem >> 6, l = (rem & 63) >> 1, half = rem & 1;
+        sR[d] = a.r_t[i * a.t_pad + l + 64 * j + 32 * half];
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* myW = sW + (size_t)warp * a.n * HF_PPW;
-    uint32_t* myK = sK + (size_t)warp * HF_PPW * (VPL + 1) * 32 + lane;
+    float* myW = sW + (size_t)warp * a.n * HF_PPW * 2;
+    float* myK = sK + (size_t)warp * KSTRIDE * 32 + lane;                           // entry e of this lane: myK[e * 32]
     unsigned lt_mask;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+    const float inf = Math<float>::inf();
 #pragma unroll
-    for (int pp = 0; pp < HF_PPW; ++pp) myK[(pp * (VPL + 1) + VPL) * 32] = 0xffffffffu;      // a lane that ran out of values never wins again
+    for (int e = 0; e < HF_PAD; ++e) { myK[e * 32] = -inf; myK[(HF_PAD + VPL + e) * 32] = inf; }
+    __syncthreads();
 
-    float best_v = -Math<float>::inf(), best_c = -Math<float>::inf();
+    float best_v = -inf, best_c = -inf;                     // lane pp < 4 follows portfolio pp of every group
     uint64_t idx_v = MCP_NO_INDEX, idx_c = MCP_NO_INDEX;
     const uint64_t groups = (a.P + HF_PPW - 1) / HF_PPW;
     const uint64_t warps_total = (uint64_t)gridDim.x * HV_WARPS;
+    const bool last_only = a.T_ > 32 * (VPL - 1);           // only a lane's last period can be padding
+    const bool last_valid = lane + 32 * (VPL - 1) < a.T_;
     // the four weight rows of a group are 4 n contiguous floats; with 4 n <= 64 (n <= 16) a lane holds the NEXT group's
     // values in two registers while the current group is being processed (the global-load latency sat in front of the STS)
     const bool prefetch = HF_PPW * a.n <= 64;
+    const int j0 = lane, j1 = lane + 32;
+    const int o0 = ((j0 % a.n) * HF_PPW + j0 / a.n) * 2, o1 = ((j1 % a.n) * HF_PPW + j1 / a.n) * 2;
     float nxt0 = 0.f, nxt1 = 0.f;
     auto fetch = [&](uint64_t g, int j) -> float {
         const uint64_t q0 = g * HF_PPW;
         return (g < groups && j < HF_PPW * a.n && q0 + (uint64_t)(j / a.n) < a.P) ? __ldg(a.w_in + q0 * (uint64_t)a.n + (uint64_t)j) : 0.f;
     };
     const uint64_t g_first = (uint64_t)blockIdx.x * HV_WARPS + warp;
-    if (prefetch) { nxt0 = fetch(g_first, lane); nxt1 = fetch(g_first, lane + 32); }
+    if (prefetch) { nxt0 = fetch(g_first, j0); nxt1 = fetch(g_first, j1); }
     for (uint64_t gq = g_first; gq < groups; gq += warps_total) {
         const uint64_t p0 = gq * HF_PPW;
         __syncwarp();
         if (prefetch) {
-            const int j0 = lane, j1 = lane + 32;
-            if (j0 < HF_PPW * a.n) myW[(j0 % a.n) * HF_PPW + j0 / a.n] = nxt0;
-            if (j1 < HF_PPW * a.n) myW[(j1 % a.n) * HF_PPW + j1 / a.n] = nxt1;
+            if (j0 < HF_PPW * a.n) *reinterpret_cast<float2*>(myW + o0) = make_float2(nxt0, nxt0);
+            if (j1 < HF_PPW * a.n) *reinterpret_cast<float2*>(myW + o1) = make_float2(nxt1, nxt1);
             nxt0 = fetch(gq + warps_total, j0);
             nxt1 = fetch(gq + warps_total, j1);
         } else {
             for (int j = lane; j < HF_PPW * a.n; j += 32) {               // rows p0 .. p0+3 are contiguous: coalesced
                 const int pp = j / a.n, i = j - pp * a.n;
-                myW[i * HF_PPW + pp] = (p0 + (uint64_t)pp < a.P) ? a.w_in[p0 * (uint64_t)a.n + (uint64_t)j] : 0.f;
+                const float w = (p0 + (uint64_t)pp < a.P) ? a.w_in[p0 * (uint64_t)a.n + (uint64_t)j] : 0.f;
+                *reinterpret_cast<float2*>(myW + (i * HF_PPW + pp) * 2) = make_float2(w, w);
             }
         }
         __syncwarp();
-        // ---- series[t] = sum_i R[t, i] w_i: this lane's periods, four portfolios (a: 0,1  b: 2,3) ----
-        float2 xa[VPL], xb[VPL];
+        // ---- series[t] = sum_i R[t, i] w_i: this lane's periods in pairs (l + 64 j, l + 64 j + 32), four portfolios ----
+        float2 x[HF_PPW][VP2];
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) { xa[v] = make_float2(0.f, 0.f); xb[v] = make_float2(0.f, 0.f); }
+        for (int pp = 0; pp < HF_PPW; ++pp)
+#pragma unroll
+            for (int j = 0; j < VP2; ++j) x[pp][j] = make_float2(0.f, 0.f);
+#pragma unroll 2
         for (int i = 0; i < a.n; ++i) {
-            const float4 w4 = *reinterpret_cast<const float4*>(myW + i * HF_PPW);
-            const float2 wa = make_float2(w4.x, w4.y), wb = make_float2(w4.z, w4.w);
-            const float* row = sR + (size_t)i * a.t_pad + lane;
+            const float4 wa = *reinterpret_cast<const float4*>(myW + i * HF_PPW * 2);          // (w0, w0, w1, w1)
+            const float4 wb = *reinterpret_cast<const float4*>(myW + i * HF_PPW * 2 + 4);      // (w2, w2, w3, w3)
+            const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w), w2 = make_float2(wb.x, wb.y), w3 = make_float2(wb.z, wb.w);
+            const float2* row = reinterpret_cast<const float2*>(sR + (size_t)i * a.t_pad) + lane;
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-                const float2 r2 = bcast2(row[32 * v]);                  // padded columns are 0
-                xa[v] = fma2(r2, wa, xa[v]);
-                xb[v] = fma2(r2, wb, xb[v]);
+            for (int j = 0; j < VP2; ++j) {
+                const float2 r2 = row[32 * j];                          // padded periods are 0
+                x[0][j] = fma2(r2, w0, x[0][j]);
+                x[1][j] = fma2(r2, w1, x[1][j]);
+                x[2][j] = fma2(r2, w2, x[2][j]);
+                x[3][j] = fma2(r2, w3, x[3][j]);
             }
         }
-        // ---- per portfolio: sort the lane's keys, park positions 1.. in shared memory ----
-        uint32_t head[HF_PPW];
-        const uint32_t* next[HF_PPW];                     // this lane's next parked key of each portfolio
+        float var4[HF_PPW], cvar4[HF_PPW];
 #pragma unroll
         for (int pp = 0; pp < HF_PPW; ++pp) {
-            uint32_t y[VPL];
+            // ---- sort the lane's values (padding = +inf sorts last) and park them between the sentinels ----
+            float y[VPL];
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-                const float xv = pp == 0 ? xa[v].x : pp == 1 ? xa[v].y : pp == 2 ? xb[v].x : xb[v].y;
-                y[v] = (lane + 32 * v < a.T_) ? HKey<float>::to_key(xv) : 0xffffffffu;      // padding sorts last
+            for (int j = 0; j < VP2; ++j) { y[2 * j] = x[pp][j].x; y[2 * j + 1] = x[pp][j].y; }
+            if (last_only) {
+                y[VPL - 1] = last_valid ? y[VPL - 1] : inf;
+            } else {
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) y[v] = (lane + 32 * v < a.T_) ? y[v] : inf;
             }
             lane_sort<VPL>(y);
-            head[pp] = y[0];
-            next[pp] = myK + (pp * (VPL + 1) + 1) * 32;
 #pragma unroll
-            for (int v = 1; v < VPL; ++v) myK[(pp * (VPL + 1) + v) * 32] = y[v];
-        }
-        // ---- pop the warp-wide minimum k_hi + 1 times (four interleaved chains): REDUX.UMIN, ballot, and the lowest
-        // owning lane (no lower lane holds the minimum) advances to its next parked key with one LDS ----
-        uint32_t k_lo_key[HF_PPW], k_hi_key[HF_PPW];
-        auto pop = [&](uint32_t (&out)[HF_PPW]) {
+            for (int v = 0; v < VPL; ++v) myK[(HF_PAD + v) * 32] = y[v];
+            // ---- S = everything <= tau in the first ROW positions: the |S| smallest values of the series ----
+            int cnt = 0;                                    // how many of this lane's values have been taken
+            int c = 0;
+            if constexpr (ROW > 0) {
+                const float tau = redux_min_f32(y[ROW]);
 #pragma unroll
-            for (int pp = 0; pp < HF_PPW; ++pp) {
-                const uint32_t m = __reduce_min_sync(0xffffffffu, head[pp]);
-                out[pp] = m;
-                const unsigned owners = __ballot_sync(0xffffffffu, head[pp] == m);
-                const bool own = head[pp] == m && (owners & lt_mask) == 0u;
-                const uint32_t nxt = *next[pp];             // every lane reloads (branch-free); only the owner takes it
-                if (own) { head[pp] = nxt; next[pp] += 32; }
+                for (int v = 0; v < ROW; ++v) cnt += y[v] <= tau ? 1 : 0;       // a prefix: y ascends
+                c = __reduce_add_sync(0xffffffffu, cnt);
             }
-        };
+            float acc = 0.f, v_lo, h;
+            const float* nx;                                // the parked value after h
+            if (c <= a.k_lo) {
+                // pops from below: the lowest lane holding the minimum gives it up
+#pragma unroll
+                for (int v = 0; v < ROW; ++v) acc = v < cnt ? acc + y[v] : acc;
+                h = y[0];
+#pragma unroll
+                for (int v = 1; v <= ROW; ++v) h = cnt >= v ? y[v] : h;
+                nx = myK + (HF_PAD + 1 + cnt) * 32;
+                float nxt = *nx;
+                float m = 0.f;
 #pragma unroll 1
-        for (int r = 0; r <= a.k_lo; ++r) pop(k_lo_key);
+                for (int need = a.k_lo + 1 - c; need > 0; --need) {
+                    m = redux_min_f32(h);
+                    const unsigned owners = __ballot_sync(0xffffffffu, h == m);
+                    if (h == m && (owners & lt_mask) == 0u) { acc += h; h = nxt; nx += 32; nxt = *nx; }
+                }
+                v_lo = m;
+            } else {
+                // removals from above: S loses its largest values until k_lo + 1 are left
+                const float* pv = myK + (HF_PAD - 1 + cnt) * 32;      // top of this lane's part of S (-inf: none)
+                float top = *pv, prv = pv[-32];
+#pragma unroll 1
+                for (int rem = c - a.k_lo - 1; rem > 0; --rem) {
+                    const float M = redux_max_f32(top);
+                    const unsigned owners = __ballot_sync(0xffffffffu, top == M);
+                    if (top == M && (owners & lt_mask) == 0u) { --cnt; top = prv; pv -= 32; prv = pv[-32]; }
+                }
+                v_lo = redux_max_f32(top);
 #pragma unroll
-        for (int pp = 0; pp < HF_PPW; ++pp) k_hi_key[pp] = k_lo_key[pp];
-        if (a.k_hi > a.k_lo) pop(k_hi_key);
-        // ---- numpy _lerp, then CVaR = mean(x[x <= VaR]) (VaR if empty), app.py:261-263 ----
-#pragma unroll
-        for (int pp = 0; pp < HF_PPW; ++pp) {
-            const float v_lo = HKey<float>::from_key(k_lo_key[pp]), v_hi = HKey<float>::from_key(k_hi_key[pp]);
+                for (int v = 0; v < ROW; ++v) acc = v < cnt ? acc + y[v] : acc;
+                nx = pv + 32;
+                h = *nx;
+                nx += 32;
+            }
+            // ---- numpy _lerp, then CVaR = mean(x[x <= VaR]), app.py:261-263 ----
+            float peek = redux_min_f32(h);
+            const float v_hi = a.k_hi > a.k_lo ? peek : v_lo;
             const float diff = v_hi - v_lo;
             float var = v_lo + diff * a.gamma;
             if (a.gamma >= 0.5f) var = v_hi - diff * (1.f - a.gamma);
-            float s = 0.f;
-            int cnt = 0;
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-                const float xv = pp == 0 ? xa[v].x : pp == 1 ? xa[v].y : pp == 2 ? xb[v].x : xb[v].y;
-                const bool in = (lane + 32 * v < a.T_) && xv <= var;
-                s += in ? xv : 0.f;
-                cnt += in ? 1 : 0;
+            int total = a.k_lo + 1;
+#pragma unroll 1
+            while (total < a.T_ && peek <= var) {           // ties at the rank (or gamma = 0 / 1 with equal neighbours)
+                const unsigned owners = __ballot_sync(0xffffffffu, h == peek);
+                if (h == peek && (owners & lt_mask) == 0u) { acc += h; h = *nx; nx += 32; }
+                ++total;
+                peek = redux_min_f32(h);
             }
-            s = warp_sum<float>(s);
-            cnt = __reduce_add_sync(0xffffffffu, cnt);
-            const float cvar = cnt > 0 ? s / (float)cnt : var;
-            const uint64_t p = p0 + (uint64_t)pp;
-            if (p < a.P) {
-                if (lane == 0) {
-                    if (a.var_out) a.var_out[p] = a.out_sign * var;
-                    if (a.cvar_out) a.cvar_out[p] = a.out_sign * cvar;
-                }
-                const uint64_t g = a.first + p;
-                if (var > best_v) { best_v = var; idx_v = g; }          // p ascends per warp: first occurrence kept
-                if (cvar > best_c) { best_c = cvar; idx_c = g; }
-            }
+            var4[pp] = var;
+            cvar4[pp] = warp_sum<float>(acc) / (float)total;
+        }
+        // ---- lane pp writes and follows portfolio pp ----
+        const float my_var = lane == 0 ? var4[0] : lane == 1 ? var4[1] : lane == 2 ? var4[2] : var4[3];
+        const float my_cvar = lane == 0 ? cvar4[0] : lane == 1 ? cvar4[1] : lane == 2 ? cvar4[2] : cvar4[3];
+        const uint64_t p = p0 + (uint64_t)lane;
+        if (lane < HF_PPW && p < a.P) {
+            if (a.var_out) a.var_out[p] = a.out_sign * my_var;
+            if (a.cvar_out) a.cvar_out[p] = a.out_sign * my_cvar;
+            const uint64_t g = a.first + p;
+            if (my_var > best_v) { best_v = my_var; idx_v = g; }          // p ascends per lane: first occurrence kept
+            if (my_cvar > best_c) { best_c = my_cvar; idx_c = g; }
         }
     }
+    warp_argmax<float>(best_v, idx_v);                      // larger value, then lower index
+    warp_argmax<float>(best_c, idx_c);
     __shared__ PfCand wc[HV_WARPS];
     if (lane == 0) wc[warp] = PfCand{(double)best_v, idx_v, (double)best_c, idx_c, 0.0, 0.0};
     __syncthreads();
@@ -374,12 +448,9 @@ __global__ void __launch_bounds__(HV_BLOCK) hist_var_fast(const HistArgs<float> 
     }
 }
 
-template <int VPL>
-static int hist_launch_fast(mcp_context* h, const HistArgs<float>& a, int max_blocks, int* blocks, cudaStream_t st, bool* done) {
-    *done = false;
-    const size_t smem = ((size_t)a.n * a.t_pad + (size_t)HV_WARPS * a.n * HF_PPW) * sizeof(float) + (size_t)HV_WARPS * HF_PPW * (VPL + 1) * 32 * sizeof(uint32_t);
-    if (a.t_pad != 32 * VPL || smem > h->prop.sharedMemPerBlockOptin) return MCP_OK;           // the plain kernel takes it
-    auto kern = hist_var_fast<VPL>;
+template <int VPL, int ROW>
+static int hist_launch_fast_row(mcp_context* h, const HistArgs<float>& a, size_t smem, int max_blocks, int* blocks, cudaStream_t st, bool* done) {
+    auto kern = hist_var_fast<VPL, ROW>;
     if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     MCP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HV_BLOCK, smem));
@@ -393,6 +464,19 @@ static int hist_launch_fast(mcp_context* h, const HistArgs<float>& a, int max_bl
     h->launches++;
     *done = true;
     return MCP_OK;
+}
+
+template <int VPL>
+static int hist_launch_fast(mcp_context* h, const HistArgs<float>& a, int max_blocks, int* blocks, cudaStream_t st, bool* done) {
+    *done = false;
+    const size_t smem = ((size_t)a.n * a.t_pad + (size_t)HV_WARPS * a.n * HF_PPW * 2 + (size_t)HV_WARPS * (VPL + 2 * HF_PAD) * 32) * sizeof(float);
+    if (a.t_pad != 32 * VPL || smem > h->prop.sharedMemPerBlockOptin) return MCP_OK;           // the plain kernel takes it
+    // first positions of the 32 lanes holding (in expectation) 7 / 16 of the smallest values: start next to k_lo + 1
+    int row = a.k_lo + 1 >= 12 ? 2 : a.k_lo + 1 >= 5 ? 1 : 0;
+    if (const char* env = getenv("MCP_HIST_ROW")) row = std::max(0, std::min(2, atoi(env)));     // A/B tests
+    if (row == 2) return hist_launch_fast_row<VPL, 2>(h, a, smem, max_blocks, blocks, st, done);
+    if (row == 1) return hist_launch_fast_row<VPL, 1>(h, a, smem, max_blocks, blocks, st, done);
+    return hist_launch_fast_row<VPL, 0>(h, a, smem, max_blocks, blocks, st, done);
 }
 
 template <typename T, int VPL>

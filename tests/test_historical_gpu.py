@@ -121,14 +121,16 @@ def test_asset_stats_kernel(mcp, c1, c2):
 @pytest.mark.parametrize("T", [33, 100, 200, 365, 384, 500])
 @pytest.mark.parametrize("alpha", [0.95, 0.99])
 def test_fast_fp32_kernel_is_bit_identical_to_the_plain_one(mcp, T, alpha):
-    """hist_var_fast (4 portfolios per warp, sorting network, REDUX pop-min) against hist_var_kernel<float>
-    (MCP_HIST_FAST=0) on the same inputs, and both against the FP64 oracle; ties included."""
+    """hist_var_fast (4 portfolios per warp, sorting network, one threshold reduction + a few warp-min pops / warp-max
+    removals) against hist_var_kernel<float> (MCP_HIST_FAST=0) on the same inputs, and both against the FP64 oracle; ties
+    included.  MCP_HIST_ROW forces the threshold row (0: pops only), so both directions of the finish run at every rank."""
     import os
     rng = np.random.default_rng(T)
     n, P = 16, 1003                                        # P % 4 != 0: the last group is partial
     R = np.round(rng.standard_normal((T, n)) * 0.04, 3)    # rounded returns: repeated series values (ties at the rank)
     W = rng.dirichlet(np.ones(n), size=P)
     W[5] = 0; W[5, 2] = 1.0                                # a one-asset portfolio: the series IS a (tied) column of R
+    W[6] = 0                                               # an all-zero row: every series value ties
     fast = mcp.historical_var_cvar(R, W, alpha, dtype="float32")
     os.environ["MCP_HIST_FAST"] = "0"
     try:
@@ -137,6 +139,34 @@ def test_fast_fp32_kernel_is_bit_identical_to_the_plain_one(mcp, T, alpha):
         del os.environ["MCP_HIST_FAST"]
     assert np.array_equal(fast["var"], plain["var"]) and np.array_equal(fast["cvar"], plain["cvar"])
     assert fast["best_var"] == plain["best_var"] and fast["best_cvar"] == plain["best_cvar"]
+    for row in ("0", "1", "2"):
+        os.environ["MCP_HIST_ROW"] = row
+        try:
+            forced = mcp.historical_var_cvar(R, W, alpha, dtype="float32")
+        finally:
+            del os.environ["MCP_HIST_ROW"]
+        assert np.array_equal(forced["var"], plain["var"]) and np.array_equal(forced["cvar"], plain["cvar"]), row
+        assert forced["best_var"] == plain["best_var"] and forced["best_cvar"] == plain["best_cvar"], row
     v, c = ref.historical_var_cvar(R, W, alpha)
     assert np.allclose(fast["var"], v, rtol=1e-4, atol=1e-7) and np.allclose(fast["cvar"], c, rtol=1e-4, atol=1e-7)
     assert fast["best_var"]["index"] == int(np.argmax(fast["var"])) and fast["best_cvar"]["index"] == int(np.argmax(fast["cvar"]))
+
+
+def test_fast_fp32_kernel_continuous_returns_many_groups(mcp):
+    """Unrounded returns (no ties), enough portfolios for every warp to loop: the fast and the plain kernel agree bit for bit
+    and sit within FP32 rounding of the FP64 oracle."""
+    import os
+    rng = np.random.default_rng(11)
+    T, n, P = 365, 16, 300_001
+    R = rng.standard_t(4, size=(T, n)) * 0.03              # heavy tails, as weekly crypto returns have
+    W = rng.dirichlet(np.ones(n), size=P)
+    fast = mcp.historical_var_cvar(R, W, 0.95, dtype="float32")
+    os.environ["MCP_HIST_FAST"] = "0"
+    try:
+        plain = mcp.historical_var_cvar(R, W, 0.95, dtype="float32")
+    finally:
+        del os.environ["MCP_HIST_FAST"]
+    assert np.array_equal(fast["var"], plain["var"]) and np.array_equal(fast["cvar"], plain["cvar"])
+    assert fast["best_var"] == plain["best_var"] and fast["best_cvar"] == plain["best_cvar"]
+    v, c = ref.historical_var_cvar(R[:, :], W[:20000], 0.95)
+    assert np.allclose(fast["var"][:20000], v, rtol=1e-4, atol=1e-7) and np.allclose(fast["cvar"][:20000], c, rtol=1e-4, atol=1e-7)

@@ -12,11 +12,15 @@ rng = np.random.default_rng(0)
 T, n, P = 365, 16, 4_000_000
 R = rng.standard_normal((T, n)) * 0.04
 W = torch.from_numpy(rng.dirichlet(np.ones(n), size=P).astype(np.float32)).cuda()
-for tag, env in (("fast", None), ("plain", "0")):
+for tag, env, row in (("fast", None, None), ("fast row=0", None, "0"), ("fast row=1", None, "1"), ("fast row=2", None, "2"), ("plain", "0", None)):
     if env is None:
         os.environ.pop("MCP_HIST_FAST", None)
     else:
         os.environ["MCP_HIST_FAST"] = env
+    if row is None:
+        os.environ.pop("MCP_HIST_ROW", None)
+    else:
+        os.environ["MCP_HIST_ROW"] = row
     for alpha in (0.95, 0.99):
         for _ in range(3):
             out = mcp.historical_var_cvar(R, W, alpha, dtype="float32")
