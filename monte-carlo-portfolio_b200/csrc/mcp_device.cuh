@@ -195,6 +195,13 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
     return *reinterpret_cast<float2*>(&rd);
 }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+    unsigned long long rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
 __device__ __forceinline__ float2 bcast2(float x) { return make_float2(x, x); }
 
 // ---- (key, index) argmax with first-occurrence tie-break ---------------------------------

@@ -265,8 +265,8 @@ template <int VPL> __device__ __forceinline__ void lane_sort(float (&y)[VPL]) {
 #undef MCP_CE
 }
 
-template <int VPL, int ROW>
-__global__ void __launch_bounds__(HV_BLOCK, 2) hist_var_fast(const HistArgs<float> a) {
+template <int VPL, int ROW, int MINB>
+__global__ void __launch_bounds__(HV_BLOCK, MINB) hist_var_fast(const HistArgs<float> a) {
     static_assert(VPL % 2 == 0 && ROW < VPL, "period pairs");
     constexpr int VP2 = VPL / 2, KSTRIDE = VPL + 2 * HF_PAD;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -296,25 +296,27 @@ __global__ void __launch_bounds__(HV_BLOCK, 2) hist_var_fast(const HistArgs<floa
     // the four weight rows of a group are 4 n contiguous floats; with 4 n <= 64 (n <= 16) a lane holds the NEXT group's
     // values in two registers while the current group is being processed (the global-load latency sat in front of the STS)
     const bool prefetch = HF_PPW * a.n <= 64;
-    const int j0 = lane, j1 = lane + 32;
+    const int j0 = lane, j1 = lane + 32, gsz = HF_PPW * a.n;
     const int o0 = ((j0 % a.n) * HF_PPW + j0 / a.n) * 2, o1 = ((j1 % a.n) * HF_PPW + j1 / a.n) * 2;
-    float nxt0 = 0.f, nxt1 = 0.f;
-    auto fetch = [&](uint64_t g, int j) -> float {
-        const uint64_t q0 = g * HF_PPW;
-        return (g < groups && j < HF_PPW * a.n && q0 + (uint64_t)(j / a.n) < a.P) ? __ldg(a.w_in + q0 * (uint64_t)a.n + (uint64_t)j) : 0.f;
-    };
     const uint64_t g_first = (uint64_t)blockIdx.x * HV_WARPS + warp;
-    if (prefetch) { nxt0 = fetch(g_first, j0); nxt1 = fetch(g_first, j1); }
+    const uint64_t w_total = a.P * (uint64_t)a.n, w_step = warps_total * (uint64_t)gsz;      // elements of w_in, per sweep of the grid
+    uint64_t e0 = g_first * (uint64_t)gsz + (uint64_t)j0;                                      // this lane's element of the NEXT group
+    float nxt0 = 0.f, nxt1 = 0.f;
+    if (prefetch) {
+        nxt0 = (j0 < gsz && e0 < w_total) ? __ldg(a.w_in + e0) : 0.f;
+        nxt1 = (j1 < gsz && e0 + 32 < w_total) ? __ldg(a.w_in + e0 + 32) : 0.f;
+    }
     for (uint64_t gq = g_first; gq < groups; gq += warps_total) {
         const uint64_t p0 = gq * HF_PPW;
         __syncwarp();
         if (prefetch) {
-            if (j0 < HF_PPW * a.n) *reinterpret_cast<float2*>(myW + o0) = make_float2(nxt0, nxt0);
-            if (j1 < HF_PPW * a.n) *reinterpret_cast<float2*>(myW + o1) = make_float2(nxt1, nxt1);
-            nxt0 = fetch(gq + warps_total, j0);
-            nxt1 = fetch(gq + warps_total, j1);
+            if (j0 < gsz) *reinterpret_cast<float2*>(myW + o0) = make_float2(nxt0, nxt0);
+            if (j1 < gsz) *reinterpret_cast<float2*>(myW + o1) = make_float2(nxt1, nxt1);
+            e0 += w_step;                                   // rows past P read as 0 (a partial last group, the tail of the grid)
+            nxt0 = (j0 < gsz && e0 < w_total) ? __ldg(a.w_in + e0) : 0.f;
+            nxt1 = (j1 < gsz && e0 + 32 < w_total) ? __ldg(a.w_in + e0 + 32) : 0.f;
         } else {
-            for (int j = lane; j < HF_PPW * a.n; j += 32) {               // rows p0 .. p0+3 are contiguous: coalesced
+            for (int j = lane; j < gsz; j += 32) {                        // rows p0 .. p0+3 are contiguous: coalesced
                 const int pp = j / a.n, i = j - pp * a.n;
                 const float w = (p0 + (uint64_t)pp < a.P) ? a.w_in[p0 * (uint64_t)a.n + (uint64_t)j] : 0.f;
                 *reinterpret_cast<float2*>(myW + (i * HF_PPW + pp) * 2) = make_float2(w, w);
@@ -323,26 +325,40 @@ __global__ void __launch_bounds__(HV_BLOCK, 2) hist_var_fast(const HistArgs<floa
         __syncwarp();
         // ---- series[t] = sum_i R[t, i] w_i: this lane's periods in pairs (l + 64 j, l + 64 j + 32), four portfolios ----
         float2 x[HF_PPW][VP2];
+        {
+            const float2* row = reinterpret_cast<const float2*>(sR) + lane;
+            const float4* wq = reinterpret_cast<const float4*>(myW);
+            const int row_step = a.t_pad >> 1;
+            {   // asset 0: fma(r, w, 0) = r w
+                const float4 wa = wq[0], wb = wq[1];                    // (w0, w0, w1, w1), (w2, w2, w3, w3)
+                const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w), w2 = make_float2(wb.x, wb.y), w3 = make_float2(wb.z, wb.w);
 #pragma unroll
-        for (int pp = 0; pp < HF_PPW; ++pp)
+                for (int j = 0; j < VP2; ++j) {
+                    const float2 r2 = row[32 * j];                      // padded periods are 0
+                    x[0][j] = mul2(r2, w0);
+                    x[1][j] = mul2(r2, w1);
+                    x[2][j] = mul2(r2, w2);
+                    x[3][j] = mul2(r2, w3);
+                }
+            }
+#pragma unroll 1
+            for (int i = 1; i < a.n; ++i) {
+                row += row_step;
+                wq += 2;
+                const float4 wa = wq[0], wb = wq[1];
+                const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w), w2 = make_float2(wb.x, wb.y), w3 = make_float2(wb.z, wb.w);
 #pragma unroll
-            for (int j = 0; j < VP2; ++j) x[pp][j] = make_float2(0.f, 0.f);
-#pragma unroll 2
-        for (int i = 0; i < a.n; ++i) {
-            const float4 wa = *reinterpret_cast<const float4*>(myW + i * HF_PPW * 2);          // (w0, w0, w1, w1)
-            const float4 wb = *reinterpret_cast<const float4*>(myW + i * HF_PPW * 2 + 4);      // (w2, w2, w3, w3)
-            const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w), w2 = make_float2(wb.x, wb.y), w3 = make_float2(wb.z, wb.w);
-            const float2* row = reinterpret_cast<const float2*>(sR + (size_t)i * a.t_pad) + lane;
-#pragma unroll
-            for (int j = 0; j < VP2; ++j) {
-                const float2 r2 = row[32 * j];                          // padded periods are 0
-                x[0][j] = fma2(r2, w0, x[0][j]);
-                x[1][j] = fma2(r2, w1, x[1][j]);
-                x[2][j] = fma2(r2, w2, x[2][j]);
-                x[3][j] = fma2(r2, w3, x[3][j]);
+                for (int j = 0; j < VP2; ++j) {
+                    const float2 r2 = row[32 * j];
+                    x[0][j] = fma2(r2, w0, x[0][j]);
+                    x[1][j] = fma2(r2, w1, x[1][j]);
+                    x[2][j] = fma2(r2, w2, x[2][j]);
+                    x[3][j] = fma2(r2, w3, x[3][j]);
+                }
             }
         }
-        float var4[HF_PPW], cvar4[HF_PPW];
+        float var4[HF_PPW], acc4[HF_PPW];
+        int total4[HF_PPW];
 #pragma unroll
         for (int pp = 0; pp < HF_PPW; ++pp) {
             // ---- sort the lane's values (padding = +inf sorts last) and park them between the sentinels ----
@@ -418,8 +434,12 @@ __global__ void __launch_bounds__(HV_BLOCK, 2) hist_var_fast(const HistArgs<floa
                 peek = redux_min_f32(h);
             }
             var4[pp] = var;
-            cvar4[pp] = warp_sum<float>(acc) / (float)total;
+            acc4[pp] = acc;
+            total4[pp] = total;
         }
+        float cvar4[HF_PPW];
+#pragma unroll
+        for (int pp = 0; pp < HF_PPW; ++pp) cvar4[pp] = warp_sum<float>(acc4[pp]) / (float)total4[pp];      // four independent butterflies
         // ---- lane pp writes and follows portfolio pp ----
         const float my_var = lane == 0 ? var4[0] : lane == 1 ? var4[1] : lane == 2 ? var4[2] : var4[3];
         const float my_cvar = lane == 0 ? cvar4[0] : lane == 1 ? cvar4[1] : lane == 2 ? cvar4[2] : cvar4[3];
@@ -448,9 +468,9 @@ __global__ void __launch_bounds__(HV_BLOCK, 2) hist_var_fast(const HistArgs<floa
     }
 }
 
-template <int VPL, int ROW>
-static int hist_launch_fast_row(mcp_context* h, const HistArgs<float>& a, size_t smem, int max_blocks, int* blocks, cudaStream_t st, bool* done) {
-    auto kern = hist_var_fast<VPL, ROW>;
+template <int VPL, int ROW, int MINB>
+static int hist_launch_fast_occ(mcp_context* h, const HistArgs<float>& a, size_t smem, int max_blocks, int* blocks, cudaStream_t st, bool* done) {
+    auto kern = hist_var_fast<VPL, ROW, MINB>;
     if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     MCP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HV_BLOCK, smem));
@@ -464,6 +484,13 @@ static int hist_launch_fast_row(mcp_context* h, const HistArgs<float>& a, size_t
     h->launches++;
     *done = true;
     return MCP_OK;
+}
+
+template <int VPL, int ROW>
+static int hist_launch_fast_row(mcp_context* h, const HistArgs<float>& a, size_t smem, int max_blocks, int* blocks, cudaStream_t st, bool* done) {
+    const char* env = getenv("MCP_HIST_OCC");                     // A/B tests: resident blocks per SM the kernel is compiled for
+    if (env && env[0] == '2') return hist_launch_fast_occ<VPL, ROW, 2>(h, a, smem, max_blocks, blocks, st, done);
+    return hist_launch_fast_occ<VPL, ROW, 3>(h, a, smem, max_blocks, blocks, st, done);
 }
 
 template <int VPL>

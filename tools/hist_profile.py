@@ -12,7 +12,10 @@ rng = np.random.default_rng(0)
 T, n, P = 365, 16, 4_000_000
 R = rng.standard_normal((T, n)) * 0.04
 W = torch.from_numpy(rng.dirichlet(np.ones(n), size=P).astype(np.float32)).cuda()
-for tag, env, row in (("fast", None, None), ("fast row=0", None, "0"), ("fast row=1", None, "1"), ("fast row=2", None, "2"), ("plain", "0", None)):
+CASES = [("fast", None, None), ("fast row=0", None, "0"), ("fast row=1", None, "1"), ("fast row=2", None, "2"), ("plain", "0", None)]
+if os.environ.get("HIST_PROFILE_ONLY_FAST"):
+    CASES = CASES[:1]
+for tag, env, row in CASES:
     if env is None:
         os.environ.pop("MCP_HIST_FAST", None)
     else:
