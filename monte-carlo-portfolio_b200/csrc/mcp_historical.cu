@@ -27,6 +27,7 @@ namespace mcp {
 constexpr int HV_BLOCK = 256;
 constexpr int HV_WARPS = HV_BLOCK / 32;
 constexpr int HV_EXTRACT_MAX = 40;        // ranks below this are found by repeated warp-min extraction
+constexpr int HV_SHRINK = 68;             // set sizes 0 .. 64 (two positions of 32 lanes)
 
 template <typename K> __device__ __forceinline__ K shfl_xor_key(K v, int m);
 template <> __device__ __forceinline__ uint32_t shfl_xor_key<uint32_t>(uint32_t v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
@@ -58,6 +59,7 @@ struct HistArgs {
     int k_lo, k_hi;         // 0-based order statistics
     T gamma;                // interpolation weight
     T out_sign;             // +1, or -1 when the arrays hold the app's metric -var / -cvar (app.py:717); picks use the unsigned values
+    float shrink[HV_SHRINK]; // hist_var_fast: where between its two thresholds the refined one goes, by the size of the first set
 };
 
 template <typename T> __device__ __forceinline__ T warp_sum(T v) {
@@ -265,15 +267,15 @@ template <int VPL> __device__ __forceinline__ void lane_sort(float (&y)[VPL]) {
 #undef MCP_CE
 }
 
-template <int VPL, int ROW, int MINB>
-__global__ void __launch_bounds__(HV_BLOCK, MINB) hist_var_fast(const HistArgs<float> a) {
+template <int VPL, int ROW, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) hist_var_fast(const HistArgs<float> a) {
     static_assert(VPL % 2 == 0 && ROW < VPL, "period pairs");
-    constexpr int VP2 = VPL / 2, KSTRIDE = VPL + 2 * HF_PAD;
+    constexpr int VP2 = VPL / 2, KSTRIDE = VPL + 2 * HF_PAD, WARPS = BLOCK / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* sR = reinterpret_cast<float*>(smem_raw);                                 // [n][VP2][32][2], t_pad = 32 VPL
-    float* sW = sR + (size_t)a.n * a.t_pad;                                         // [HV_WARPS][n][4][2]
-    float* sK = sW + (size_t)HV_WARPS * a.n * HF_PPW * 2;                           // [HV_WARPS][KSTRIDE][32]
-    for (int d = threadIdx.x; d < a.n * a.t_pad; d += HV_BLOCK) {
+    float* sW = sR + (size_t)a.n * a.t_pad;                                         // [WARPS][n][4][2]
+    float* sK = sW + (size_t)WARPS * a.n * HF_PPW * 2;                           // [WARPS][KSTRIDE][32]
+    for (int d = threadIdx.x; d < a.n * a.t_pad; d += BLOCK) {
         const int i = d / a.t_pad, rem = d - i * a.t_pad, j = rem >> 6, l = (rem & 63) >> 1, half = rem & 1;
         sR[d] = a.r_t[i * a.t_pad + l + 64 * j + 32 * half];
     }
@@ -288,9 +290,9 @@ __global__ void __launch_bounds__(HV_BLOCK, MINB) hist_var_fast(const HistArgs<f
     __syncthreads();
 
     float best_v = -inf, best_c = -inf;                     // lane pp < 4 follows portfolio pp of every group
-    uint64_t idx_v = MCP_NO_INDEX, idx_c = MCP_NO_INDEX;
+    uint32_t it_v = 0xffffffffu, it_c = 0xffffffffu, it = 0;   // the warp's sweep number of the best group (a 64-bit index costs two more registers each)
     const uint64_t groups = (a.P + HF_PPW - 1) / HF_PPW;
-    const uint64_t warps_total = (uint64_t)gridDim.x * HV_WARPS;
+    const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
     const bool last_only = a.T_ > 32 * (VPL - 1);           // only a lane's last period can be padding
     const bool last_valid = lane + 32 * (VPL - 1) < a.T_;
     // the four weight rows of a group are 4 n contiguous floats; with 4 n <= 64 (n <= 16) a lane holds the NEXT group's
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(HV_BLOCK, MINB) hist_var_fast(const HistArgs<f
     const bool prefetch = HF_PPW * a.n <= 64;
     const int j0 = lane, j1 = lane + 32, gsz = HF_PPW * a.n;
     const int o0 = ((j0 % a.n) * HF_PPW + j0 / a.n) * 2, o1 = ((j1 % a.n) * HF_PPW + j1 / a.n) * 2;
-    const uint64_t g_first = (uint64_t)blockIdx.x * HV_WARPS + warp;
+    const uint64_t g_first = (uint64_t)blockIdx.x * WARPS + warp;
     const uint64_t w_total = a.P * (uint64_t)a.n, w_step = warps_total * (uint64_t)gsz;      // elements of w_in, per sweep of the grid
     uint64_t e0 = g_first * (uint64_t)gsz + (uint64_t)j0;                                      // this lane's element of the NEXT group
     float nxt0 = 0.f, nxt1 = 0.f;
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(HV_BLOCK, MINB) hist_var_fast(const HistArgs<f
         nxt0 = (j0 < gsz && e0 < w_total) ? __ldg(a.w_in + e0) : 0.f;
         nxt1 = (j1 < gsz && e0 + 32 < w_total) ? __ldg(a.w_in + e0 + 32) : 0.f;
     }
-    for (uint64_t gq = g_first; gq < groups; gq += warps_total) {
+    for (uint64_t gq = g_first; gq < groups; gq += warps_total, ++it) {
         const uint64_t p0 = gq * HF_PPW;
         __syncwarp();
         if (prefetch) {
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(HV_BLOCK, MINB) hist_var_fast(const HistArgs<f
                 }
             }
 #pragma unroll 1
-            for (int i = 1; i < a.n; ++i) {
+            for (int i = 1; i < a.n; ++i) {                            // (unrolled, ptxas hoists the next assets' loads and spills)
                 row += row_step;
                 wq += 2;
                 const float4 wa = wq[0], wb = wq[1];
@@ -382,6 +384,19 @@ __global__ void __launch_bounds__(HV_BLOCK, MINB) hist_var_fast(const HistArgs<f
 #pragma unroll
                 for (int v = 0; v < ROW; ++v) cnt += y[v] <= tau ? 1 : 0;       // a prefix: y ascends
                 c = __reduce_add_sync(0xffffffffu, cnt);
+                if (c > a.k_lo + 1) {
+                    // S is too big (the size of S has a wide spread: tau is an extreme value).  ONE refined threshold, interpolated
+                    // between the minimum of the lanes' ROW-th values and tau by the sizes the two sets typically have, lands
+                    // within 2-3 values of the rank; any theta <= tau gives a valid set, the nearer of the two sets is kept.
+                    const float tau_l = redux_min_f32(y[ROW - 1]);
+                    const float theta = fminf(fmaf(tau - tau_l, a.shrink[c], tau_l), tau);
+                    int cnt2 = 0;
+#pragma unroll
+                    for (int v = 0; v < ROW; ++v) cnt2 += y[v] <= theta ? 1 : 0;
+                    const int c2 = __reduce_add_sync(0xffffffffu, cnt2);
+                    const int d2 = c2 > a.k_lo + 1 ? c2 - (a.k_lo + 1) : a.k_lo + 1 - c2;
+                    if (d2 < c - (a.k_lo + 1)) { cnt = cnt2; c = c2; }
+                }
             }
             float acc = 0.f, v_lo, h;
             const float* nx;                                // the parked value after h
@@ -393,24 +408,23 @@ __global__ void __launch_bounds__(HV_BLOCK, MINB) hist_var_fast(const HistArgs<f
 #pragma unroll
                 for (int v = 1; v <= ROW; ++v) h = cnt >= v ? y[v] : h;
                 nx = myK + (HF_PAD + 1 + cnt) * 32;
-                float nxt = *nx;
                 float m = 0.f;
 #pragma unroll 1
                 for (int need = a.k_lo + 1 - c; need > 0; --need) {
                     m = redux_min_f32(h);
                     const unsigned owners = __ballot_sync(0xffffffffu, h == m);
-                    if (h == m && (owners & lt_mask) == 0u) { acc += h; h = nxt; nx += 32; nxt = *nx; }
+                    if (h == m && (owners & lt_mask) == 0u) { acc += h; h = *nx; nx += 32; }
                 }
                 v_lo = m;
             } else {
                 // removals from above: S loses its largest values until k_lo + 1 are left
                 const float* pv = myK + (HF_PAD - 1 + cnt) * 32;      // top of this lane's part of S (-inf: none)
-                float top = *pv, prv = pv[-32];
+                float top = *pv;
 #pragma unroll 1
                 for (int rem = c - a.k_lo - 1; rem > 0; --rem) {
                     const float M = redux_max_f32(top);
                     const unsigned owners = __ballot_sync(0xffffffffu, top == M);
-                    if (top == M && (owners & lt_mask) == 0u) { --cnt; top = prv; pv -= 32; prv = pv[-32]; }
+                    if (top == M && (owners & lt_mask) == 0u) { --cnt; pv -= 32; top = *pv; }
                 }
                 v_lo = redux_max_f32(top);
 #pragma unroll
@@ -447,19 +461,20 @@ __global__ void __launch_bounds__(HV_BLOCK, MINB) hist_var_fast(const HistArgs<f
         if (lane < HF_PPW && p < a.P) {
             if (a.var_out) a.var_out[p] = a.out_sign * my_var;
             if (a.cvar_out) a.cvar_out[p] = a.out_sign * my_cvar;
-            const uint64_t g = a.first + p;
-            if (my_var > best_v) { best_v = my_var; idx_v = g; }          // p ascends per lane: first occurrence kept
-            if (my_cvar > best_c) { best_c = my_cvar; idx_c = g; }
+            if (my_var > best_v) { best_v = my_var; it_v = it; }          // p ascends per lane: first occurrence kept
+            if (my_cvar > best_c) { best_c = my_cvar; it_c = it; }
         }
     }
+    uint64_t idx_v = it_v == 0xffffffffu ? MCP_NO_INDEX : a.first + (g_first + (uint64_t)it_v * warps_total) * HF_PPW + (uint64_t)lane;
+    uint64_t idx_c = it_c == 0xffffffffu ? MCP_NO_INDEX : a.first + (g_first + (uint64_t)it_c * warps_total) * HF_PPW + (uint64_t)lane;
     warp_argmax<float>(best_v, idx_v);                      // larger value, then lower index
     warp_argmax<float>(best_c, idx_c);
-    __shared__ PfCand wc[HV_WARPS];
+    __shared__ PfCand wc[WARPS];
     if (lane == 0) wc[warp] = PfCand{(double)best_v, idx_v, (double)best_c, idx_c, 0.0, 0.0};
     __syncthreads();
     if (threadIdx.x == 0) {
         PfCand b = wc[0];
-        for (int w = 1; w < HV_WARPS; ++w) {
+        for (int w = 1; w < WARPS; ++w) {
             const PfCand o = wc[w];
             if (cand_better<double>(o.key_s, o.idx_s, b.key_s, b.idx_s)) { b.key_s = o.key_s; b.idx_s = o.idx_s; }
             if (cand_better<double>(o.key_d, o.idx_d, b.key_d, b.idx_d)) { b.key_d = o.key_d; b.idx_d = o.idx_d; }
@@ -468,18 +483,25 @@ __global__ void __launch_bounds__(HV_BLOCK, MINB) hist_var_fast(const HistArgs<f
     }
 }
 
-template <int VPL, int ROW, int MINB>
-static int hist_launch_fast_occ(mcp_context* h, const HistArgs<float>& a, size_t smem, int max_blocks, int* blocks, cudaStream_t st, bool* done) {
-    auto kern = hist_var_fast<VPL, ROW, MINB>;
+constexpr size_t hist_fast_smem(int n, int t_pad, int vpl, int warps) {
+    return ((size_t)n * t_pad + (size_t)warps * n * HF_PPW * 2 + (size_t)warps * (vpl + 2 * HF_PAD) * 32) * sizeof(float);
+}
+
+template <int VPL, int ROW, int BLOCK, int MINB>
+static int hist_launch_fast_occ(mcp_context* h, const HistArgs<float>& a, int max_blocks, int* blocks, cudaStream_t st, bool* done) {
+    constexpr int WARPS = BLOCK / 32;
+    const size_t smem = hist_fast_smem(a.n, a.t_pad, VPL, WARPS);
+    if (smem > h->prop.sharedMemPerBlockOptin) return MCP_OK;                                   // the plain kernel takes it
+    auto kern = hist_var_fast<VPL, ROW, BLOCK, MINB>;
     if (smem > 40 * 1024) MCP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    MCP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HV_BLOCK, smem));
+    MCP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem));
     if (per_sm < 1) return MCP_OK;
     const uint64_t groups = (a.P + HF_PPW - 1) / HF_PPW;
-    uint64_t grid = std::min<uint64_t>((uint64_t)h->prop.multiProcessorCount * per_sm, (groups + HV_WARPS - 1) / HV_WARPS);
+    uint64_t grid = std::min<uint64_t>((uint64_t)h->prop.multiProcessorCount * per_sm, (groups + WARPS - 1) / WARPS);
     grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, max_blocks));
     *blocks = (int)grid;
-    kern<<<(unsigned)grid, HV_BLOCK, smem, st>>>(a);
+    kern<<<(unsigned)grid, BLOCK, smem, st>>>(a);
     MCP_CUDA(h, cudaGetLastError());
     h->launches++;
     *done = true;
@@ -487,23 +509,29 @@ static int hist_launch_fast_occ(mcp_context* h, const HistArgs<float>& a, size_t
 }
 
 template <int VPL, int ROW>
-static int hist_launch_fast_row(mcp_context* h, const HistArgs<float>& a, size_t smem, int max_blocks, int* blocks, cudaStream_t st, bool* done) {
-    const char* env = getenv("MCP_HIST_OCC");                     // A/B tests: resident blocks per SM the kernel is compiled for
-    if (env && env[0] == '2') return hist_launch_fast_occ<VPL, ROW, 2>(h, a, smem, max_blocks, blocks, st, done);
-    return hist_launch_fast_occ<VPL, ROW, 3>(h, a, smem, max_blocks, blocks, st, done);
+static int hist_launch_fast_row(mcp_context* h, const HistArgs<float>& a, int max_blocks, int* blocks, cudaStream_t st, bool* done) {
+    const char* env = getenv("MCP_HIST_OCC");                     // A/B tests: block size x resident blocks the kernel is compiled for
+    if (env && env[0] == '2') return hist_launch_fast_occ<VPL, ROW, 256, 2>(h, a, max_blocks, blocks, st, done);
+    if (env && env[0] == '4') return hist_launch_fast_occ<VPL, ROW, 320, 2>(h, a, max_blocks, blocks, st, done);
+    return hist_launch_fast_occ<VPL, ROW, 256, 3>(h, a, max_blocks, blocks, st, done);
 }
 
 template <int VPL>
 static int hist_launch_fast(mcp_context* h, const HistArgs<float>& a, int max_blocks, int* blocks, cudaStream_t st, bool* done) {
     *done = false;
-    const size_t smem = ((size_t)a.n * a.t_pad + (size_t)HV_WARPS * a.n * HF_PPW * 2 + (size_t)HV_WARPS * (VPL + 2 * HF_PAD) * 32) * sizeof(float);
-    if (a.t_pad != 32 * VPL || smem > h->prop.sharedMemPerBlockOptin) return MCP_OK;           // the plain kernel takes it
+    if (a.t_pad != 32 * VPL) return MCP_OK;                                                     // the plain kernel takes it
     // first positions of the 32 lanes holding (in expectation) 7 / 16 of the smallest values: start next to k_lo + 1
     int row = a.k_lo + 1 >= 12 ? 2 : a.k_lo + 1 >= 5 ? 1 : 0;
     if (const char* env = getenv("MCP_HIST_ROW")) row = std::max(0, std::min(2, atoi(env)));     // A/B tests
-    if (row == 2) return hist_launch_fast_row<VPL, 2>(h, a, smem, max_blocks, blocks, st, done);
-    if (row == 1) return hist_launch_fast_row<VPL, 1>(h, a, smem, max_blocks, blocks, st, done);
-    return hist_launch_fast_row<VPL, 0>(h, a, smem, max_blocks, blocks, st, done);
+    // refined threshold = tau_l + (tau - tau_l) shrink[|S|]: linear in the rank between the sizes the sets below tau_l (typically
+    // 1 / 7 values for row 1 / 2) and below tau (|S|) have; a heuristic only -- every threshold <= tau is exact
+    HistArgs<float> b = a;
+    const float need = (float)(a.k_lo + 1), c_l = row == 2 ? 7.f : 1.f;
+    for (int c = 0; c < HV_SHRINK; ++c) b.shrink[c] = (float)c > c_l ? std::min(1.f, std::max(0.f, (need - c_l) / ((float)c - c_l))) : 1.f;
+    if (getenv("MCP_HIST_REFINE") && getenv("MCP_HIST_REFINE")[0] == '0') for (float& f : b.shrink) f = 1.f;      // A/B tests: theta = tau
+    if (row == 2) return hist_launch_fast_row<VPL, 2>(h, b, max_blocks, blocks, st, done);
+    if (row == 1) return hist_launch_fast_row<VPL, 1>(h, b, max_blocks, blocks, st, done);
+    return hist_launch_fast_row<VPL, 0>(h, b, max_blocks, blocks, st, done);
 }
 
 template <typename T, int VPL>
