@@ -561,14 +561,14 @@ def run_ours(args):
                                  "(e2e through the public API: mu/Sigma estimated on the device, weights kept on the GPU between the sweep and "
                                  "the historical kernel, -cvar written by the kernel, one copy per array into pooled page-locked memory)",
                      "opt_idx": mo["opt_idx"],
-                     "kernel": {"name": "hist_var_fast<12> (4 portfolios per warp, FFMA2 series, sorting network + REDUX pop-min)", "portfolios_per_s": Ph / (hv["kernel_ms"] * 1e-3),
+                     "kernel": {"name": "hist_var_fast<12,ROW=2> (4 portfolios per warp, period-pair FFMA2 series, per-lane sorting network, one threshold reduction + interpolated refinement, a few CREDUX pops / removals)", "portfolios_per_s": Ph / (hv["kernel_ms"] * 1e-3),
                                 "kernel_ms": hv["kernel_ms"],
                                 "roofline": {"bound": "fp32-simt", "achieved": hflop, "unit": "TFLOP/s",
                                              "algorithmic_flop_per_portfolio": 2 * Th * n,
                                              "peak": fma_peak, "frac": hflop / fma_peak,
                                              "note": "R.w is T*N FMA per portfolio; the exact order-statistic selection (per-lane "
-                                                     "sort, REDUX / vote pops: no flops) and shared-memory loads are most of the "
-                                                     "instruction stream"}}}
+                                                     "sort on the ALU pipe, CREDUX / vote steps: no flops) and shared-memory loads are "
+                                                     "most of the instruction stream"}}}
         del Wd
 
     # ---- the app's own size: one rerun of tab 3 = 5 methods x 2500 portfolios (app.py:681-682) ----

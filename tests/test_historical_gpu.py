@@ -123,7 +123,8 @@ def test_asset_stats_kernel(mcp, c1, c2):
 def test_fast_fp32_kernel_is_bit_identical_to_the_plain_one(mcp, T, alpha):
     """hist_var_fast (4 portfolios per warp, sorting network, one threshold reduction + a few warp-min pops / warp-max
     removals) against hist_var_kernel<float> (MCP_HIST_FAST=0) on the same inputs, and both against the FP64 oracle; ties
-    included.  MCP_HIST_ROW forces the threshold row (0: pops only), so both directions of the finish run at every rank."""
+    included.  MCP_HIST_ROW forces the threshold row (0: pops only), so both directions of the finish run at every rank;
+    MCP_HIST_REFINE=0 skips the interpolated threshold, MCP_HIST_OCC picks the other compiled block shapes."""
     import os
     rng = np.random.default_rng(T)
     n, P = 16, 1003                                        # P % 4 != 0: the last group is partial
@@ -131,6 +132,9 @@ def test_fast_fp32_kernel_is_bit_identical_to_the_plain_one(mcp, T, alpha):
     W = rng.dirichlet(np.ones(n), size=P)
     W[5] = 0; W[5, 2] = 1.0                                # a one-asset portfolio: the series IS a (tied) column of R
     W[6] = 0                                               # an all-zero row: every series value ties
+    R[0::32, 3] = -0.3 - 0.01 * np.arange(len(R[0::32]))   # asset 3's worst periods all belong to lane 0 ...
+    W[7] = 0; W[7, 3] = 1.0                                # ... so this portfolio's whole tail sits in one lane
+    W[8] = 0; W[8, 3] = 0.7; W[8, 2] = 0.3
     fast = mcp.historical_var_cvar(R, W, alpha, dtype="float32")
     os.environ["MCP_HIST_FAST"] = "0"
     try:
@@ -139,14 +143,15 @@ def test_fast_fp32_kernel_is_bit_identical_to_the_plain_one(mcp, T, alpha):
         del os.environ["MCP_HIST_FAST"]
     assert np.array_equal(fast["var"], plain["var"]) and np.array_equal(fast["cvar"], plain["cvar"])
     assert fast["best_var"] == plain["best_var"] and fast["best_cvar"] == plain["best_cvar"]
-    for row in ("0", "1", "2"):
-        os.environ["MCP_HIST_ROW"] = row
+    for knob, value in (("MCP_HIST_ROW", "0"), ("MCP_HIST_ROW", "1"), ("MCP_HIST_ROW", "2"), ("MCP_HIST_REFINE", "0"),
+                        ("MCP_HIST_OCC", "2"), ("MCP_HIST_OCC", "3")):
+        os.environ[knob] = value
         try:
             forced = mcp.historical_var_cvar(R, W, alpha, dtype="float32")
         finally:
-            del os.environ["MCP_HIST_ROW"]
-        assert np.array_equal(forced["var"], plain["var"]) and np.array_equal(forced["cvar"], plain["cvar"]), row
-        assert forced["best_var"] == plain["best_var"] and forced["best_cvar"] == plain["best_cvar"], row
+            del os.environ[knob]
+        assert np.array_equal(forced["var"], plain["var"]) and np.array_equal(forced["cvar"], plain["cvar"]), (knob, value)
+        assert forced["best_var"] == plain["best_var"] and forced["best_cvar"] == plain["best_cvar"], (knob, value)
     v, c = ref.historical_var_cvar(R, W, alpha)
     assert np.allclose(fast["var"], v, rtol=1e-4, atol=1e-7) and np.allclose(fast["cvar"], c, rtol=1e-4, atol=1e-7)
     assert fast["best_var"]["index"] == int(np.argmax(fast["var"])) and fast["best_cvar"]["index"] == int(np.argmax(fast["cvar"]))
