@@ -175,3 +175,36 @@ def test_fast_fp32_kernel_continuous_returns_many_groups(mcp):
     assert fast["best_var"] == plain["best_var"] and fast["best_cvar"] == plain["best_cvar"]
     v, c = ref.historical_var_cvar(R[:, :], W[:20000], 0.95)
     assert np.allclose(fast["var"][:20000], v, rtol=1e-4, atol=1e-7) and np.allclose(fast["cvar"][:20000], c, rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("n", [1, 3, 7, 16, 17, 24, 40])
+def test_fast_fp32_kernel_shapes_fuzz(mcp, n):
+    """Seeded sweep over period counts, universe sizes (n > 16: the weights of a group no longer fit a lane's two prefetch
+    registers), ranks and portfolio counts: hist_var_fast == hist_var_kernel<float> bit for bit, both within FP32 rounding of
+    the FP64 oracle (app.py:258-263 on app.py:710's series)."""
+    import os
+    rng = np.random.default_rng(1000 + n)
+    for case in range(6):
+        T = int(rng.integers(97, 513))
+        P = int(rng.integers(1, 700))
+        alpha = float(rng.choice([0.9, 0.95, 0.975, 0.99, 0.999]))
+        hidx = (T - 1) * ((1 - alpha) * 100 / 100.0)
+        if hidx - np.floor(hidx) > 1 - 1e-6:               # gamma = 1 - 4e-15 is 1.0f in FP32: VaR's upper neighbour enters the tail mean
+            T += 1                                         # there, numpy's own FP64 lerp sits on the same knife edge (INTEGRATION.md)
+        R = rng.standard_t(3, size=(T, n)) * 0.03
+        if case % 2:
+            R = np.round(R, 2)                             # ties
+        W = rng.dirichlet(np.ones(n), size=P)
+        if case == 5:
+            W = -W                                         # short book: the tail is the other side of every series
+        fast = mcp.historical_var_cvar(R, W, alpha, dtype="float32")
+        os.environ["MCP_HIST_FAST"] = "0"
+        try:
+            plain = mcp.historical_var_cvar(R, W, alpha, dtype="float32")
+        finally:
+            del os.environ["MCP_HIST_FAST"]
+        tag = (n, T, P, alpha, case)
+        assert np.array_equal(fast["var"], plain["var"]) and np.array_equal(fast["cvar"], plain["cvar"]), tag
+        assert fast["best_var"] == plain["best_var"] and fast["best_cvar"] == plain["best_cvar"], tag
+        v, c = ref.historical_var_cvar(R, W, alpha)
+        assert np.allclose(fast["var"], v, rtol=1e-4, atol=2e-7) and np.allclose(fast["cvar"], c, rtol=1e-4, atol=2e-7), tag
