@@ -559,7 +559,8 @@ def run_ours(args):
                      "value": Ph / dt, "unit": "portfolios/s", "ms_per_step": dt * 1e3,
                      "workload": "simulate_method('CVaR'): 1e6 Philox portfolios, all arrays to host, T=365 x N=16 returns matrix "
                                  "(e2e through the public API: mu/Sigma estimated on the device, weights kept on the GPU between the sweep and "
-                                 "the historical kernel, -cvar written by the kernel, one copy per array into pooled page-locked memory)",
+                                 "the historical kernel, -cvar written by the kernel, one copy per array into pooled page-locked memory, the sweep's "
+                                 "arrays copied on a side stream while the historical kernel runs)",
                      "opt_idx": mo["opt_idx"],
                      "kernel": {"name": "hist_var_fast<12,ROW=2> (4 portfolios per warp, period-pair FFMA2 series, per-lane sorting network, one threshold reduction + interpolated refinement, a few CREDUX pops / removals)", "portfolios_per_s": Ph / (hv["kernel_ms"] * 1e-3),
                                 "kernel_ms": hv["kernel_ms"],

@@ -62,6 +62,14 @@ class Engine:
     def launch_count(self) -> int:
         return int(lib().mcp_launch_count(self._h))
 
+    def copy_stream(self):
+        """A (non-blocking) torch stream of this device for copies that overlap the engine's kernels."""
+        import torch
+        st = getattr(self, "_copy_stream", None)
+        if st is None:
+            st = self._copy_stream = torch.cuda.Stream(device=self.device)
+        return st
+
     def last_kernel_ms(self) -> float:
         return float(lib().mcp_last_kernel_ms(self._h))
 
@@ -861,14 +869,23 @@ def simulate_method(returns_matrix, method="Monte Carlo", n_portfolios=2500, *, 
                             seed=seed, dtype=dtype, device=device, return_arrays="device", weights=weights)
     if r.n_accepted == 0:
         raise ValueError("no portfolio satisfied the bounds (the reference raises at argmax of an empty array, app.py:747)")
-    hv = historical_var_cvar(R, r.weights, alpha, dtype=dtype, device=device, negate=True)
-    key, pick = ("var", "best_var") if method == "VaR" else ("cvar", "best_cvar")
     Pa = r.n_accepted
     host = {"weights": _result_empty((Pa, n), npdt), "returns": _result_empty((Pa,), npdt), "risks": _result_empty((Pa,), npdt),
             "metrics": _result_empty((Pa,), npdt)}
-    for name, src in (("weights", r.weights), ("returns", r.returns), ("risks", r.risks), ("metrics", hv[key])):
-        torch.from_numpy(host[name]).copy_(src, non_blocking=True)       # D2H into (pooled) page-locked memory: one DMA each
-    torch.cuda.current_stream(eng.device).synchronize()
+    # The sweep's arrays are final: their copies back (the weights are 16 of the 19 values per portfolio) leave on a side stream
+    # while the historical kernel runs on the same weights; only the metric follows the kernel.  One DMA each, into (pooled)
+    # page-locked memory.
+    main = torch.cuda.current_stream(eng.device)
+    side = eng.copy_stream()
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        for name, src in (("weights", r.weights), ("returns", r.returns), ("risks", r.risks)):
+            torch.from_numpy(host[name]).copy_(src, non_blocking=True)
+    hv = historical_var_cvar(R, r.weights, alpha, dtype=dtype, device=device, negate=True)
+    key, pick = ("var", "best_var") if method == "VaR" else ("cvar", "best_cvar")
+    torch.from_numpy(host["metrics"]).copy_(hv[key], non_blocking=True)
+    main.synchronize()
+    side.synchronize()
     opt = int(hv[pick]["index"])
     return {"risks": host["risks"], "returns": host["returns"], "weights": host["weights"], "metrics": host["metrics"],
             "opt_idx": opt, "opt_weights": np.asarray(host["weights"][opt], dtype=np.float64)}
