@@ -567,6 +567,8 @@ def run_ours(args):
                                 "roofline": {"bound": "fp32-simt", "achieved": hflop, "unit": "TFLOP/s",
                                              "algorithmic_flop_per_portfolio": 2 * Th * n,
                                              "peak": fma_peak, "frac": hflop / fma_peak,
+                                             "algorithmic_bytes_per_portfolio": 4 * n + 8,
+                                             "ncu": ncu_figures("hist_var_fast<12, 2, 320, 2>"),
                                              "note": "R.w is T*N FMA per portfolio; the exact order-statistic selection (per-lane "
                                                      "sort on the ALU pipe, CREDUX / vote steps: no flops) and shared-memory loads are "
                                                      "most of the instruction stream"}}}
