@@ -23,4 +23,8 @@ oracle.  What pins it instead:
   restates the north-star text with the reference's conventions
   (``app.py:258-263`` quantiles, ``app.py:253`` arithmetic compounding,
   ``app.py:709`` volatility).
+
+* ``oracle/hist_select_model.py`` is not a restatement of the reference but of the KERNEL: the lane-by-lane selection of
+  ``hist_var_fast`` in numpy, checked against a plain sort (``tests/test_hist_model_cpu.py``) so that the algorithm's set
+  logic is pinned on the CPU tier as well.
 """
